@@ -1,0 +1,132 @@
+/* sgp.h -- C-ABI of the B200-native projected-process (sparse GP) hot path.
+ *
+ * Drop-in boundary for ONE path of akopich/spark-gp (reference paths relative to
+ * /root/reference/src/main/scala/org/apache/spark/ml/):
+ *
+ *   commons/ProjectedGaussianProcessHelper.scala:20-36   getMatrixKmnKnmAndVectorKmny
+ *       G = sum_e K_mn^(e) K_mn^(e)^T  (m x m),  b = sum_e K_mn^(e) y_e  (m)
+ *   commons/ProjectedGaussianProcessHelper.scala:49-65   getMagicVector / assertSymPositiveDefinite
+ *   commons/GaussianProcessCommons.scala:118-126         GaussianProjectedProcessRawPredictor.predict
+ *
+ * The reference has NO FFI of its own (pure Scala on Breeze); these entry points are what a JNI shim
+ * replacing the body of `getMatrixKmnKnmAndVectorKmny` / `getMagicVector` would bind (INTEGRATION.md
+ * shows the Scala + JNI stub).  Plain pointers and sizes only; the caller owns every host array; the
+ * context owns device memory, streams, cuSOLVER/cuBLAS handles and the NCCL communicator.  Every call
+ * returns an int status (never throws, never aborts); sgp_last_error() gives the text.
+ *
+ * Threading: a context is bound to one CUDA device and may be used from any ONE thread at a time
+ * (Spark executor task threads: one context per task/partition, or lock around it).  No global
+ * mutable state.
+ */
+#ifndef SGP_H_
+#define SGP_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sgp_ctx sgp_ctx;
+
+/* status codes; the host shim maps them back to the reference's exceptions */
+enum {
+  SGP_OK = 0,
+  SGP_E_BADARG = 1,   /* IllegalArgumentException / require(...)                                  */
+  SGP_E_CUDA = 2,     /* CUDA / cuSOLVER / cuBLAS runtime failure                                 */
+  SGP_E_NOT_PD = 3,   /* NotPositiveDefiniteException   (PGPH:9-11, 62-65)                        */
+  SGP_E_NCCL = 4,
+  SGP_E_STATE = 5,    /* call order violated (e.g. accumulate before begin) ~ TrainingVectorsNotInitializedException */
+  SGP_E_SINGULAR = 6, /* MatrixSingularException (commons/util/logDetAndInv.scala:27-28), LU info > 0 */
+  SGP_E_NOMEM = 7
+};
+
+/* Flattened kernel DSL (the files under commons/kernel/).  A kernel is a sum of terms  sum_t scale_t * k_t:
+ *   SGP_TERM_ARD : k(a,b) = exp(-sum_k beta_k^2 (a_k-b_k)^2)      kernel/ARDRBFKernel.scala:43-46
+ *   SGP_TERM_RBF : k(a,b) = exp(-||a-b||^2 / (2 sigma^2))         kernel/RBFKernel.scala:66-76
+ *   SGP_TERM_EYE : identity kernel: contributes ZERO to any cross kernel (kernel/Kernel.scala:157),
+ *                  `scale` to the training-kernel diagonal (:151), to selfKernel (:161) and to
+ *                  whiteNoiseVar (:159).
+ * `scale` is the product of all ScalarTimesKernel factors above the leaf (kernel/ScalarTimesKernel.scala:20-28). */
+enum { SGP_TERM_ARD = 0, SGP_TERM_RBF = 1, SGP_TERM_EYE = 2 };
+
+typedef struct {
+  int32_t type;        /* SGP_TERM_*                                   */
+  int32_t reserved;
+  double scale;        /* C >= 0                                       */
+  double sigma;        /* RBF only                                     */
+  const double* beta;  /* ARD only: d inverse length-scales            */
+} sgp_kernel_term;
+
+typedef struct {
+  int32_t n_terms;
+  int32_t reserved;
+  const sgp_kernel_term* terms;
+} sgp_kernel_desc;
+
+/* Arithmetic modes of the statistics kernel.  All modes accumulate G and b in fp64. */
+enum {
+  SGP_PREC_F64 = 0,        /* default: fp32-accurate kernel elements (direct-form distances, full-precision expf),
+                              fp64 DMMA Gram.  Parity-grade (<= 1e-6 on mean/variance). */
+  SGP_PREC_F64_STRICT = 1  /* elements in fp64 as well (verification mode, ~1e-13 on G,b)               */
+};
+
+/* ---- context ------------------------------------------------------------------------------ */
+int sgp_ctx_create(sgp_ctx** out, int device);
+int sgp_ctx_destroy(sgp_ctx* ctx);
+const char* sgp_last_error(const sgp_ctx* ctx);   /* valid until the next call on ctx; ctx==NULL -> creation error */
+int sgp_set_precision(sgp_ctx* ctx, int mode);
+int sgp_version(void);
+
+/* ---- multi-GPU (one process / context per GPU; replaces PGPH:23 broadcast + PGPH:25-35 treeAggregate) */
+#define SGP_UNIQUE_ID_BYTES 128
+int sgp_comm_unique_id(void* out128);                                   /* rank 0, then ship the bytes to all ranks */
+int sgp_comm_init(sgp_ctx* ctx, const void* id128, int rank, int nranks);
+
+/* ---- the hot path:  PGPH:20-36 ------------------------------------------------------------- */
+/* Active set Z: m x d row-major fp64 (activeSet: Array[Vector]).  Resets G, b to zero. */
+int sgp_stats_begin(sgp_ctx* ctx, const sgp_kernel_desc* kernel, const double* Z, int32_t m, int32_t d);
+
+/* One shard / partition / expert group of points in HOST memory: X is n x d row-major (fp64, or fp32
+ * when x_is_f32 != 0), y is n fp64 labels.  Copies host->device in pipelined chunks and launches the
+ * fused K_mn + Gram kernel per chunk.  May be called any number of times between begin and finish. */
+int sgp_stats_accumulate(sgp_ctx* ctx, const void* X, int32_t x_is_f32, const double* y, int64_t n);
+
+/* Same, points already resident in device memory (the bench's `value` leg). */
+int sgp_stats_accumulate_device(sgp_ctx* ctx, const void* dX, int32_t x_is_f32, const double* dy, int64_t n);
+
+/* Sum over ranks (one ncclAllReduce of the packed [G;b], if a communicator exists), then copy out.
+ * G_out: m x m fp64 (symmetric, so row-/column-major are the same bytes), b_out: m.  Either may be NULL
+ * (statistics stay on the device for sgp_magic). */
+int sgp_stats_finish(sgp_ctx* ctx, double* G_out, double* b_out);
+
+/* Block until the context's stream is idle (timing hygiene for callers using the _device entry). */
+int sgp_sync(sgp_ctx* ctx);
+
+/* ---- the m x m tail:  PGPH:49-65 ------------------------------------------------------------ */
+/* Uses the kernel + active set of the last sgp_stats_begin and the device-resident G, b (after finish),
+ * or host G_in/b_in when non-NULL.  K_mm = trainingKernel (Eye terms on the diagonal),
+ * A = whiteNoiseVar*K_mm + G; SGP_E_NOT_PD if any eigenvalue of A < 0; magicVector = A \ b (LU);
+ * magicMatrix = whiteNoiseVar*inv(A) - inv(K_mm).  Outputs may be NULL (kept on device for predict). */
+int sgp_magic(sgp_ctx* ctx, const double* G_in, const double* b_in,
+              double* magic_vector /* m */, double* magic_matrix /* m x m */);
+
+/* ---- prediction:  GPC:121-125 for a block of test vectors ----------------------------------- */
+/* mean_t = k(x_t, Z) . magicVector ;  var_t = selfKernel + k(x_t,Z) magicMatrix k(x_t,Z)^T.
+ * X: n x d row-major fp64 host.  var_out may be NULL. */
+int sgp_predict(sgp_ctx* ctx, const double* X, int64_t n, double* mean_out, double* var_out);
+
+/* ---- introspection (tests / bench) ---------------------------------------------------------- */
+/* Number of kernels this library launched on ctx since creation. */
+int64_t sgp_launch_count(const sgp_ctx* ctx);
+/* Device time (ms, CUDA events on the context's stream) of the Gram kernel launches since the last
+ * sgp_stats_begin, and how many there were. */
+int sgp_gram_kernel_time(sgp_ctx* ctx, double* total_ms, int64_t* launches);
+/* Evaluate K(X_test, Z) (n x m row-major fp64 out) with the current kernel -- the `crossKernel`
+ * contract of kernel/Kernel.scala:69-74 (used by the golden-vector tests). */
+int sgp_cross_kernel(sgp_ctx* ctx, const double* X, int64_t n, double* K_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SGP_H_ */

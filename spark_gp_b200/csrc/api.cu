@@ -1,0 +1,419 @@
+// C-ABI entry points (include/sgp.h): context, multi-GPU plumbing, the statistics pipeline.
+#include "sgp_internal.h"
+
+#include <dlfcn.h>
+
+#include <cmath>
+#include <cstring>
+#include <new>
+
+namespace sgp {
+
+static thread_local std::string g_create_err;
+
+// NCCL is resolved lazily with dlopen instead of being a link-time dependency: a host process that also
+// loads PyTorch already carries torch's own libnccl.so.2, and two different NCCL builds under one soname
+// cannot coexist.  dlopen("libnccl.so.2") returns the copy that is already mapped, else the system one.
+struct NcclApi {
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  bool ok = false;
+};
+static NcclApi& nccl() {
+  static NcclApi api = [] {
+    NcclApi a;
+    void* h = dlopen("libnccl.so.2", RTLD_LAZY | RTLD_LOCAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_LAZY | RTLD_LOCAL);
+    if (!h) return a;
+    a.GetUniqueId = reinterpret_cast<decltype(a.GetUniqueId)>(dlsym(h, "ncclGetUniqueId"));
+    a.CommInitRank = reinterpret_cast<decltype(a.CommInitRank)>(dlsym(h, "ncclCommInitRank"));
+    a.AllReduce = reinterpret_cast<decltype(a.AllReduce)>(dlsym(h, "ncclAllReduce"));
+    a.CommDestroy = reinterpret_cast<decltype(a.CommDestroy)>(dlsym(h, "ncclCommDestroy"));
+    a.GetErrorString = reinterpret_cast<decltype(a.GetErrorString)>(dlsym(h, "ncclGetErrorString"));
+    a.ok = a.GetUniqueId && a.CommInitRank && a.AllReduce && a.CommDestroy && a.GetErrorString;
+    return a;
+  }();
+  return api;
+}
+
+int fail(Ctx* c, int code, const std::string& msg) {
+  if (c) c->err = msg; else g_create_err = msg;
+  return code;
+}
+
+static void free_active_set(Ctx* c) {
+  cudaFree(c->dZ); cudaFree(c->dZs); cudaFree(c->dBeta); cudaFree(c->dGb);
+  cudaFree(c->dMagicVec); cudaFree(c->dMagicMat);
+  c->dZ = c->dZs = c->dBeta = c->dGb = c->dMagicVec = c->dMagicMat = nullptr;
+}
+
+static int ensure_partials(Ctx* c, int n_slices) {
+  const size_t gb = static_cast<size_t>(n_slices) * c->m_pad * c->m_pad * sizeof(double);
+  const size_t bb = static_cast<size_t>(n_slices) * c->m_pad * sizeof(double);
+  if (gb > c->gpart_bytes) {
+    cudaFree(c->dGpart); c->dGpart = nullptr; c->gpart_bytes = 0;
+    SGP_CUDA(c, cudaMalloc(&c->dGpart, gb));
+    c->gpart_bytes = gb;
+  }
+  if (bb > c->bpart_bytes) {
+    cudaFree(c->dBpart); c->dBpart = nullptr; c->bpart_bytes = 0;
+    SGP_CUDA(c, cudaMalloc(&c->dBpart, bb));
+    c->bpart_bytes = bb;
+  }
+  return SGP_OK;
+}
+
+// One fused-kernel launch over n device-resident points + the deterministic slice reduction.
+static int launch_stats(Ctx* c, const void* dX, int x_is_f32, const double* dy, long long n) {
+  if (n <= 0) return SGP_OK;
+  const int nt1 = c->m_pad / kTile;
+  const int ntiles = nt1 * (nt1 + 1) / 2;
+  int n_slices = c->num_sms / ntiles;            // fill the SMs: tiles x point-slices
+  if (n_slices < 1) n_slices = 1;
+  const long long blocks = (n + 15) / 16;
+  if (n_slices > blocks) n_slices = static_cast<int>(blocks);
+  int rc = ensure_partials(c, n_slices);
+  if (rc != SGP_OK) return rc;
+
+  GramParams p{};
+  p.X = dX; p.y = dy; p.n = n; p.x_is_f32 = x_is_f32;
+  p.d = c->d; p.dpad = c->dpad; p.m = c->m; p.m_pad = c->m_pad;
+  p.n_terms = c->kf.n_terms;
+  for (int t = 0; t < kMaxTerms; ++t) p.scale[t] = c->kf.scale[t];
+  p.Zs = c->dZs; p.beta = c->dBeta;
+  p.Gpart = c->dGpart; p.bpart = c->dBpart;
+  p.n_slices = n_slices; p.n_tiles_1d = nt1;
+
+  cudaEvent_t e0, e1;
+  SGP_CUDA(c, cudaEventCreate(&e0));
+  SGP_CUDA(c, cudaEventCreate(&e1));
+  SGP_CUDA(c, cudaEventRecord(e0, c->stream));
+  SGP_CUDA(c, launch_gram_f64(p, c->precision == SGP_PREC_F64_STRICT, c->stream));
+  SGP_CUDA(c, cudaEventRecord(e1, c->stream));
+  c->gram_events.emplace_back(e0, e1);
+  const size_t mm = static_cast<size_t>(c->m) * c->m;
+  SGP_CUDA(c, launch_gram_reduce(c->dGb, c->dGb + mm, c->dGpart, c->dBpart, n_slices, c->m, c->m_pad, c->stream));
+  c->launches += 2;
+  return SGP_OK;
+}
+
+static void drop_gram_events(Ctx* c) {
+  for (auto& e : c->gram_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+  c->gram_events.clear();
+}
+
+}  // namespace sgp
+
+using namespace sgp;
+
+extern "C" {
+
+int sgp_version(void) { return 100; }
+
+int sgp_ctx_create(sgp_ctx** out, int device) {
+  if (!out) return fail(nullptr, SGP_E_BADARG, "out == NULL");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(nullptr, SGP_E_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e) +
+                                         " (this library has no CPU fallback)");
+  if (device < 0 || device >= ndev) return fail(nullptr, SGP_E_BADARG, "device index out of range");
+  Ctx* c = new (std::nothrow) Ctx();
+  if (!c) return fail(nullptr, SGP_E_NOMEM, "out of host memory");
+  c->device = device;
+  auto bail = [&](int code, const std::string& m) { std::string mm = m; delete c; return fail(nullptr, code, mm); };
+  if ((e = cudaSetDevice(device)) != cudaSuccess) return bail(SGP_E_CUDA, cudaGetErrorString(e));
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return bail(SGP_E_CUDA, cudaGetErrorString(e));
+  if (prop.major != 10)
+    return bail(SGP_E_CUDA, "this library is built for sm_100a (B200) only; device is sm_" +
+                                std::to_string(prop.major) + std::to_string(prop.minor));
+  c->num_sms = prop.multiProcessorCount;
+  if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+      (e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking)) != cudaSuccess)
+    return bail(SGP_E_CUDA, cudaGetErrorString(e));
+  for (int i = 0; i < 2; ++i) {
+    cudaEventCreateWithFlags(&c->stage_free[i], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->stage_ready[i], cudaEventDisableTiming);
+  }
+  if (cusolverDnCreate(&c->solver) != CUSOLVER_STATUS_SUCCESS) return bail(SGP_E_CUDA, "cusolverDnCreate failed");
+  if (cublasCreate(&c->blas) != CUBLAS_STATUS_SUCCESS) return bail(SGP_E_CUDA, "cublasCreate failed");
+  *out = reinterpret_cast<sgp_ctx*>(c);
+  return SGP_OK;
+}
+
+int sgp_ctx_destroy(sgp_ctx* h) {
+  Ctx* c = reinterpret_cast<Ctx*>(h);
+  if (!c) return SGP_OK;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  drop_gram_events(c);
+  free_active_set(c);
+  cudaFree(c->dGpart); cudaFree(c->dBpart);
+  for (int i = 0; i < 2; ++i) {
+    cudaFree(c->stageX[i]); cudaFree(c->stageY[i]);
+    if (c->stage_free[i]) cudaEventDestroy(c->stage_free[i]);
+    if (c->stage_ready[i]) cudaEventDestroy(c->stage_ready[i]);
+  }
+  if (c->comm && nccl().ok) nccl().CommDestroy(c->comm);
+  if (c->solver) cusolverDnDestroy(c->solver);
+  if (c->blas) cublasDestroy(c->blas);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  delete c;
+  return SGP_OK;
+}
+
+const char* sgp_last_error(const sgp_ctx* h) {
+  const Ctx* c = reinterpret_cast<const Ctx*>(h);
+  return c ? c->err.c_str() : g_create_err.c_str();
+}
+
+int sgp_set_precision(sgp_ctx* h, int mode) {
+  Ctx* c = reinterpret_cast<Ctx*>(h);
+  if (!c) return SGP_E_BADARG;
+  if (mode != SGP_PREC_F64 && mode != SGP_PREC_F64_STRICT) return fail(c, SGP_E_BADARG, "unknown precision mode");
+  c->precision = mode;
+  return SGP_OK;
+}
+
+int sgp_comm_unique_id(void* out128) {
+  if (!out128) return SGP_E_BADARG;
+  static_assert(sizeof(ncclUniqueId) <= SGP_UNIQUE_ID_BYTES, "ncclUniqueId does not fit");
+  if (!nccl().ok) return fail(nullptr, SGP_E_NCCL, "libnccl.so.2 could not be loaded");
+  ncclUniqueId id;
+  if (nccl().GetUniqueId(&id) != ncclSuccess) return fail(nullptr, SGP_E_NCCL, "ncclGetUniqueId failed");
+  std::memset(out128, 0, SGP_UNIQUE_ID_BYTES);
+  std::memcpy(out128, &id, sizeof(id));
+  return SGP_OK;
+}
+
+int sgp_comm_init(sgp_ctx* h, const void* id128, int rank, int nranks) {
+  Ctx* c = reinterpret_cast<Ctx*>(h);
+  if (!c || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return fail(c, SGP_E_BADARG, "bad comm arguments");
+  if (!nccl().ok) return fail(c, SGP_E_NCCL, "libnccl.so.2 could not be loaded");
+  SGP_CUDA(c, cudaSetDevice(c->device));
+  ncclUniqueId id;
+  std::memcpy(&id, id128, sizeof(id));
+  ncclResult_t r = nccl().CommInitRank(&c->comm, nranks, id, rank);
+  if (r != ncclSuccess) return fail(c, SGP_E_NCCL, std::string("ncclCommInitRank: ") + nccl().GetErrorString(r));
+  c->rank = rank; c->nranks = nranks;
+  return SGP_OK;
+}
+
+int sgp_stats_begin(sgp_ctx* h, const sgp_kernel_desc* k, const double* Z, int32_t m, int32_t d) {
+  Ctx* c = reinterpret_cast<Ctx*>(h);
+  if (!c) return SGP_E_BADARG;
+  if (!k || !Z || m <= 0 || d <= 0 || k->n_terms <= 0 || !k->terms)
+    return fail(c, SGP_E_BADARG, "sgp_stats_begin: null or empty argument");
+  SGP_CUDA(c, cudaSetDevice(c->device));
+  // ---- flatten: drop Eye terms from the cross path (kernel/Kernel.scala:157), sum their coefficients ----
+  KernelFlat kf;
+  const int dpad = (d + 3) & ~3;
+  std::vector<double> beta(static_cast<size_t>(kMaxTerms) * dpad, 0.0);
+  for (int t = 0; t < k->n_terms; ++t) {
+    const sgp_kernel_term& term = k->terms[t];
+    if (!(term.scale >= 0.0)) return fail(c, SGP_E_BADARG, "requirement failed: C should be positive");
+    kf.self_kernel += term.scale;
+    if (term.type == SGP_TERM_EYE) { kf.eye_sum += term.scale; continue; }
+    if (kf.n_terms == kMaxTerms) return fail(c, SGP_E_BADARG, "too many non-Eye kernel terms (max 4)");
+    double* bt = beta.data() + static_cast<size_t>(kf.n_terms) * dpad;
+    if (term.type == SGP_TERM_ARD) {
+      if (!term.beta) return fail(c, SGP_E_BADARG, "ARD term without beta");
+      for (int j = 0; j < d; ++j) bt[j] = term.beta[j];
+    } else if (term.type == SGP_TERM_RBF) {
+      if (!(term.sigma > 0.0)) return fail(c, SGP_E_BADARG, "RBF sigma must be > 0");
+      // exp(-|x-z|^2 / (2 sigma^2)) = exp(-sum_k (x_k - z_k)^2 beta^2), beta = 1/(sqrt(2) sigma)
+      for (int j = 0; j < d; ++j) bt[j] = 1.0 / (std::sqrt(2.0) * term.sigma);
+    } else {
+      return fail(c, SGP_E_BADARG, "unknown kernel term type");
+    }
+    kf.scale[kf.n_terms++] = term.scale;
+  }
+  free_active_set(c);
+  c->m = m; c->d = d; c->dpad = dpad; c->m_pad = (m + kTile - 1) / kTile * kTile; c->kf = kf;
+  const size_t mm = static_cast<size_t>(m) * m;
+  const int nt = kf.n_terms > 0 ? kf.n_terms : 1;
+  SGP_CUDA(c, cudaMalloc(&c->dZ, static_cast<size_t>(m) * d * 8));
+  SGP_CUDA(c, cudaMalloc(&c->dZs, static_cast<size_t>(nt) * c->m_pad * dpad * 8));
+  SGP_CUDA(c, cudaMalloc(&c->dBeta, static_cast<size_t>(kMaxTerms) * dpad * 8));
+  SGP_CUDA(c, cudaMalloc(&c->dGb, (mm + m) * 8));
+  SGP_CUDA(c, cudaMalloc(&c->dMagicVec, static_cast<size_t>(m) * 8));
+  SGP_CUDA(c, cudaMalloc(&c->dMagicMat, mm * 8));
+  SGP_CUDA(c, cudaMemcpyAsync(c->dZ, Z, static_cast<size_t>(m) * d * 8, cudaMemcpyHostToDevice, c->stream));
+  SGP_CUDA(c, cudaMemcpyAsync(c->dBeta, beta.data(), beta.size() * 8, cudaMemcpyHostToDevice, c->stream));
+  SGP_CUDA(c, cudaMemsetAsync(c->dGb, 0, (mm + m) * 8, c->stream));
+  for (int t = 0; t < kf.n_terms; ++t) {
+    SGP_CUDA(c, launch_scale_rows(c->dZs + static_cast<size_t>(t) * c->m_pad * dpad, c->dZ,
+                                  c->dBeta + static_cast<size_t>(t) * dpad, m, c->m_pad, d, dpad, c->stream));
+    c->launches += 1;
+  }
+  SGP_CUDA(c, cudaStreamSynchronize(c->stream));   // Z / beta are host temporaries of the caller
+  drop_gram_events(c);
+  c->begun = true; c->finished = false; c->has_magic = false;
+  return SGP_OK;
+}
+
+int sgp_stats_accumulate_device(sgp_ctx* h, const void* dX, int32_t x_is_f32, const double* dy, int64_t n) {
+  Ctx* c = reinterpret_cast<Ctx*>(h);
+  if (!c) return SGP_E_BADARG;
+  if (!c->begun || c->finished) return fail(c, SGP_E_STATE, "sgp_stats_begin should have been called first");
+  if (n < 0 || (n > 0 && (!dX || !dy))) return fail(c, SGP_E_BADARG, "null shard");
+  SGP_CUDA(c, cudaSetDevice(c->device));
+  if (c->kf.n_terms == 0) return SGP_OK;   // only Eye terms: the cross kernel is identically zero
+  return launch_stats(c, dX, x_is_f32, dy, n);
+}
+
+int sgp_stats_accumulate(sgp_ctx* h, const void* X, int32_t x_is_f32, const double* y, int64_t n) {
+  Ctx* c = reinterpret_cast<Ctx*>(h);
+  if (!c) return SGP_E_BADARG;
+  if (!c->begun || c->finished) return fail(c, SGP_E_STATE, "sgp_stats_begin should have been called first");
+  if (n < 0 || (n > 0 && (!X || !y))) return fail(c, SGP_E_BADARG, "null shard");
+  if (n == 0 || c->kf.n_terms == 0) return SGP_OK;
+  SGP_CUDA(c, cudaSetDevice(c->device));
+  const size_t esz = x_is_f32 ? 4 : 8;
+  const size_t row = static_cast<size_t>(c->d) * esz;
+  // chunk so that copy (PCIe) and compute overlap: ~32 MB of X per chunk, at least 64k points
+  long long chunk = static_cast<long long>((32u << 20) / row);
+  if (chunk < 65536) chunk = 65536;
+  if (chunk > n) chunk = n;
+  if (chunk > c->stage_points || row * chunk > c->stage_bytes) {
+    SGP_CUDA(c, cudaStreamSynchronize(c->stream));
+    SGP_CUDA(c, cudaStreamSynchronize(c->copy_stream));
+    for (int i = 0; i < 2; ++i) {
+      cudaFree(c->stageX[i]); cudaFree(c->stageY[i]);
+      c->stageX[i] = nullptr; c->stageY[i] = nullptr;
+      SGP_CUDA(c, cudaMalloc(&c->stageX[i], row * chunk));
+      SGP_CUDA(c, cudaMalloc(&c->stageY[i], static_cast<size_t>(chunk) * 8));
+      SGP_CUDA(c, cudaEventRecord(c->stage_free[i], c->stream));
+    }
+    c->stage_bytes = row * chunk; c->stage_points = chunk;
+  }
+  const char* Xb = static_cast<const char*>(X);
+  int buf = 0;
+  for (long long p0 = 0; p0 < n; p0 += chunk, buf ^= 1) {
+    const long long cn = (n - p0 < chunk) ? (n - p0) : chunk;
+    SGP_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->stage_free[buf], 0));
+    SGP_CUDA(c, cudaMemcpyAsync(c->stageX[buf], Xb + static_cast<size_t>(p0) * row, row * cn, cudaMemcpyHostToDevice,
+                                c->copy_stream));
+    SGP_CUDA(c, cudaMemcpyAsync(c->stageY[buf], y + p0, static_cast<size_t>(cn) * 8, cudaMemcpyHostToDevice,
+                                c->copy_stream));
+    SGP_CUDA(c, cudaEventRecord(c->stage_ready[buf], c->copy_stream));
+    SGP_CUDA(c, cudaStreamWaitEvent(c->stream, c->stage_ready[buf], 0));
+    int rc = launch_stats(c, c->stageX[buf], x_is_f32, c->stageY[buf], cn);
+    if (rc != SGP_OK) return rc;
+    SGP_CUDA(c, cudaEventRecord(c->stage_free[buf], c->stream));
+  }
+  // the caller may reuse / free X, y as soon as we return
+  SGP_CUDA(c, cudaStreamSynchronize(c->copy_stream));
+  return SGP_OK;
+}
+
+int sgp_stats_finish(sgp_ctx* h, double* G_out, double* b_out) {
+  Ctx* c = reinterpret_cast<Ctx*>(h);
+  if (!c) return SGP_E_BADARG;
+  if (!c->begun) return fail(c, SGP_E_STATE, "sgp_stats_begin should have been called first");
+  SGP_CUDA(c, cudaSetDevice(c->device));
+  const size_t mm = static_cast<size_t>(c->m) * c->m;
+  if (!c->finished && c->comm && c->nranks > 1) {
+    // PGPH:31-35 combOp: one all-reduce of the packed [G;b] over NVLink
+    ncclResult_t r = nccl().AllReduce(c->dGb, c->dGb, mm + c->m, ncclDouble, ncclSum, c->comm, c->stream);
+    if (r != ncclSuccess) return fail(c, SGP_E_NCCL, std::string("ncclAllReduce: ") + nccl().GetErrorString(r));
+    c->launches += 1;
+  }
+  c->finished = true;
+  if (G_out) SGP_CUDA(c, cudaMemcpyAsync(G_out, c->dGb, mm * 8, cudaMemcpyDeviceToHost, c->stream));
+  if (b_out)
+    SGP_CUDA(c, cudaMemcpyAsync(b_out, c->dGb + mm, static_cast<size_t>(c->m) * 8, cudaMemcpyDeviceToHost, c->stream));
+  SGP_CUDA(c, cudaStreamSynchronize(c->stream));
+  return SGP_OK;
+}
+
+int sgp_sync(sgp_ctx* h) {
+  Ctx* c = reinterpret_cast<Ctx*>(h);
+  if (!c) return SGP_E_BADARG;
+  SGP_CUDA(c, cudaSetDevice(c->device));
+  SGP_CUDA(c, cudaStreamSynchronize(c->copy_stream));
+  SGP_CUDA(c, cudaStreamSynchronize(c->stream));
+  return SGP_OK;
+}
+
+int sgp_magic(sgp_ctx* h, const double* G_in, const double* b_in, double* magic_vector, double* magic_matrix) {
+  Ctx* c = reinterpret_cast<Ctx*>(h);
+  if (!c) return SGP_E_BADARG;
+  if (!c->begun) return fail(c, SGP_E_STATE, "sgp_stats_begin should have been called first");
+  if ((G_in == nullptr) != (b_in == nullptr)) return fail(c, SGP_E_BADARG, "G_in and b_in must be given together");
+  SGP_CUDA(c, cudaSetDevice(c->device));
+  const size_t mm = static_cast<size_t>(c->m) * c->m;
+  if (G_in) {
+    SGP_CUDA(c, cudaMemcpyAsync(c->dGb, G_in, mm * 8, cudaMemcpyHostToDevice, c->stream));
+    SGP_CUDA(c, cudaMemcpyAsync(c->dGb + mm, b_in, static_cast<size_t>(c->m) * 8, cudaMemcpyHostToDevice, c->stream));
+    c->finished = true;
+  } else if (!c->finished) {
+    return fail(c, SGP_E_STATE, "sgp_stats_finish should have been called first");
+  }
+  return run_tail(c, magic_vector, magic_matrix);
+}
+
+int sgp_predict(sgp_ctx* h, const double* X, int64_t n, double* mean_out, double* var_out) {
+  Ctx* c = reinterpret_cast<Ctx*>(h);
+  if (!c) return SGP_E_BADARG;
+  if (!c->has_magic) return fail(c, SGP_E_STATE, "sgp_magic should have been called first");
+  if (n < 0 || (n > 0 && (!X || !mean_out))) return fail(c, SGP_E_BADARG, "null argument");
+  if (n == 0) return SGP_OK;
+  SGP_CUDA(c, cudaSetDevice(c->device));
+  return run_predict(c, X, n, mean_out, var_out);
+}
+
+int64_t sgp_launch_count(const sgp_ctx* h) {
+  const Ctx* c = reinterpret_cast<const Ctx*>(h);
+  return c ? c->launches : 0;
+}
+
+int sgp_gram_kernel_time(sgp_ctx* h, double* total_ms, int64_t* launches) {
+  Ctx* c = reinterpret_cast<Ctx*>(h);
+  if (!c) return SGP_E_BADARG;
+  SGP_CUDA(c, cudaSetDevice(c->device));
+  SGP_CUDA(c, cudaStreamSynchronize(c->stream));
+  double tot = 0.0;
+  for (auto& e : c->gram_events) {
+    float ms = 0.f;
+    SGP_CUDA(c, cudaEventElapsedTime(&ms, e.first, e.second));
+    tot += ms;
+  }
+  if (total_ms) *total_ms = tot;
+  if (launches) *launches = static_cast<int64_t>(c->gram_events.size());
+  return SGP_OK;
+}
+
+int sgp_cross_kernel(sgp_ctx* h, const double* X, int64_t n, double* K_out) {
+  Ctx* c = reinterpret_cast<Ctx*>(h);
+  if (!c) return SGP_E_BADARG;
+  if (!c->begun) return fail(c, SGP_E_STATE, "setTrainingVectors method should have been called first");
+  if (n <= 0 || !X || !K_out) return fail(c, SGP_E_BADARG, "null argument");
+  if (n > 65535 * 8) return fail(c, SGP_E_BADARG, "sgp_cross_kernel: n too large for one call");
+  SGP_CUDA(c, cudaSetDevice(c->device));
+  double *dX = nullptr, *dK = nullptr;
+  SGP_CUDA(c, cudaMalloc(&dX, static_cast<size_t>(n) * c->d * 8));
+  cudaError_t e = cudaMalloc(&dK, static_cast<size_t>(n) * c->m * 8);
+  if (e != cudaSuccess) { cudaFree(dX); return fail(c, SGP_E_CUDA, cudaGetErrorString(e)); }
+  cudaMemcpyAsync(dX, X, static_cast<size_t>(n) * c->d * 8, cudaMemcpyHostToDevice, c->stream);
+  if (c->kf.n_terms > 0) {
+    e = launch_cross_kernel(dK, dX, c->dZs, c->dBeta, c->kf, n, c->d, c->dpad, c->m, c->m_pad, c->stream);
+    c->launches += 1;
+  } else {
+    e = cudaMemsetAsync(dK, 0, static_cast<size_t>(n) * c->m * 8, c->stream);
+  }
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(K_out, dK, static_cast<size_t>(n) * c->m * 8, cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  cudaFree(dX); cudaFree(dK);
+  if (e != cudaSuccess) return fail(c, SGP_E_CUDA, cudaGetErrorString(e));
+  return SGP_OK;
+}
+
+}  // extern "C"

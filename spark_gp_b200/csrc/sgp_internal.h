@@ -1,0 +1,117 @@
+// Internal declarations shared by the translation units of libsgp.so (not part of the C-ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cusolverDn.h>
+#include <cublas_v2.h>
+#include <nccl.h>
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/sgp.h"
+
+namespace sgp {
+
+constexpr int kMaxTerms = 4;      // non-Eye terms of a flattened kernel
+constexpr int kTile = 128;        // edge of one G tile (active-set indices per CTA tile)
+constexpr int kSMsB200 = 148;
+
+// Flattened, device-ready kernel description (built by sgp_stats_begin).
+struct KernelFlat {
+  int n_terms = 0;                 // non-Eye terms
+  double scale[kMaxTerms] = {0};   // C_t
+  double eye_sum = 0.0;            // sum of Eye coefficients = whiteNoiseVar
+  double self_kernel = 0.0;        // sum of all scales (every leaf has k(x,x) = 1)
+};
+
+// Launch parameters of the fused K_mn + Gram kernel (gram_f64.cu).
+struct GramParams {
+  const void* X;        // n x d row-major, fp32 or fp64
+  const double* y;      // n
+  long long n;
+  int x_is_f32;
+  int d, dpad;          // dpad = d rounded up to a multiple of 4
+  int m, m_pad;         // m_pad = m rounded up to a multiple of kTile
+  int n_terms;
+  double scale[kMaxTerms];
+  const double* Zs;     // [n_terms][m_pad][dpad]  beta-scaled active set (zero padded)
+  const double* beta;   // [n_terms][dpad]         per-term feature scales (zero padded)
+  double* Gpart;        // [n_slices][m_pad*m_pad] per-slice partial tiles (lower block triangle)
+  double* bpart;        // [n_slices][m_pad]
+  int n_slices;
+  int n_tiles_1d;       // m_pad / kTile
+};
+
+struct Ctx {
+  int device = 0;
+  int precision = SGP_PREC_F64;
+  std::string err;
+  cudaStream_t stream = nullptr;       // compute
+  cudaStream_t copy_stream = nullptr;  // H2D staging
+  cusolverDnHandle_t solver = nullptr;
+  cublasHandle_t blas = nullptr;
+  ncclComm_t comm = nullptr;
+  int rank = 0, nranks = 1;
+  int num_sms = kSMsB200;
+
+  // active set / kernel (valid after begin)
+  bool begun = false, finished = false, has_magic = false;
+  int m = 0, d = 0, dpad = 0, m_pad = 0;
+  KernelFlat kf;
+  double* dZ = nullptr;      // m x d raw active set (fp64)
+  double* dZs = nullptr;     // [n_terms][m_pad][dpad]
+  double* dBeta = nullptr;   // [n_terms][dpad]
+  double* dGb = nullptr;     // packed [G (m*m) ; b (m)] -- one all-reduce
+  double* dGpart = nullptr;  size_t gpart_bytes = 0;
+  double* dBpart = nullptr;  size_t bpart_bytes = 0;
+  int n_slices = 1;
+  // tail / predict state
+  double* dMagicVec = nullptr;   // m
+  double* dMagicMat = nullptr;   // m x m
+  size_t magic_cap = 0;
+  // host->device staging (double buffered)
+  void* stageX[2] = {nullptr, nullptr};
+  double* stageY[2] = {nullptr, nullptr};
+  size_t stage_bytes = 0;       // per X buffer
+  long long stage_points = 0;
+  cudaEvent_t stage_free[2] = {nullptr, nullptr};   // recorded when the kernel consuming buffer i is done
+  cudaEvent_t stage_ready[2] = {nullptr, nullptr};  // recorded when the H2D into buffer i is done
+  // instrumentation
+  int64_t launches = 0;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> gram_events;
+};
+
+// error helpers ---------------------------------------------------------------------------------
+int fail(Ctx* c, int code, const std::string& msg);
+#define SGP_CUDA(c, expr)                                                                         \
+  do {                                                                                            \
+    cudaError_t e_ = (expr);                                                                      \
+    if (e_ != cudaSuccess)                                                                        \
+      return ::sgp::fail((c), SGP_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));    \
+  } while (0)
+
+// kernels (each returns a cudaError_t from the launch) -----------------------------------------
+cudaError_t launch_gram_f64(const GramParams& p, bool strict_elements, cudaStream_t s);
+cudaError_t launch_gram_reduce(double* G /*m x m*/, double* b, const double* Gpart, const double* bpart,
+                               int n_slices, int m, int m_pad, cudaStream_t s);
+cudaError_t launch_scale_rows(double* out /*[rows][dpad]*/, const double* in /*rows x d*/, const double* beta,
+                              int rows_in, int rows_out, int d, int dpad, cudaStream_t s);
+cudaError_t launch_kmm_build(double* Kmm /*m x m*/, const double* Zs, const double* scale_dev_or_null,
+                             const KernelFlat& kf, int m, int m_pad, int dpad, cudaStream_t s);
+cudaError_t launch_cross_kernel(double* K /*n x m*/, const double* X /*n x d*/, const double* Zs,
+                                const double* beta, const KernelFlat& kf, long long n, int d, int dpad,
+                                int m, int m_pad, cudaStream_t s);
+cudaError_t launch_axpby_diag(double* A, const double* K, const double* G, double wn, int m, cudaStream_t s);
+cudaError_t launch_set_identity(double* I, int m, cudaStream_t s);
+cudaError_t launch_magic_matrix(double* out, const double* invA, const double* invK, double wn, int m,
+                                cudaStream_t s);
+cudaError_t launch_predict_finish(double* mean, double* var, const double* K /*n x m*/,
+                                  const double* W /*n x m = K*M*/, const double* mv, double self_k,
+                                  long long n, int m, cudaStream_t s);
+
+int run_tail(Ctx* c, double* magic_vector, double* magic_matrix);
+int run_predict(Ctx* c, const double* X, long long n, double* mean_out, double* var_out);
+
+}  // namespace sgp

@@ -1,0 +1,179 @@
+"""`ProjectedProcessEngine`: the Python face of the C-ABI (one context = one GPU).
+
+Mirrors the reference seam `ProjectedGaussianProcessHelper` (commons/ProjectedGaussianProcessHelper.scala):
+  getMatrixKmnKnmAndVectorKmny(experts, activeSet)  ->  begin / accumulate* / finish
+  getMagicVector(kernel, G, b, ...)                 ->  magic()
+and `GaussianProjectedProcessRawPredictor.predict` (commons/GaussianProcessCommons.scala:121-125) -> predict().
+Error codes are mapped back to the reference's exception types."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _native as N
+from .kernels import Kernel
+
+
+class NotPositiveDefiniteException(Exception):
+    """ProjectedGaussianProcessHelper.scala:9-11."""
+
+
+class TrainingVectorsNotInitializedException(Exception):
+    """kernel/Kernel.scala:116-117 (raised here for call-order violations)."""
+
+
+class MatrixSingularException(Exception):
+    """breeze MatrixSingularException (commons/util/logDetAndInv.scala:27-28)."""
+
+
+class SgpError(RuntimeError):
+    pass
+
+
+def _make_desc(kernel: Kernel, d: int):
+    terms = kernel.flatten()
+    arr = (N.KernelTerm * len(terms))()
+    keep = []
+    for i, t in enumerate(terms):
+        arr[i].type = t["type"]
+        arr[i].scale = t["scale"]
+        arr[i].sigma = t.get("sigma", 0.0)
+        if t["type"] == N.SGP_TERM_ARD:
+            beta = np.ascontiguousarray(t["beta"], dtype=np.float64)
+            if len(beta) != d:
+                raise ValueError("ARDRBFKernel has %d betas but the data has %d features" % (len(beta), d))
+            keep.append(beta)
+            arr[i].beta = beta.ctypes.data_as(C.POINTER(C.c_double))
+    desc = N.KernelDesc(len(terms), 0, arr)
+    return desc, (arr, keep)
+
+
+class ProjectedProcessEngine:
+    def __init__(self, device: int = 0):
+        self._lib = N.load()
+        self._h = C.c_void_p()
+        rc = self._lib.sgp_ctx_create(C.byref(self._h), device)
+        if rc != N.SGP_OK:
+            raise SgpError("sgp_ctx_create failed (%d): %s" % (rc, self._lib.sgp_last_error(None).decode()))
+        self.m = self.d = 0
+
+    def close(self):
+        if self._h:
+            self._lib.sgp_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc == N.SGP_OK:
+            return
+        msg = self._lib.sgp_last_error(self._h).decode()
+        if rc == N.SGP_E_NOT_PD:
+            raise NotPositiveDefiniteException(msg)
+        if rc == N.SGP_E_STATE:
+            raise TrainingVectorsNotInitializedException(msg)
+        if rc == N.SGP_E_SINGULAR:
+            raise MatrixSingularException(msg)
+        if rc == N.SGP_E_BADARG:
+            raise ValueError(msg)
+        raise SgpError("sgp error %d: %s" % (rc, msg))
+
+    # ---- configuration ---------------------------------------------------------------------------
+    def set_precision(self, mode: int):
+        self._check(self._lib.sgp_set_precision(self._h, mode))
+
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = C.create_string_buffer(N.SGP_UNIQUE_ID_BYTES)
+        rc = N.load().sgp_comm_unique_id(buf)
+        if rc != N.SGP_OK:
+            raise SgpError("sgp_comm_unique_id failed")
+        return buf.raw
+
+    def comm_init(self, unique_id: bytes, rank: int, nranks: int):
+        buf = C.create_string_buffer(unique_id, N.SGP_UNIQUE_ID_BYTES)
+        self._check(self._lib.sgp_comm_init(self._h, buf, rank, nranks))
+
+    # ---- getMatrixKmnKnmAndVectorKmny ---------------------------------------------------------------
+    def begin(self, kernel: Kernel, active_set):
+        Z = np.ascontiguousarray(active_set, dtype=np.float64)
+        if Z.ndim != 2:
+            raise ValueError("activeSet must be m x d")
+        self.m, self.d = Z.shape
+        desc, keep = _make_desc(kernel, self.d)
+        self._check(self._lib.sgp_stats_begin(self._h, C.byref(desc), N.ptr(Z), self.m, self.d))
+        del keep
+
+    def accumulate(self, X, y):
+        """One shard of points in host memory.  X: n x d (float32 or float64), y: n."""
+        X = np.asarray(X)
+        if X.dtype != np.float32:
+            X = np.asarray(X, dtype=np.float64)
+        X = np.ascontiguousarray(X)
+        y = np.ascontiguousarray(y, dtype=np.float64)
+        if X.ndim != 2 or X.shape[1] != self.d or len(y) != len(X):
+            raise ValueError("shard shape mismatch")
+        self._check(self._lib.sgp_stats_accumulate(self._h, N.ptr(X), int(X.dtype == np.float32), N.ptr(y), len(X)))
+
+    def accumulate_ptr(self, x_ptr: int, x_is_f32: bool, y_ptr: int, n: int, device: bool):
+        fn = self._lib.sgp_stats_accumulate_device if device else self._lib.sgp_stats_accumulate
+        self._check(fn(self._h, C.c_void_p(x_ptr), int(x_is_f32), C.c_void_p(y_ptr), n))
+
+    def finish(self, copy_out: bool = True):
+        if not copy_out:
+            self._check(self._lib.sgp_stats_finish(self._h, None, None))
+            return None, None
+        G = np.empty((self.m, self.m))
+        b = np.empty(self.m)
+        self._check(self._lib.sgp_stats_finish(self._h, N.ptr(G), N.ptr(b)))
+        return G, b
+
+    def sync(self):
+        self._check(self._lib.sgp_sync(self._h))
+
+    # ---- getMagicVector -------------------------------------------------------------------------------
+    def magic(self, G=None, b=None, copy_out: bool = True):
+        mv = np.empty(self.m) if copy_out else None
+        mm = np.empty((self.m, self.m)) if copy_out else None
+        if G is not None:
+            G = np.ascontiguousarray(G, dtype=np.float64)
+            b = np.ascontiguousarray(b, dtype=np.float64)
+        self._check(self._lib.sgp_magic(self._h, N.ptr(G) if G is not None else None,
+                                        N.ptr(b) if b is not None else None,
+                                        N.ptr(mv) if copy_out else None, N.ptr(mm) if copy_out else None))
+        return mv, mm
+
+    # ---- predict --------------------------------------------------------------------------------------
+    def predict(self, X, with_variance: bool = True):
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        if X.ndim == 1:
+            X = X[None, :]
+        mean = np.empty(len(X))
+        var = np.empty(len(X)) if with_variance else None
+        self._check(self._lib.sgp_predict(self._h, N.ptr(X), len(X), N.ptr(mean),
+                                          N.ptr(var) if with_variance else None))
+        return mean, var
+
+    def cross_kernel(self, X):
+        """kernel.crossKernel(test) with the active set as training vectors: len(test) x m."""
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        if X.ndim == 1:
+            X = X[None, :]
+        K = np.empty((len(X), self.m))
+        self._check(self._lib.sgp_cross_kernel(self._h, N.ptr(X), len(X), N.ptr(K)))
+        return K
+
+    # ---- introspection ---------------------------------------------------------------------------------
+    def launch_count(self) -> int:
+        return int(self._lib.sgp_launch_count(self._h))
+
+    def gram_kernel_time(self):
+        ms = C.c_double()
+        n = C.c_int64()
+        self._check(self._lib.sgp_gram_kernel_time(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value

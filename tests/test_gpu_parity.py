@@ -1,0 +1,270 @@
+"""GPU parity tests (run on a B200: `pytest -m gpu`).  Everything goes through the C-ABI (ctypes) and is
+compared with the fp64 oracle on identical seeded inputs, or with the committed golden fixtures.
+
+Tolerances (written here once):
+  TOL_STRICT = 1e-11  G, b in SGP_PREC_F64_STRICT (all-fp64) mode, relative to max|G| / max|b|
+  TOL_STATS  = 1e-6   G, b in the default mode (fp32-accurate elements, fp64 accumulation); SURVEY 8(d) gate
+  TOL_PRED   = 1e-5   posterior mean / variance / magicVector (BASELINE.json north_star tolerance)
+"""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+import spark_gp_b200 as sg
+from spark_gp_b200 import _native as N
+
+pytestmark = pytest.mark.gpu
+
+TOL_STRICT, TOL_STATS, TOL_PRED = 1e-11, 1e-6, 1e-5
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def eng():
+    e = sg.ProjectedProcessEngine(0)
+    yield e
+    e.close()
+
+
+def rel(a, b):
+    return float(np.abs(np.asarray(a) - np.asarray(b)).max() / max(np.abs(np.asarray(b)).max(), 1e-300))
+
+
+def oracle_stats(okernel_factory, X, y, Z, n_e=100):
+    experts = oracle.get_expert_labels_and_kernels(X, y, okernel_factory, n_e)
+    theta = okernel_factory().get_hyperparameters()
+    return oracle.projected_process(experts, Z, okernel_factory, theta)
+
+
+def run_stats(eng, kernel, X, y, Z, precision=N.SGP_PREC_F64, splits=None):
+    eng.set_precision(precision)
+    eng.begin(kernel, Z)
+    if splits is None:
+        eng.accumulate(X, y)
+    else:
+        lo = 0
+        for hi in list(splits) + [len(X)]:
+            eng.accumulate(X[lo:hi], y[lo:hi])
+            lo = hi
+    return eng.finish()
+
+
+# ---------------- the reference's own golden vectors, through the CUDA path ---------------------------
+DATASET = np.array([[1.0, 2.0], [2.0, 3.0], [5.0, 7.0]])
+
+
+def test_rbf_cross_kernel_golden(eng):                      # RBFKernelTest.scala:62-76
+    eng.begin(sg.RBFKernel(np.sqrt(0.2)), DATASET[1:])      # "training vectors" = dataset.drop(1)
+    ck = eng.cross_kernel(DATASET[:1])
+    assert ck.shape == (1, 2)                               # test.length x train.length
+    correct = np.array([[6.737947e-03, 3.053624e-45]])
+    assert np.all(np.abs(ck - correct) < 1e-4)
+    assert np.allclose(ck, correct, rtol=1e-6, atol=0)
+
+
+def test_rbf_training_kernel_golden(eng):                   # RBFKernelTest.scala:29-39 (cross(X,X) == training kernel)
+    eng.begin(sg.RBFKernel(np.sqrt(0.2)), DATASET)
+    K = eng.cross_kernel(DATASET)
+    correct = np.array([[1.000000e+00, 6.737947e-03, 3.053624e-45],
+                        [6.737947e-03, 1.000000e+00, 7.187782e-28],
+                        [3.053624e-45, 7.187782e-28, 1.000000e+00]])
+    assert np.allclose(K, correct, rtol=1e-6, atol=0)
+
+
+def test_survey_smoke_values(eng):                          # SURVEY.md 8(c) derived values
+    k = 1 * sg.ARDRBFKernel(np.array([0.2, 0.3])) + sg.const(1) * sg.EyeKernel() + sg.const(1e-4) * sg.EyeKernel()
+    y = np.array([0.5, -1.0, 2.0])
+    Z = DATASET[[0, 2]]
+    for prec, tol in ((N.SGP_PREC_F64_STRICT, 1e-11), (N.SGP_PREC_F64, 1e-6)):
+        G, b = run_stats(eng, k, DATASET, y, Z, prec)
+        assert np.allclose(G, [[1.774140301212, 0.256300623707], [0.256300623707, 1.030412437856]], rtol=tol)
+        assert np.allclose(b, [-0.266943005698, 1.862489218084], rtol=tol)
+        mv, mm = eng.magic()
+        assert np.allclose(mv, [-0.122545269186, 0.627149214156], rtol=max(tol, 1e-10) * 10)
+        assert np.allclose(mm, [[-0.233122498440, -0.013597424403], [-0.013597424403, -0.167542879982]],
+                           rtol=max(tol, 1e-10) * 10)
+        mean, var = eng.predict(np.array([[3.0, 4.0]]))
+        assert np.isclose(mean[0], 0.164885948858, rtol=max(tol, 1e-10) * 10)
+        assert np.isclose(var[0], 1.887496212554, rtol=max(tol, 1e-10) * 10)
+
+
+# ---------------- committed golden fixtures ------------------------------------------------------------
+def _small_case(name):
+    z = np.load(os.path.join(GOLD, "small_cases.npz"))
+    return {k.split("/", 1)[1]: z[k] for k in z.files if k.startswith(name + "/")}
+
+
+SMALL_KERNELS = {
+    "ard_ragged": lambda d: 2.5 * sg.ARDRBFKernel(np.linspace(0.5, 1.5, d)) + sg.const(0.3) * sg.EyeKernel(),
+    "rbf_wide": lambda d: sg.RBFKernel(3.0),
+    "sum_two": lambda d: 1.5 * sg.ARDRBFKernel(np.full(d, 0.7)) + 0.5 * sg.RBFKernel(2.0) + sg.const(1) * sg.EyeKernel(),
+}
+
+
+@pytest.mark.parametrize("name", list(SMALL_KERNELS))
+@pytest.mark.parametrize("strict", [True, False])
+def test_small_golden_cases(eng, name, strict):
+    c = _small_case(name)
+    d = c["X"].shape[1]
+    kernel = SMALL_KERNELS[name](d) + sg.const(1e-3) * sg.EyeKernel()       # GPC:18 sigma2 term
+    G, b = run_stats(eng, kernel, c["X"], c["y"], c["Z"], N.SGP_PREC_F64_STRICT if strict else N.SGP_PREC_F64)
+    tol = TOL_STRICT if strict else TOL_STATS
+    assert rel(G, c["G"]) < tol and rel(b, c["b"]) < tol
+    assert np.array_equal(G, G.T)
+    mv, mm = eng.magic()
+    assert rel(mv, c["magic_vector"]) < TOL_PRED
+    assert rel(mm, c["magic_matrix"]) < TOL_PRED
+    mean, var = eng.predict(c["Xtest"])
+    assert rel(mean, c["mean"]) < TOL_PRED
+    assert np.abs(var / c["var"] - 1).max() < TOL_PRED
+
+
+def test_airfoil_golden(eng):
+    """BASELINE config 1 (airfoil, expert=100, active=1000, ARD(5)); fixture made by tests/golden/make_golden.py."""
+    c = np.load(os.path.join(GOLD, "airfoil_case.npz"))
+    kernel = (1 * sg.ARDRBFKernel(5) + sg.const(1) * sg.EyeKernel() + sg.const(float(c["sigma2"])) * sg.EyeKernel())
+    kernel.setHyperparameters(c["theta"])
+    G, b = run_stats(eng, kernel, c["X"], c["y"], c["Z"])
+    gmax = np.abs(c["G_diag"]).max()
+    assert np.abs(np.diag(G) - c["G_diag"]).max() / gmax < TOL_STATS
+    assert np.abs(G[0] - c["G_row0"]).max() / gmax < TOL_STATS
+    assert abs(G.sum() - c["G_sum"]) / abs(c["G_sum"]) < TOL_STATS
+    assert rel(b, c["b"]) < TOL_STATS
+    mv, mm = eng.magic()
+    assert rel(mv, c["magic_vector"]) < TOL_PRED
+    assert rel(np.diag(mm), c["magic_matrix_diag"]) < TOL_PRED
+    mean, var = eng.predict(c["Xtest"])
+    assert rel(mean, c["mean"]) < TOL_PRED
+    assert np.abs(var / c["var"] - 1).max() < TOL_PRED
+
+
+# ---------------- seeded inputs vs the oracle, edge cases ---------------------------------------------
+@pytest.mark.parametrize("n,d,m", [(1, 1, 1), (15, 2, 3), (16, 4, 128), (17, 5, 129), (257, 7, 256), (1000, 33, 200),
+                                   (2048, 16, 384), (333, 70, 50)])
+def test_ragged_shapes_vs_oracle(eng, n, d, m):
+    rng = np.random.default_rng(n * 1000 + d * 10 + m)
+    X = rng.standard_normal((n, d))
+    y = rng.standard_normal(n)
+    Z = rng.standard_normal((m, d))
+    beta = rng.uniform(0.2, 0.9, d) / np.sqrt(d)
+    k = 1.7 * sg.ARDRBFKernel(beta) + sg.const(1e-2) * sg.EyeKernel()
+    ok = lambda: 1.7 * oracle.ARDRBFKernel(beta) + oracle.const(1e-2) * oracle.EyeKernel()
+    _, G0, b0 = oracle_stats(ok, X, y, Z, n_e=max(2, min(100, n)))
+    G, b = run_stats(eng, k, X, y, Z, N.SGP_PREC_F64_STRICT)
+    assert rel(G, G0) < TOL_STRICT and rel(b, b0) < TOL_STRICT
+    G, b = run_stats(eng, k, X, y, Z, N.SGP_PREC_F64)
+    assert rel(G, G0) < TOL_STATS and rel(b, b0) < TOL_STATS
+
+
+def test_empty_shard_and_only_eye_kernel(eng):
+    rng = np.random.default_rng(3)
+    X, y, Z = rng.standard_normal((40, 3)), rng.standard_normal(40), rng.standard_normal((5, 3))
+    k = 1 * sg.ARDRBFKernel(3) + sg.const(0.1) * sg.EyeKernel()
+    eng.begin(k, Z)
+    eng.accumulate(X[:0], y[:0])                            # empty shard is a no-op
+    eng.accumulate(X, y)
+    G1, b1 = eng.finish()
+    G2, b2 = run_stats(eng, k, X, y, Z)
+    assert np.array_equal(G1, G2) and np.array_equal(b1, b2)
+    G, b = run_stats(eng, sg.const(2.0) * sg.EyeKernel(), X, y, Z)    # Eye only: crossKernel == 0 (Kernel.scala:157)
+    assert not G.any() and not b.any()
+
+
+def test_shard_linearity_and_fp32_inputs(eng):
+    """G, b are sums over points: any split of the shard gives the same statistics (to fp64 rounding);
+    fp32 inputs are consumed exactly (identical to their fp64 up-cast)."""
+    rng = np.random.default_rng(11)
+    X = rng.random((5000, 8), dtype=np.float32)
+    y = np.sin(X.astype(np.float64).sum(1))
+    Z = X[:300].astype(np.float64)
+    k = 1 * sg.ARDRBFKernel(np.full(8, 1.5)) + sg.const(1) * sg.EyeKernel()
+    G1, b1 = run_stats(eng, k, X, y, Z)
+    G2, b2 = run_stats(eng, k, X, y, Z, splits=[17, 1000, 1001, 4096])
+    assert rel(G2, G1) < 1e-13 and rel(b2, b1) < 1e-13
+    G3, b3 = run_stats(eng, k, X.astype(np.float64), y, Z)
+    assert rel(G3, G1) < 1e-13 and rel(b3, b1) < 1e-13
+    G4, b4 = run_stats(eng, k, X, 2.0 * y, Z)               # b is linear in y, G independent of y
+    assert np.array_equal(G4, G1) and rel(b4, 2.0 * b1) < 1e-15
+    assert np.array_equal(G1, G1.T)
+
+
+def test_determinism(eng):
+    rng = np.random.default_rng(12)
+    X, y, Z = rng.random((3000, 6)), rng.random(3000), rng.random((260, 6))
+    k = 1 * sg.ARDRBFKernel(6)+ sg.const(1) * sg.EyeKernel()
+    G1, b1 = run_stats(eng, k, X, y, Z)
+    G2, b2 = run_stats(eng, k, X, y, Z)
+    assert np.array_equal(G1, G2) and np.array_equal(b1, b2)   # no atomics: bit-reproducible
+
+
+# ---------------- error behaviour ------------------------------------------------------------------------
+def test_not_positive_definite(eng):
+    k = 1 * sg.ARDRBFKernel(2) + sg.const(1e-12) * sg.EyeKernel()
+    eng.begin(k, DATASET)
+    with pytest.raises(sg.NotPositiveDefiniteException):
+        eng.magic(G=-10.0 * np.eye(3), b=np.ones(3))
+
+
+def test_call_order_errors():
+    e = sg.ProjectedProcessEngine(0)
+    with pytest.raises(sg.TrainingVectorsNotInitializedException):
+        e._check(e._lib.sgp_stats_accumulate(e._h, None, 0, None, 0))
+    with pytest.raises(sg.TrainingVectorsNotInitializedException):
+        e._check(e._lib.sgp_predict(e._h, None, 0, None, None))
+    with pytest.raises(ValueError):
+        e.begin(sg.Scalar(1.0) * sg.ARDRBFKernel(3), np.zeros((4, 2)))     # beta length != d
+    e.close()
+
+
+# ---------------- Estimator surface ------------------------------------------------------------------------
+def test_estimator_fit_predict_matches_oracle():
+    from spark_gp_b200.regression import ExplicitActiveSetProvider
+    rng = np.random.default_rng(21)
+    X = rng.random((3000, 4))
+    y = np.sin(3 * X.sum(1)) + 0.05 * rng.standard_normal(3000)
+    Z = X[rng.permutation(3000)[:200]]
+    theta = np.array([1.3, 1.1, 0.9, 1.2, 0.8])
+    gp = (sg.GaussianProcessRegression().setKernel(lambda: 1 * sg.ARDRBFKernel(4) + sg.const(1) * sg.EyeKernel())
+          .setSigma2(1e-4).setActiveSetSize(200).setDatasetSizeForExpert(100)
+          .setActiveSetProvider(ExplicitActiveSetProvider(Z)))
+    model = gp.fit(X, y, hyperparameters=theta)
+    ofac = oracle.get_kernel(lambda: 1 * oracle.ARDRBFKernel(4) + oracle.const(1) * oracle.EyeKernel(), 1e-4)
+    experts = oracle.get_expert_labels_and_kernels(X, y, ofac, 100)
+    pred, G0, b0 = oracle.projected_process(experts, Z, ofac, theta)
+    Xt = rng.random((500, 4))
+    m0, v0 = pred.predict_many(Xt)
+    assert rel(model.predict(Xt), m0) < TOL_PRED
+    mean, var = model.rawPredictor.predict(Xt)
+    assert rel(mean, m0) < TOL_PRED and np.abs(var / v0 - 1).max() < TOL_PRED
+    m1, v1 = model.rawPredictor.predict(Xt[0])
+    o1 = pred.predict(Xt[0])
+    assert abs(m1 - o1[0]) < TOL_PRED * abs(m0).max() and abs(v1 / o1[1] - 1) < TOL_PRED
+
+
+# ---------------- BASELINE-size run: size-independent properties -----------------------------------------------
+def test_full_size_config2_properties(eng):
+    """synthetic 1M x 16 fp32, active=1000 (BASELINE configs[1]): the oracle cannot finish this in seconds, so
+    check (a) a 20k-point sub-shard against the oracle, (b) shard-additivity of the full run, (c) symmetry,
+    (d) trace(G) = sum_n |k_n|^2 >= 0 and G_jj <= N * C^2."""
+    rng = np.random.default_rng(13)
+    N_, d, m = 1_000_000, 16, 1000
+    X = rng.random((N_, d), dtype=np.float32)
+    y = np.sin(X.astype(np.float64).sum(1)) + 0.1 * rng.standard_normal(N_)
+    Z = X[rng.permutation(N_)[:m]].astype(np.float64)
+    beta = np.full(d, np.sqrt(18.0 / d))
+    k = 1 * sg.ARDRBFKernel(beta) + sg.const(1) * sg.EyeKernel() + sg.const(1e-4) * sg.EyeKernel()
+    ok = lambda: 1 * oracle.ARDRBFKernel(beta) + oracle.const(1) * oracle.EyeKernel() + oracle.const(1e-4) * oracle.EyeKernel()
+    Gs, bs = run_stats(eng, k, X[:20000], y[:20000], Z)
+    _, G0, b0 = oracle_stats(ok, X[:20000].astype(np.float64), y[:20000], Z, n_e=100)
+    assert rel(Gs, G0) < TOL_STATS and rel(bs, b0) < TOL_STATS
+    G, b = run_stats(eng, k, X, y, Z)
+    Gh, bh = run_stats(eng, k, X[:400_000], y[:400_000], Z)
+    Gt, bt = run_stats(eng, k, X[400_000:], y[400_000:], Z)
+    assert rel(Gh + Gt, G) < 1e-12 and rel(bh + bt, b) < 1e-12
+    assert np.array_equal(G, G.T)
+    assert np.all(np.diag(G) > 0) and np.all(np.diag(G) <= N_ * 1.0 + 1e-6)
+    assert np.all(np.abs(G) <= np.sqrt(np.outer(np.diag(G), np.diag(G))) * (1 + 1e-12))   # Cauchy-Schwarz
+    mv, _ = eng.magic(G, b, copy_out=True)
+    assert np.all(np.isfinite(mv))
