@@ -122,6 +122,10 @@ int64_t sgp_launch_count(const sgp_ctx* ctx);
 /* Device time (ms, CUDA events on the context's stream) of the Gram kernel launches since the last
  * sgp_stats_begin, and how many there were. */
 int sgp_gram_kernel_time(sgp_ctx* ctx, double* total_ms, int64_t* launches);
+/* Device-side stopwatch on the context's compute stream (CUDA events; torch.cuda.Event cannot see this
+ * stream).  slot in [0, 8): sgp_event_record enqueues an event; sgp_event_elapsed_ms waits for both. */
+int sgp_event_record(sgp_ctx* ctx, int slot);
+int sgp_event_elapsed_ms(sgp_ctx* ctx, int slot_start, int slot_stop, double* ms);
 /* Evaluate K(X_test, Z) (n x m row-major fp64 out) with the current kernel -- the `crossKernel`
  * contract of kernel/Kernel.scala:69-74 (used by the golden-vector tests). */
 int sgp_cross_kernel(sgp_ctx* ctx, const double* X, int64_t n, double* K_out);

@@ -20,7 +20,8 @@ SGP_UNIQUE_ID_BYTES = 128
 EXPORTS = ["sgp_ctx_create", "sgp_ctx_destroy", "sgp_last_error", "sgp_set_precision", "sgp_version",
            "sgp_comm_unique_id", "sgp_comm_init", "sgp_stats_begin", "sgp_stats_accumulate",
            "sgp_stats_accumulate_device", "sgp_stats_finish", "sgp_sync", "sgp_magic", "sgp_predict",
-           "sgp_launch_count", "sgp_gram_kernel_time", "sgp_cross_kernel"]
+           "sgp_launch_count", "sgp_gram_kernel_time", "sgp_cross_kernel", "sgp_event_record",
+           "sgp_event_elapsed_ms"]
 
 
 class KernelTerm(C.Structure):
@@ -63,6 +64,8 @@ def load() -> C.CDLL:
     lib.sgp_launch_count.restype = i64
     lib.sgp_gram_kernel_time.argtypes = [vp, dp, C.POINTER(i64)]
     lib.sgp_cross_kernel.argtypes = [vp, vp, i64, vp]
+    lib.sgp_event_record.argtypes = [vp, C.c_int]
+    lib.sgp_event_elapsed_ms.argtypes = [vp, C.c_int, C.c_int, dp]
     for name in EXPORTS:
         if name not in ("sgp_last_error", "sgp_launch_count"):
             getattr(lib, name).restype = C.c_int

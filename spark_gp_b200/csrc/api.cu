@@ -152,6 +152,7 @@ int sgp_ctx_destroy(sgp_ctx* h) {
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
   drop_gram_events(c);
+  for (auto& e : c->user_events) if (e) cudaEventDestroy(e);
   free_active_set(c);
   cudaFree(c->dGpart); cudaFree(c->dBpart);
   for (int i = 0; i < 2; ++i) {
@@ -387,6 +388,29 @@ int sgp_gram_kernel_time(sgp_ctx* h, double* total_ms, int64_t* launches) {
   }
   if (total_ms) *total_ms = tot;
   if (launches) *launches = static_cast<int64_t>(c->gram_events.size());
+  return SGP_OK;
+}
+
+int sgp_event_record(sgp_ctx* h, int slot) {
+  Ctx* c = reinterpret_cast<Ctx*>(h);
+  if (!c) return SGP_E_BADARG;
+  if (slot < 0 || slot >= 8) return fail(c, SGP_E_BADARG, "event slot out of range");
+  SGP_CUDA(c, cudaSetDevice(c->device));
+  if (!c->user_events[slot]) SGP_CUDA(c, cudaEventCreate(&c->user_events[slot]));
+  SGP_CUDA(c, cudaEventRecord(c->user_events[slot], c->stream));
+  return SGP_OK;
+}
+
+int sgp_event_elapsed_ms(sgp_ctx* h, int a, int b, double* ms) {
+  Ctx* c = reinterpret_cast<Ctx*>(h);
+  if (!c) return SGP_E_BADARG;
+  if (a < 0 || a >= 8 || b < 0 || b >= 8 || !ms || !c->user_events[a] || !c->user_events[b])
+    return fail(c, SGP_E_BADARG, "bad event slots");
+  SGP_CUDA(c, cudaSetDevice(c->device));
+  SGP_CUDA(c, cudaEventSynchronize(c->user_events[b]));
+  float f = 0.f;
+  SGP_CUDA(c, cudaEventElapsedTime(&f, c->user_events[a], c->user_events[b]));
+  *ms = f;
   return SGP_OK;
 }
 

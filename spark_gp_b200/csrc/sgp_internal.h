@@ -81,6 +81,7 @@ struct Ctx {
   // instrumentation
   int64_t launches = 0;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> gram_events;
+  cudaEvent_t user_events[8] = {nullptr};
 };
 
 // error helpers ---------------------------------------------------------------------------------

@@ -172,6 +172,14 @@ class ProjectedProcessEngine:
     def launch_count(self) -> int:
         return int(self._lib.sgp_launch_count(self._h))
 
+    def event_record(self, slot: int):
+        self._check(self._lib.sgp_event_record(self._h, slot))
+
+    def event_elapsed_ms(self, a: int, b: int) -> float:
+        ms = C.c_double()
+        self._check(self._lib.sgp_event_elapsed_ms(self._h, a, b, C.byref(ms)))
+        return ms.value
+
     def gram_kernel_time(self):
         ms = C.c_double()
         n = C.c_int64()
