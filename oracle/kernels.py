@@ -134,9 +134,15 @@ class ARDRBFKernel(_TrainDatasetBearing):
 
     def _kernel_elements(self, a: np.ndarray, b: np.ndarray) -> np.ndarray:
         """ARDRBFKernel.scala:43-46 for every pair (a_i, b_j): norm((a-b)*:*beta), squared, exp(-.)."""
-        diff = (a[:, None, :] - b[None, :, :]) * self.beta
-        wd = np.sqrt(np.sum(diff * diff, axis=2))    # breeze `norm` (2-norm)
-        return np.exp(-wd * wd)
+        # accumulated feature by feature (same terms, in index order, as breeze's norm loop); keeps the
+        # temporaries at len(a) x len(b) instead of len(a) x len(b) x d
+        acc = np.zeros((len(a), len(b)))
+        for k in range(a.shape[1]):
+            diff = (a[:, k, None] - b[None, :, k]) * self.beta[k]
+            diff *= diff
+            acc += diff
+        wd = np.sqrt(acc)                            # breeze `norm` (2-norm) ...
+        return np.exp(-wd * wd)                      # ... squared again (ARDRBFKernel.scala:44-45)
 
     def training_kernel(self):                      # ARDRBFKernel.scala:48-59
         t = self.get_training_vectors()
@@ -168,8 +174,12 @@ class ARDRBFKernel(_TrainDatasetBearing):
 
 def _sqdist(a: np.ndarray, b: np.ndarray) -> np.ndarray:
     """`Vectors.sqdist` for every pair: sum_k (a_ik - b_jk)^2 (direct form, as Spark does for dense)."""
-    diff = a[:, None, :] - b[None, :, :]
-    return np.sum(diff * diff, axis=2)
+    acc = np.zeros((len(a), len(b)))
+    for k in range(a.shape[1]):
+        diff = a[:, k, None] - b[None, :, k]
+        diff *= diff
+        acc += diff
+    return acc
 
 
 class RBFKernel(_TrainDatasetBearing):
