@@ -17,7 +17,7 @@ from multiprocessing import shared_memory
 
 import numpy as np
 
-from .ppa import get_expert_labels_and_kernels, get_matrix_kmn_knm_and_vector_kmny
+from .ppa import group_for_experts, get_matrix_kmn_knm_and_vector_kmny
 
 
 def usable_cores() -> int:
@@ -33,9 +33,9 @@ def _worker(w, workers, shm_name, m, X, y, Z, kernel_factory, theta, n_e, start_
         threadpool_limits(limits=1)
     except Exception:                                     # pragma: no cover
         pass
-    experts = get_expert_labels_and_kernels(X, y, kernel_factory, n_e)[w::workers]
-    for _, k in experts:
-        k.set_hyperparameters(theta)
+    groups = group_for_experts(len(X), n_e)[w::workers]                      # GPC:26-31
+    experts = [(y[idx], kernel_factory().set_training_vectors(X[idx]).set_hyperparameters(theta))
+               for idx in groups]                                                # GPC:35-36, GPR:50
     shm = shared_memory.SharedMemory(name=shm_name)
     out = np.ndarray((workers, m * m + m), dtype=np.float64, buffer=shm.buf)
     done_q.put(("ready", w))
