@@ -38,7 +38,8 @@ enum {
   SGP_E_NCCL = 4,
   SGP_E_STATE = 5,    /* call order violated (e.g. accumulate before begin) ~ TrainingVectorsNotInitializedException */
   SGP_E_SINGULAR = 6, /* MatrixSingularException (commons/util/logDetAndInv.scala:27-28), LU info > 0 */
-  SGP_E_NOMEM = 7
+  SGP_E_NOMEM = 7,
+  SGP_E_RANGE = 8     /* SGP_PREC_I8 only: scaled coordinates outside the fp16 operand range; rerun in SGP_PREC_F64 */
 };
 
 /* Flattened kernel DSL (the files under commons/kernel/).  A kernel is a sum of terms  sum_t scale_t * k_t:
@@ -68,7 +69,11 @@ typedef struct {
 enum {
   SGP_PREC_F64 = 0,        /* default: fp32-accurate kernel elements (direct-form distances, full-precision expf),
                               fp64 DMMA Gram.  Parity-grade (<= 1e-6 on mean/variance). */
-  SGP_PREC_F64_STRICT = 1  /* elements in fp64 as well (verification mode, ~1e-13 on G,b)               */
+  SGP_PREC_F64_STRICT = 1, /* elements in fp64 as well (verification mode, ~1e-13 on G,b)               */
+  SGP_PREC_I8 = 2,         /* tcgen05 path: distance contraction on fp16 hi/lo splits (fp32 in TMEM), kernel elements
+                              as 23-bit fixed point in three balanced int8 digits, Gram = six kind::i8 products with
+                              EXACT int32 accumulation, folded into fp64.  Kernels with one non-Eye term, d <= 32. */
+  SGP_PREC_AUTO = 3        /* default: SGP_PREC_I8 when the kernel/shape qualifies, else SGP_PREC_F64           */
 };
 
 /* ---- context ------------------------------------------------------------------------------ */
@@ -126,6 +131,10 @@ int sgp_gram_kernel_time(sgp_ctx* ctx, double* total_ms, int64_t* launches);
  * stream).  slot in [0, 8): sgp_event_record enqueues an event; sgp_event_elapsed_ms waits for both. */
 int sgp_event_record(sgp_ctx* ctx, int slot);
 int sgp_event_elapsed_ms(sgp_ctx* ctx, int slot_start, int slot_stop, double* ms);
+/* Debug aid for SGP_PREC_I8: the first call arms a dump; later calls return, for the first 64-point unit of
+ * the first CTA of the last launch, T = -q*log2(e) (128 active rows x 64 points, fp32) and the fixed-point words
+ * (0x4B000000 | (u + 0x8080)). */
+int sgp_debug_i8_tile(sgp_ctx* ctx, float* T_out /* 128*64 */, uint32_t* w_out /* 128*64 */);
 /* Evaluate K(X_test, Z) (n x m row-major fp64 out) with the current kernel -- the `crossKernel`
  * contract of kernel/Kernel.scala:69-74 (used by the golden-vector tests). */
 int sgp_cross_kernel(sgp_ctx* ctx, const double* X, int64_t n, double* K_out);

@@ -5,5 +5,5 @@ host-side mirror of the reference's kernel DSL / Estimator surface.  No CPU fall
 from .kernels import (Kernel, ARDRBFKernel, RBFKernel, EyeKernel, ConstantTimesKernel, TrainableScalarTimesKernel,
                       SumOfKernels, Scalar, WhiteNoiseKernel, const)
 from .engine import (ProjectedProcessEngine, NotPositiveDefiniteException, TrainingVectorsNotInitializedException,
-                     MatrixSingularException, SgpError)
+                     MatrixSingularException, SgpError, OperandRangeError)
 from .regression import GaussianProcessRegression, GaussianProcessRegressionModel, RandomActiveSetProvider

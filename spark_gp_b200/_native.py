@@ -11,9 +11,9 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libsgp.so")
 
-SGP_OK, SGP_E_BADARG, SGP_E_CUDA, SGP_E_NOT_PD, SGP_E_NCCL, SGP_E_STATE, SGP_E_SINGULAR, SGP_E_NOMEM = range(8)
+SGP_OK, SGP_E_BADARG, SGP_E_CUDA, SGP_E_NOT_PD, SGP_E_NCCL, SGP_E_STATE, SGP_E_SINGULAR, SGP_E_NOMEM, SGP_E_RANGE = range(9)
 SGP_TERM_ARD, SGP_TERM_RBF, SGP_TERM_EYE = 0, 1, 2
-SGP_PREC_F64, SGP_PREC_F64_STRICT = 0, 1
+SGP_PREC_F64, SGP_PREC_F64_STRICT, SGP_PREC_I8, SGP_PREC_AUTO = 0, 1, 2, 3
 SGP_UNIQUE_ID_BYTES = 128
 
 # every symbol include/sgp.h declares (tests/test_abi.py checks the .so exports each of them)
@@ -21,7 +21,7 @@ EXPORTS = ["sgp_ctx_create", "sgp_ctx_destroy", "sgp_last_error", "sgp_set_preci
            "sgp_comm_unique_id", "sgp_comm_init", "sgp_stats_begin", "sgp_stats_accumulate",
            "sgp_stats_accumulate_device", "sgp_stats_finish", "sgp_sync", "sgp_magic", "sgp_predict",
            "sgp_launch_count", "sgp_gram_kernel_time", "sgp_cross_kernel", "sgp_event_record",
-           "sgp_event_elapsed_ms"]
+           "sgp_event_elapsed_ms", "sgp_debug_i8_tile"]
 
 
 class KernelTerm(C.Structure):
@@ -65,6 +65,7 @@ def load() -> C.CDLL:
     lib.sgp_gram_kernel_time.argtypes = [vp, dp, C.POINTER(i64)]
     lib.sgp_cross_kernel.argtypes = [vp, vp, i64, vp]
     lib.sgp_event_record.argtypes = [vp, C.c_int]
+    lib.sgp_debug_i8_tile.argtypes = [vp, vp, vp]
     lib.sgp_event_elapsed_ms.argtypes = [vp, C.c_int, C.c_int, dp]
     for name in EXPORTS:
         if name not in ("sgp_last_error", "sgp_launch_count"):

@@ -47,7 +47,9 @@ int fail(Ctx* c, int code, const std::string& msg) {
 static void free_active_set(Ctx* c) {
   cudaFree(c->dZ); cudaFree(c->dZs); cudaFree(c->dBeta); cudaFree(c->dGb);
   cudaFree(c->dMagicVec); cudaFree(c->dMagicMat);
+  cudaFree(c->dI8Scale); cudaFree(c->dI8Centre); cudaFree(c->dI8Flags); cudaFree(c->dI8Zt);
   c->dZ = c->dZs = c->dBeta = c->dGb = c->dMagicVec = c->dMagicMat = nullptr;
+  c->dI8Scale = c->dI8Centre = nullptr; c->dI8Flags = nullptr; c->dI8Zt = nullptr; c->i8_ok = false;
 }
 
 static int ensure_partials(Ctx* c, int n_slices) {
@@ -87,11 +89,36 @@ static int launch_stats(Ctx* c, const void* dX, int x_is_f32, const double* dy, 
   p.Gpart = c->dGpart; p.bpart = c->dBpart;
   p.n_slices = n_slices; p.n_tiles_1d = nt1;
 
+  const bool use_i8 = c->i8_ok && (c->precision == SGP_PREC_I8 || c->precision == SGP_PREC_AUTO);
+  if (c->precision == SGP_PREC_I8 && !c->i8_ok)
+    return fail(c, SGP_E_BADARG, "SGP_PREC_I8 needs a kernel with exactly one non-Eye term and d <= 32");
+  if (use_i8) {
+    const int nch = i8_nchunks(c->d);
+    const size_t xb = i8_points_scratch_bytes(n, nch);
+    const size_t yb = static_cast<size_t>((n + 63) / 64) * 64 * sizeof(float);
+    if (xb > c->i8_xt_bytes) {
+      cudaFree(c->dI8Xt); c->dI8Xt = nullptr; c->i8_xt_bytes = 0;
+      SGP_CUDA(c, cudaMalloc(&c->dI8Xt, xb));
+      c->i8_xt_bytes = xb;
+    }
+    if (yb > c->i8_ys_bytes) {
+      cudaFree(c->dI8Ys); c->dI8Ys = nullptr; c->i8_ys_bytes = 0;
+      SGP_CUDA(c, cudaMalloc(&c->dI8Ys, yb));
+      c->i8_ys_bytes = yb;
+    }
+    SGP_CUDA(c, launch_i8_prep_points(c->dI8Xt, c->dI8Ys, dX, x_is_f32, dy, n, c->d, c->dI8Scale, c->dI8Centre,
+                                      c->dI8Flags, c->stream));
+    c->launches += 1;
+  }
   cudaEvent_t e0, e1;
   SGP_CUDA(c, cudaEventCreate(&e0));
   SGP_CUDA(c, cudaEventCreate(&e1));
   SGP_CUDA(c, cudaEventRecord(e0, c->stream));
-  SGP_CUDA(c, launch_gram_f64(p, c->precision == SGP_PREC_F64_STRICT, c->stream));
+  if (use_i8)
+    SGP_CUDA(c, launch_gram_i8(c->dI8Xt, c->dI8Ys, c->dI8Zt, n, c->d, c->m_pad, n_slices, c->dGpart, c->dBpart,
+                               c->kf.scale[0], c->dbgT, c->dbgW, c->stream));
+  else
+    SGP_CUDA(c, launch_gram_f64(p, c->precision == SGP_PREC_F64_STRICT, c->stream));
   SGP_CUDA(c, cudaEventRecord(e1, c->stream));
   c->gram_events.emplace_back(e0, e1);
   const size_t mm = static_cast<size_t>(c->m) * c->m;
@@ -155,6 +182,7 @@ int sgp_ctx_destroy(sgp_ctx* h) {
   for (auto& e : c->user_events) if (e) cudaEventDestroy(e);
   free_active_set(c);
   cudaFree(c->dGpart); cudaFree(c->dBpart);
+  cudaFree(c->dI8Xt); cudaFree(c->dI8Ys); cudaFree(c->dbgT); cudaFree(c->dbgW);
   for (int i = 0; i < 2; ++i) {
     cudaFree(c->stageX[i]); cudaFree(c->stageY[i]);
     if (c->stage_free[i]) cudaEventDestroy(c->stage_free[i]);
@@ -177,7 +205,7 @@ const char* sgp_last_error(const sgp_ctx* h) {
 int sgp_set_precision(sgp_ctx* h, int mode) {
   Ctx* c = reinterpret_cast<Ctx*>(h);
   if (!c) return SGP_E_BADARG;
-  if (mode != SGP_PREC_F64 && mode != SGP_PREC_F64_STRICT) return fail(c, SGP_E_BADARG, "unknown precision mode");
+  if (mode < SGP_PREC_F64 || mode > SGP_PREC_AUTO) return fail(c, SGP_E_BADARG, "unknown precision mode");
   c->precision = mode;
   return SGP_OK;
 }
@@ -253,6 +281,30 @@ int sgp_stats_begin(sgp_ctx* h, const sgp_kernel_desc* k, const double* Z, int32
                                   c->dBeta + static_cast<size_t>(t) * dpad, m, c->m_pad, d, dpad, c->stream));
     c->launches += 1;
   }
+  // ---- tcgen05 int8 path: qualifies for one non-Eye term and d <= 32 (two 64-column K chunks) -------------
+  c->i8_ok = (kf.n_terms == 1 && d <= 32);
+  if (c->i8_ok) {
+    const int dp16 = (d + 15) / 16 * 16;
+    std::vector<double> sc(dp16, 0.0), ctr(dp16, 0.0);
+    const double s2 = std::sqrt(1.4426950408889634074);          // sqrt(log2 e): exponent in base 2
+    for (int j = 0; j < d; ++j) {
+      sc[j] = s2 * beta[j];
+      double acc = 0.0;
+      for (int i = 0; i < m; ++i) acc += Z[static_cast<size_t>(i) * d + j];
+      ctr[j] = acc / m;                                          // distances are translation invariant
+    }
+    SGP_CUDA(c, cudaMalloc(&c->dI8Scale, dp16 * 8));
+    SGP_CUDA(c, cudaMalloc(&c->dI8Centre, dp16 * 8));
+    SGP_CUDA(c, cudaMalloc(&c->dI8Flags, sizeof(int)));
+    SGP_CUDA(c, cudaMalloc(&c->dI8Zt, i8_active_scratch_bytes(c->m_pad, i8_nchunks(d))));
+    SGP_CUDA(c, cudaMemcpyAsync(c->dI8Scale, sc.data(), dp16 * 8, cudaMemcpyHostToDevice, c->stream));
+    SGP_CUDA(c, cudaMemcpyAsync(c->dI8Centre, ctr.data(), dp16 * 8, cudaMemcpyHostToDevice, c->stream));
+    SGP_CUDA(c, cudaMemsetAsync(c->dI8Flags, 0, sizeof(int), c->stream));
+    SGP_CUDA(c, launch_i8_prep_active(c->dI8Zt, c->dZ, m, c->m_pad, d, c->dI8Scale, c->dI8Centre, c->dI8Flags,
+                                      c->stream));
+    c->launches += 1;
+    SGP_CUDA(c, cudaStreamSynchronize(c->stream));               // sc / ctr are locals
+  }
   SGP_CUDA(c, cudaStreamSynchronize(c->stream));   // Z / beta are host temporaries of the caller
   drop_gram_events(c);
   c->begun = true; c->finished = false; c->has_magic = false;
@@ -320,6 +372,14 @@ int sgp_stats_finish(sgp_ctx* h, double* G_out, double* b_out) {
   if (!c->begun) return fail(c, SGP_E_STATE, "sgp_stats_begin should have been called first");
   SGP_CUDA(c, cudaSetDevice(c->device));
   const size_t mm = static_cast<size_t>(c->m) * c->m;
+  if (!c->finished && c->i8_ok && c->dI8Flags) {
+    int flags = 0;
+    SGP_CUDA(c, cudaMemcpyAsync(&flags, c->dI8Flags, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    SGP_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (flags & 1)
+      return fail(c, SGP_E_RANGE, "scaled coordinates exceed the fp16 operand range of SGP_PREC_I8; "
+                                  "rerun the statistics with sgp_set_precision(SGP_PREC_F64)");
+  }
   if (!c->finished && c->comm && c->nranks > 1) {
     // PGPH:31-35 combOp: one all-reduce of the packed [G;b] over NVLink
     ncclResult_t r = nccl().AllReduce(c->dGb, c->dGb, mm + c->m, ncclDouble, ncclSum, c->comm, c->stream);
@@ -388,6 +448,22 @@ int sgp_gram_kernel_time(sgp_ctx* h, double* total_ms, int64_t* launches) {
   }
   if (total_ms) *total_ms = tot;
   if (launches) *launches = static_cast<int64_t>(c->gram_events.size());
+  return SGP_OK;
+}
+
+int sgp_debug_i8_tile(sgp_ctx* h, float* T_out, uint32_t* w_out) {
+  Ctx* c = reinterpret_cast<Ctx*>(h);
+  if (!c) return SGP_E_BADARG;
+  SGP_CUDA(c, cudaSetDevice(c->device));
+  if (!c->dbgT) {   // arm: the next I8 launches dump the first distance tile of CTA (0,0)
+    SGP_CUDA(c, cudaMalloc(&c->dbgT, 128 * 64 * 4));
+    SGP_CUDA(c, cudaMalloc(&c->dbgW, 128 * 64 * 4));
+    SGP_CUDA(c, cudaMemset(c->dbgT, 0, 128 * 64 * 4));
+    SGP_CUDA(c, cudaMemset(c->dbgW, 0, 128 * 64 * 4));
+  }
+  SGP_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (T_out) SGP_CUDA(c, cudaMemcpy(T_out, c->dbgT, 128 * 64 * 4, cudaMemcpyDeviceToHost));
+  if (w_out) SGP_CUDA(c, cudaMemcpy(w_out, c->dbgW, 128 * 64 * 4, cudaMemcpyDeviceToHost));
   return SGP_OK;
 }
 

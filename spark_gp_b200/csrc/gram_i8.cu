@@ -1,0 +1,629 @@
+// Fused K_mn + Gram kernel on the 5th-gen tensor cores (tcgen05 / TMEM), exact-accumulation path.
+//
+// Same contract as gram_f64.cu (one shard of points -> per-slice partial tiles of G = sum_n k_n k_n^T and
+// b = sum_n k_n y_n; replaces commons/ProjectedGaussianProcessHelper.scala:27-29 and the crossKernel chain
+// kernel/ARDRBFKernel.scala:81-89 / RBFKernel.scala:66-76 / ScalarTimesKernel.scala:24 /
+// SumOfKernels.scala:57-58), for kernels with ONE non-Eye term  C * exp(-sum_k beta_k^2 (x_k - z_k)^2).
+//
+// Why integers.  tools/precision_study.py: the posterior mean only matches the fp64 reference to 1e-5 if
+// the Gram is ACCUMULATED better than fp32 -- so fp32 TMEM accumulators (kind::f16/tf32) cannot carry the
+// parity gate, while fp32-accurate *elements* are 50x inside it.  kind::i8 accumulates in int32, which is
+// exact.  Every kernel element kappa = exp(-q) in (0,1] becomes a 23-bit fixed-point integer
+// u = rint(kappa * c0) written in balanced base-256 digits u = s2*2^16 + s1*2^8 + s0 (s2 in [0,127]
+// unsigned, s1,s0 in [-128,127] signed), and
+//     sum_n u_ni u_nj = 2^32 [S2'S2] + 2^24 [S2'S1 + S1'S2] + 2^16 [S2'S0 + S0'S2 + S1'S1] + (dropped)
+// is six int8 tensor-core products into three int32 TMEM accumulators.  The dropped products (weights 2^8,
+// 2^0) are zero-mean because the low digits are balanced: ~7e-9 per point relative to full scale.
+//
+// Pipeline of one CTA (owns G tile (I,J), I>=J, 128x128, and a slice of the shard's 64-point units):
+//   warp 0   producer : cp.async.bulk (TMA engine, UBLKCP) of pre-swizzled operand images, 4-stage ring
+//   warp 1   MMA      : one thread issues  (a) distance MMAs  T[128 active x 64 points] (kind::f16, fp32 in
+//                       TMEM): -q*log2(e) as ONE contraction over the fp16 hi/lo split of the scaled,
+//                       centred coordinates with the row/column norms folded in as extra K columns;
+//                       (b) the 12 Gram MMAs (kind::i8) of the previous unit
+//   warp 2   TMEM allocator (512 columns: 3 x 128 int32 accumulators + 2 x 64 distance tiles)
+//   warps 4-11 epilogue: tcgen05.ld T -> ex2 -> fixed point via one FFMA against 2^23 -> byte planes (PRMT)
+//                       -> 16-byte stores into the K-major SWIZZLE_128B int8 operand panels in shared memory
+//                       (A/B operands of the Gram MMAs), b += kappa*y on diagonal tiles; every 32768 points
+//                       the int32 accumulators are folded into the fp64 partial tile (no overflow possible).
+#include <cuda_fp16.h>
+
+#include "sgp_internal.h"
+
+namespace sgp {
+namespace {
+
+constexpr int UP = 64;                  // points per pipeline unit
+constexpr int XSTAGES = 4;
+constexpr int YSTAGES = 8;               // y ring is deeper than the operand ring: the epilogue reads y after the
+                                        // operand stage of the same unit may already have been recycled
+constexpr int NTHREADS = 384;
+constexpr uint32_t TM_ACC4 = 0, TM_ACC3 = 128, TM_ACC2 = 256, TM_Q0 = 384;   // TMEM column map
+constexpr float C0 = 8355000.0f;        // fixed-point scale: u <= C0*(1+8e-5) keeps u + 0x8080 < 2^23
+constexpr float MAGIC = 8388608.0f + 32896.0f;   // 2^23 + 0x8080: mantissa of (kappa*C0 + MAGIC) = u + 0x8080
+constexpr int PANEL_BYTES = 16384;      // 128 rows x 128 bytes, SWIZZLE_128B K-major
+constexpr int XIMG_BYTES = 8192;        // 64 rows x 128 bytes
+
+// ---------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// Bounded spin: a protocol bug must not hang the GPU box -- trap after ~4 s instead.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  long long t0 = 0;
+  for (uint32_t it = 0;; ++it) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) return;
+    if ((it & 0xFFFFu) == 0xFFFFu) {
+      const long long t = clock64();
+      if (t0 == 0) t0 = t;
+      else if (t - t0 > 8000000000LL) __trap();
+    }
+  }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void mma_i8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+  return d;
+}
+
+// UMMA shared-memory descriptor, K-major, SWIZZLE_128B (cute::UMMA::SmemDescriptor): start>>4 [0,14),
+// LBO>>4 [16,30) (unused for swizzled K-major: 1), SBO>>4 [32,46) = 1024 B between 8-row groups,
+// version=1 [46,48), layout_type=2 (SWIZZLE_128B) [61,64).  Tile bases are 1024-byte aligned.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  return static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// UMMA instruction descriptor (cute::UMMA::InstrDescriptor): c_format [4,6), a_format [7,10), b_format [10,13),
+// a_major bit 15 / b_major bit 16 (0 = K-major), N>>3 [17,23), M>>4 [24,29).
+__host__ __device__ constexpr uint32_t idesc_f16_f32(int M, int N) {
+  return (1u << 4) | (0u << 7) | (0u << 10) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+}
+__host__ __device__ constexpr uint32_t idesc_i8_s32(int M, int N, bool a_signed, bool b_signed) {
+  return (2u << 4) | ((a_signed ? 1u : 0u) << 7) | ((b_signed ? 1u : 0u) << 10) | (static_cast<uint32_t>(N >> 3) << 17) |
+         (static_cast<uint32_t>(M >> 4) << 24);
+}
+
+// byte offset of (row r, 16-byte chunk c16 in [0,8)) inside a K-major SWIZZLE_128B tile with 128-byte rows
+__host__ __device__ __forceinline__ uint32_t sw128_off(int r, int c16) {
+  return static_cast<uint32_t>((r >> 3) * 1024 + (r & 7) * 128 + ((c16 ^ (r & 7)) << 4));
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Operand preparation: fp16 hi/lo split of the scaled, centred coordinates + norm columns, written as
+// ready-to-copy shared-memory images (K-major SWIZZLE_128B).  Logical K columns (dp = d padded to 16):
+//   [0,dp)        A: zh_k   B: 2*xh_k          [dp,2dp)   A: zl_k   B: 2*xh_k
+//   [2dp,3dp)     A: zh_k   B: 2*xl_k          [3dp,3dp+16) A: 1,1,1,c1,c2,c3,0..  B: r1,r2,r3,1,1,1,0..
+// with x^ = sqrt(log2 e) * beta * (x - centre) = xh + xl (fp16 each), r = -|xh+xl|^2 = r1+r2+r3, c likewise, so
+// that  sum_K A*B = 2 x^.z^ - |x^|^2 - |z^|^2 (+ xl.zl, ~1e-8)  = -q * log2(e)  of the represented points.
+// ---------------------------------------------------------------------------------------------------
+struct SplitRow {
+  __half hi[32], lo[32];
+  __half n1, n2, n3;   // three-piece fp16 expansion of -|hi+lo|^2
+};
+
+__device__ __forceinline__ void split_row(const double* v, int dp, SplitRow& s, double& norm2) {
+  double acc = 0.0;
+  for (int k = 0; k < dp; ++k) {
+    const __half h = __double2half(v[k]);
+    const __half l = __double2half(v[k] - static_cast<double>(__half2float(h)));
+    s.hi[k] = h; s.lo[k] = l;
+    const double r = static_cast<double>(__half2float(h)) + static_cast<double>(__half2float(l));
+    acc += r * r;
+  }
+  norm2 = acc;
+  const double n = -acc;
+  s.n1 = __double2half(n);
+  const double e1 = n - static_cast<double>(__half2float(s.n1));
+  s.n2 = __double2half(e1);
+  s.n3 = __double2half(e1 - static_cast<double>(__half2float(s.n2)));
+}
+
+template <bool IS_B>   // IS_B: point rows (B operand), else active-set rows (A operand)
+__device__ __forceinline__ __half operand_col(const SplitRow& s, int dp, int L, bool valid) {
+  const __half zero = __float2half(0.f), one = __float2half(1.f);
+  if (L < 3 * dp) {
+    if (!valid) return zero;
+    const int seg = L / dp, k = L % dp;
+    if (IS_B) {
+      const __half h = (seg == 2) ? s.lo[k] : s.hi[k];
+      return __hadd(h, h);                                   // 2*x (exact)
+    }
+    return (seg == 1) ? s.lo[k] : s.hi[k];
+  }
+  const int a = L - 3 * dp;                                   // augmented columns
+  if (IS_B) {
+    if (a == 0) return valid ? s.n1 : __float2half(-60000.f);  // padded point: T = -60000 -> kappa = 0
+    if (a == 1) return valid ? s.n2 : zero;
+    if (a == 2) return valid ? s.n3 : zero;
+    if (a < 6) return one;
+    return zero;
+  }
+  if (a < 3) return one;
+  if (a == 3) return valid ? s.n1 : __float2half(-60000.f);    // padded active row
+  if (a == 4) return valid ? s.n2 : zero;
+  if (a == 5) return valid ? s.n3 : zero;
+  return zero;
+}
+
+// X (n x d, fp32/fp64) -> images [unit][chunk][64 rows x 128 B] and ys (fp32, zero padded)
+__global__ void prep_points_kernel(uint8_t* __restrict__ Xt, float* __restrict__ ys, const void* __restrict__ X,
+                                   int x_is_f32, const double* __restrict__ y, long long n, long long n_units,
+                                   int d, int dp, int nchunks, const double* __restrict__ scale /*[dp]*/,
+                                   const double* __restrict__ centre /*[dp]*/, int* __restrict__ flags) {
+  const long long pt = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (pt >= n_units * UP) return;
+  const bool valid = pt < n;
+  double v[32];
+  for (int k = 0; k < dp; ++k) {
+    double x = 0.0;
+    if (valid && k < d) {
+      const size_t off = static_cast<size_t>(pt) * d + k;
+      x = x_is_f32 ? static_cast<double>(reinterpret_cast<const float*>(X)[off]) : reinterpret_cast<const double*>(X)[off];
+      x = (x - centre[k]) * scale[k];
+    }
+    v[k] = x;
+  }
+  SplitRow s;
+  double norm2;
+  split_row(v, dp, s, norm2);
+  if (valid && !(norm2 <= 16384.0)) atomicOr(flags, 1);          // out of the fp16 operand range -> caller falls back
+  ys[pt] = valid ? static_cast<float>(y[pt]) : 0.f;
+  const long long unit = pt / UP;
+  const int r = static_cast<int>(pt % UP);
+  for (int c = 0; c < nchunks; ++c) {
+    uint8_t* img = Xt + (static_cast<size_t>(unit) * nchunks + c) * XIMG_BYTES;
+    for (int c16 = 0; c16 < 8; ++c16) {
+      __align__(16) __half h[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) h[e] = operand_col<true>(s, dp, c * 64 + c16 * 8 + e, valid);
+      *reinterpret_cast<uint4*>(img + sw128_off(r, c16)) = *reinterpret_cast<const uint4*>(h);
+    }
+  }
+}
+
+// Z (m x d fp64) -> images [tile][chunk][128 rows x 128 B]
+__global__ void prep_active_kernel(uint8_t* __restrict__ Zt, const double* __restrict__ Z, int m, int m_pad, int d,
+                                   int dp, int nchunks, const double* __restrict__ scale, const double* __restrict__ centre,
+                                   int* __restrict__ flags) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= m_pad) return;
+  const bool valid = j < m;
+  double v[32];
+  for (int k = 0; k < dp; ++k) v[k] = (valid && k < d) ? (Z[static_cast<size_t>(j) * d + k] - centre[k]) * scale[k] : 0.0;
+  SplitRow s;
+  double norm2;
+  split_row(v, dp, s, norm2);
+  if (valid && !(norm2 <= 16384.0)) atomicOr(flags, 1);
+  const int tile = j / kTile, r = j % kTile;
+  for (int c = 0; c < nchunks; ++c) {
+    uint8_t* img = Zt + (static_cast<size_t>(tile) * nchunks + c) * PANEL_BYTES;
+    for (int c16 = 0; c16 < 8; ++c16) {
+      __align__(16) __half h[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) h[e] = operand_col<false>(s, dp, c * 64 + c16 * 8 + e, valid);
+      *reinterpret_cast<uint4*>(img + sw128_off(r, c16)) = *reinterpret_cast<const uint4*>(h);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// The fused kernel
+// ---------------------------------------------------------------------------------------------------
+struct I8Params {
+  const uint8_t* Xt;    // [n_units][nchunks][8192]
+  const float* ys;      // [n_units*64]
+  const uint8_t* Zt;    // [n_tiles_1d][nchunks][16384]
+  long long n_units;
+  int nchunks;          // 64-column K chunks of the distance contraction (1 or 2)
+  int ksteps_last;      // 16-column k-steps used in the last chunk
+  int m_pad, n_tiles_1d, n_slices;
+  int flush_units;      // fold int32 accumulators into fp64 every this many units (<= 512)
+  double* Gpart;        // [n_slices][m_pad*m_pad]
+  double* bpart;        // [n_slices][m_pad]
+  double gscale;        // C^2 / C0^2
+  double bscale;        // C
+  float* dbg_T;         // optional [128*64] : T of the first distance tile of CTA (0,0)
+  uint32_t* dbg_w;      // optional [128*64] : fixed-point words of the same tile
+};
+
+__global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_kernel(const I8Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - raw);
+  // carve-up (all operand tiles 1024-byte aligned)
+  const uint32_t s_panel = base;                                          // [2 panels][3 slices][16384]
+  const uint32_t s_zt = s_panel + 6 * PANEL_BYTES;                        // [2][nchunks][16384]
+  const uint32_t s_xs = s_zt + 2 * p.nchunks * PANEL_BYTES;               // [XSTAGES][nchunks][8192]
+  const uint32_t s_ys = s_xs + XSTAGES * p.nchunks * XIMG_BYTES;          // [YSTAGES][64] float
+  const uint32_t s_bred = s_ys + YSTAGES * UP * 4;                        // [2][128] double
+  const uint32_t s_bar = s_bred + 2 * 128 * 8;                            // mbarriers
+  const uint32_t b_xfull = s_bar, b_xempty = s_bar + 8 * XSTAGES, b_qfull = b_xempty + 8 * XSTAGES,
+                 b_qempty = b_qfull + 16, b_pfull = b_qempty + 16, b_pempty = b_pfull + 16, b_accfull = b_pempty + 16,
+                 b_accempty = b_accfull + 8, b_zfull = b_accempty + 8, s_tmem = b_zfull + 8;
+  uint8_t* sm_panel = sm;
+  float* sm_ys = reinterpret_cast<float*>(sm + (s_ys - base));
+  double* sm_bred = reinterpret_cast<double*>(sm + (s_bred - base));
+  volatile uint32_t* sm_tmem = reinterpret_cast<volatile uint32_t*>(sm + (s_tmem - base));
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  int ti, tj;
+  {
+    const int t = blockIdx.x;
+    ti = static_cast<int>((sqrtf(8.0f * t + 1.0f) - 1.0f) * 0.5f);
+    while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+    while (ti * (ti + 1) / 2 > t) --ti;
+    tj = t - ti * (ti + 1) / 2;
+  }
+  const bool diag = (ti == tj);
+  const int np = diag ? 1 : 2;
+
+  const long long ups = (p.n_units + p.n_slices - 1) / p.n_slices;
+  const long long u_lo = ups * blockIdx.y;
+  long long u_hi = u_lo + ups;
+  if (u_hi > p.n_units) u_hi = p.n_units;
+  const long long nu = u_hi > u_lo ? u_hi - u_lo : 0;
+
+  double* Gp = p.Gpart + static_cast<size_t>(blockIdx.y) * p.m_pad * p.m_pad;
+  double* bp = p.bpart + static_cast<size_t>(blockIdx.y) * p.m_pad;
+
+  if (nu == 0) {   // empty slice: the partial tile must still be defined
+    for (int e = tid; e < kTile * kTile; e += NTHREADS)
+      Gp[static_cast<size_t>(ti * kTile + e / kTile) * p.m_pad + tj * kTile + (e % kTile)] = 0.0;
+    if (diag && tid < kTile) bp[ti * kTile + tid] = 0.0;
+    return;
+  }
+
+  // ---- one-time setup -------------------------------------------------------------------------------
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < XSTAGES; ++s) { mbar_init(b_xfull + 8 * s, 1); mbar_init(b_xempty + 8 * s, 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(b_qfull + 8 * i, 1); mbar_init(b_qempty + 8 * i, 8);
+      mbar_init(b_pfull + 8 * i, 8); mbar_init(b_pempty + 8 * i, 1);
+    }
+    mbar_init(b_accfull, 1); mbar_init(b_accempty, 8); mbar_init(b_zfull, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_tmem), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *sm_tmem;
+
+  if (warp == 0) {
+    // ================= producer: bulk copies of operand images ========================================
+    if (lane == 0) {
+      mbar_expect_tx(b_zfull, static_cast<uint32_t>(np * p.nchunks * PANEL_BYTES));
+      for (int P = 0; P < np; ++P) {
+        const int tile = P ? tj : ti;
+        bulk_g2s(s_zt + P * p.nchunks * PANEL_BYTES, p.Zt + static_cast<size_t>(tile) * p.nchunks * PANEL_BYTES,
+                 static_cast<uint32_t>(p.nchunks * PANEL_BYTES), b_zfull);
+      }
+      const uint32_t xbytes = static_cast<uint32_t>(p.nchunks * XIMG_BYTES);
+      for (long long i = 0; i < nu; ++i) {
+        const int s = static_cast<int>(i & (XSTAGES - 1));
+        if (i >= XSTAGES) mbar_wait(b_xempty + 8 * s, static_cast<uint32_t>(((i / XSTAGES) - 1) & 1));
+        mbar_expect_tx(b_xfull + 8 * s, xbytes + UP * 4);
+        bulk_g2s(s_xs + s * xbytes, p.Xt + static_cast<size_t>(u_lo + i) * xbytes, xbytes, b_xfull + 8 * s);
+        bulk_g2s(s_ys + static_cast<uint32_t>(i & (YSTAGES - 1)) * UP * 4, p.ys + static_cast<size_t>(u_lo + i) * UP, UP * 4,
+                 b_xfull + 8 * s);
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer (one thread) =========================================================
+    if (lane == 0) {
+      constexpr uint32_t IDESC_D = idesc_f16_f32(128, UP);
+      const uint32_t xbytes = static_cast<uint32_t>(p.nchunks * XIMG_BYTES);
+      uint32_t flush_idx = 0;
+      auto gram = [&](long long j) {
+        const uint32_t h = static_cast<uint32_t>(j & 1);
+        mbar_wait(b_pfull + 8 * h, static_cast<uint32_t>((j >> 1) & 1));
+        tc_fence_after();
+        const bool first = (j % p.flush_units) == 0;
+        const uint32_t pa = s_panel, pb = s_panel + (diag ? 0 : 3 * PANEL_BYTES);
+        auto prod = [&](int a, int b, uint32_t acc_col, bool fresh) {
+          const uint32_t id = idesc_i8_s32(128, 128, a != 2, b != 2);
+#pragma unroll
+          for (uint32_t ks = 0; ks < 2; ++ks) {
+            const uint64_t da = umma_desc_sw128(pa + a * PANEL_BYTES + h * 64 + ks * 32);
+            const uint64_t db = umma_desc_sw128(pb + b * PANEL_BYTES + h * 64 + ks * 32);
+            mma_i8(tmem + acc_col, da, db, id, (fresh && ks == 0) ? 0u : 1u);
+          }
+        };
+        prod(2, 2, TM_ACC4, first);
+        prod(2, 1, TM_ACC3, first);
+        prod(1, 2, TM_ACC3, false);
+        prod(2, 0, TM_ACC2, first);
+        prod(0, 2, TM_ACC2, false);
+        prod(1, 1, TM_ACC2, false);
+        tc_commit(b_pempty + 8 * h);
+        if (((j + 1) % p.flush_units) == 0 || j == nu - 1) {
+          tc_commit(b_accfull);
+          if (j != nu - 1) {
+            mbar_wait(b_accempty, flush_idx & 1);
+            tc_fence_after();
+          }
+          ++flush_idx;
+        }
+      };
+      mbar_wait(b_zfull, 0);
+      for (long long i = 0; i < nu; ++i) {
+        const int s = static_cast<int>(i & (XSTAGES - 1));
+        mbar_wait(b_xfull + 8 * s, static_cast<uint32_t>((i / XSTAGES) & 1));
+        tc_fence_after();
+        for (int P = 0; P < np; ++P) {
+          const long long t = i * np + P;
+          const uint32_t qb = static_cast<uint32_t>(t & 1);
+          if (t >= 2) {
+            mbar_wait(b_qempty + 8 * qb, static_cast<uint32_t>(((t >> 1) - 1) & 1));
+            tc_fence_after();
+          }
+          const uint32_t d_tmem = tmem + TM_Q0 + qb * UP;
+          for (int c = 0; c < p.nchunks; ++c) {
+            const int nks = (c == p.nchunks - 1) ? p.ksteps_last : 4;
+            for (int ks = 0; ks < nks; ++ks) {
+              const uint64_t da = umma_desc_sw128(s_zt + (P * p.nchunks + c) * PANEL_BYTES + ks * 32);
+              const uint64_t db = umma_desc_sw128(s_xs + s * xbytes + c * XIMG_BYTES + ks * 32);
+              mma_f16(d_tmem, da, db, IDESC_D, (c | ks) ? 1u : 0u);
+            }
+          }
+          tc_commit(b_qfull + 8 * qb);
+        }
+        tc_commit(b_xempty + 8 * s);
+        if (i >= 1) gram(i - 1);
+      }
+      gram(nu - 1);
+    }
+  } else if (warp >= 4) {
+    // ================= epilogue warps ===================================================================
+    const int ew = warp - 4;
+    const int lq = ew & 3;              // TMEM lane quarter of this warp (== warp % 4)
+    const int ch = ew >> 2;             // which 32 of the 64 columns (points) of a distance tile
+    const int L = lq * 32 + lane;       // TMEM lane == active-set row inside the tile
+    const uint32_t lane_bits = static_cast<uint32_t>(lq * 32) << 16;
+    double bsum = 0.0;
+    uint32_t flush_idx = 0;
+    bool first_flush = true;
+    const bool dbg = (p.dbg_T != nullptr) && blockIdx.x == 0 && blockIdx.y == 0;
+    for (long long i = 0; i < nu; ++i) {
+      const uint32_t h = static_cast<uint32_t>(i & 1);
+      const int s = static_cast<int>(i & (YSTAGES - 1));
+      if (i >= 2) mbar_wait(b_pempty + 8 * h, static_cast<uint32_t>(((i >> 1) - 1) & 1));
+      float bacc = 0.f;
+      for (int P = 0; P < np; ++P) {
+        const long long t = i * np + P;
+        const uint32_t qb = static_cast<uint32_t>(t & 1);
+        mbar_wait(b_qfull + 8 * qb, static_cast<uint32_t>((t >> 1) & 1));
+        tc_fence_after();
+        uint32_t T[32];
+        tmem_ld32(tmem + lane_bits + TM_Q0 + qb * UP + ch * 32, T);
+        tmem_wait_ld();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(b_qempty + 8 * qb);
+        if (dbg && i == 0 && P == 0) {
+          for (int k = 0; k < 32; ++k) p.dbg_T[L * UP + ch * 32 + k] = __uint_as_float(T[k]);
+        }
+        // kappa = 2^T ; fixed point: mantissa(kappa*C0 + MAGIC) = u + 0x8080
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+          const float e = ex2f(__uint_as_float(T[k]));
+          if (diag) bacc = fmaf(e, sm_ys[s * UP + ch * 32 + k], bacc);
+          T[k] = __float_as_uint(fmaf(e, C0, MAGIC));
+        }
+        if (dbg && i == 0 && P == 0) {
+          for (int k = 0; k < 32; ++k) p.dbg_w[L * UP + ch * 32 + k] = T[k];
+        }
+        // byte planes: 4 consecutive points -> one word per digit; 16 points -> one 16-byte store per digit
+        uint8_t* pan = sm_panel + P * 3 * PANEL_BYTES;
+#pragma unroll
+        for (int g16 = 0; g16 < 2; ++g16) {
+          uint32_t d0[4], d1[4], d2[4];
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const uint32_t w0 = T[g16 * 16 + g * 4 + 0], w1 = T[g16 * 16 + g * 4 + 1], w2 = T[g16 * 16 + g * 4 + 2],
+                           w3 = T[g16 * 16 + g * 4 + 3];
+            const uint32_t t01 = prmt(w0, w1, 0x5140), t23 = prmt(w2, w3, 0x5140);
+            d0[g] = prmt(t01, t23, 0x5410) ^ 0x80808080u;     // s0 = byte0 - 128 (two's complement)
+            d1[g] = prmt(t01, t23, 0x7632) ^ 0x80808080u;     // s1 = byte1 - 128
+            const uint32_t u01 = prmt(w0, w1, 0x0062), u23 = prmt(w2, w3, 0x0062);
+            d2[g] = prmt(u01, u23, 0x5410);                   // s2 = byte2 (0..127)
+          }
+          const uint32_t off = sw128_off(L, static_cast<int>(h * 4 + ch * 2 + g16));
+          *reinterpret_cast<uint4*>(pan + 0 * PANEL_BYTES + off) = make_uint4(d0[0], d0[1], d0[2], d0[3]);
+          *reinterpret_cast<uint4*>(pan + 1 * PANEL_BYTES + off) = make_uint4(d1[0], d1[1], d1[2], d1[3]);
+          *reinterpret_cast<uint4*>(pan + 2 * PANEL_BYTES + off) = make_uint4(d2[0], d2[1], d2[2], d2[3]);
+        }
+      }
+      bsum += static_cast<double>(bacc);
+      fence_proxy_async();               // generic-proxy panel writes -> visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(b_pfull + 8 * h);
+
+      if (((i + 1) % p.flush_units) == 0 || i == nu - 1) {
+        // ---- fold the exact int32 accumulators into the fp64 partial tile --------------------------------
+        mbar_wait(b_accfull, flush_idx & 1);
+        tc_fence_after();
+        double* grow = Gp + static_cast<size_t>(ti * kTile + L) * p.m_pad + tj * kTile;
+        for (int cg = 0; cg < 4; ++cg) {
+          const int col0 = ch * 64 + cg * 16;
+          uint32_t a4[16], a3[16], a2[16];
+          tmem_ld16(tmem + lane_bits + TM_ACC4 + col0, a4);
+          tmem_ld16(tmem + lane_bits + TM_ACC3 + col0, a3);
+          tmem_ld16(tmem + lane_bits + TM_ACC2 + col0, a2);
+          tmem_wait_ld();
+#pragma unroll
+          for (int k = 0; k < 16; k += 2) {
+            double v0 = 4294967296.0 * static_cast<double>(static_cast<int>(a4[k])) +
+                        16777216.0 * static_cast<double>(static_cast<int>(a3[k])) +
+                        65536.0 * static_cast<double>(static_cast<int>(a2[k]));
+            double v1 = 4294967296.0 * static_cast<double>(static_cast<int>(a4[k + 1])) +
+                        16777216.0 * static_cast<double>(static_cast<int>(a3[k + 1])) +
+                        65536.0 * static_cast<double>(static_cast<int>(a2[k + 1]));
+            v0 *= p.gscale; v1 *= p.gscale;
+            double2* dst = reinterpret_cast<double2*>(grow + col0 + k);
+            if (first_flush) {
+              *dst = make_double2(v0, v1);
+            } else {
+              double2 o = *dst;
+              o.x += v0; o.y += v1;
+              *dst = o;
+            }
+          }
+        }
+        first_flush = false;
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(b_accempty);
+        ++flush_idx;
+      }
+    }
+    if (diag) {
+      sm_bred[ch * 128 + L] = bsum;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (ch == 0) bp[ti * kTile + L] = p.bscale * (sm_bred[L] + sm_bred[128 + L]);
+    }
+  }
+
+  // ---- teardown ----------------------------------------------------------------------------------------
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+  }
+}
+
+}  // namespace
+
+// -------------------------------------------------------------------------------------------------------
+// host side
+// -------------------------------------------------------------------------------------------------------
+size_t i8_points_scratch_bytes(long long n, int nchunks) {
+  const long long units = (n + UP - 1) / UP;
+  return static_cast<size_t>(units) * nchunks * XIMG_BYTES;
+}
+size_t i8_active_scratch_bytes(int m_pad, int nchunks) {
+  return static_cast<size_t>(m_pad / kTile) * nchunks * PANEL_BYTES;
+}
+int i8_nchunks(int d) {
+  const int dp = (d + 15) / 16 * 16;
+  return (3 * dp + 16 + 63) / 64;
+}
+
+cudaError_t launch_i8_prep_active(uint8_t* Zt, const double* dZ, int m, int m_pad, int d, const double* dScale,
+                                  const double* dCentre, int* dFlags, cudaStream_t s) {
+  const int dp = (d + 15) / 16 * 16;
+  prep_active_kernel<<<(m_pad + 127) / 128, 128, 0, s>>>(Zt, dZ, m, m_pad, d, dp, i8_nchunks(d), dScale, dCentre, dFlags);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_i8_prep_points(uint8_t* Xt, float* ys, const void* dX, int x_is_f32, const double* dy, long long n,
+                                  int d, const double* dScale, const double* dCentre, int* dFlags, cudaStream_t s) {
+  const int dp = (d + 15) / 16 * 16;
+  const long long units = (n + UP - 1) / UP;
+  const long long threads = units * UP;
+  prep_points_kernel<<<static_cast<unsigned>((threads + 127) / 128), 128, 0, s>>>(Xt, ys, dX, x_is_f32, dy, n, units, d, dp,
+                                                                                i8_nchunks(d), dScale, dCentre, dFlags);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_gram_i8(const uint8_t* Xt, const float* ys, const uint8_t* Zt, long long n, int d, int m_pad,
+                           int n_slices, double* Gpart, double* bpart, double C, float* dbg_T, uint32_t* dbg_w,
+                           cudaStream_t s) {
+  I8Params p{};
+  const int dp = (d + 15) / 16 * 16;
+  p.Xt = Xt; p.ys = ys; p.Zt = Zt;
+  p.n_units = (n + UP - 1) / UP;
+  p.nchunks = i8_nchunks(d);
+  p.ksteps_last = (3 * dp + 16) / 16 - 4 * (p.nchunks - 1);
+  p.m_pad = m_pad; p.n_tiles_1d = m_pad / kTile; p.n_slices = n_slices;
+  p.flush_units = 512;                       // 32768 points: 3 * 128*128 * 32768 < 2^31
+  p.Gpart = Gpart; p.bpart = bpart;
+  p.gscale = C * C / (static_cast<double>(C0) * static_cast<double>(C0));
+  p.bscale = C;
+  p.dbg_T = dbg_T; p.dbg_w = dbg_w;
+  const size_t smem = 1024 + 6 * PANEL_BYTES + 2 * p.nchunks * PANEL_BYTES + XSTAGES * p.nchunks * XIMG_BYTES +
+                      YSTAGES * UP * 4 + 2 * 128 * 8 + 256;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kmn_gram_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  const int nt = p.n_tiles_1d * (p.n_tiles_1d + 1) / 2;
+  dim3 grid(nt, n_slices);
+  kmn_gram_i8_kernel<<<grid, NTHREADS, smem, s>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace sgp

@@ -46,7 +46,7 @@ struct GramParams {
 
 struct Ctx {
   int device = 0;
-  int precision = SGP_PREC_F64;
+  int precision = SGP_PREC_AUTO;
   std::string err;
   cudaStream_t stream = nullptr;       // compute
   cudaStream_t copy_stream = nullptr;  // H2D staging
@@ -67,6 +67,14 @@ struct Ctx {
   double* dGpart = nullptr;  size_t gpart_bytes = 0;
   double* dBpart = nullptr;  size_t bpart_bytes = 0;
   int n_slices = 1;
+  // tcgen05 int8 path (gram_i8.cu)
+  bool i8_ok = false;            // kernel/shape qualifies (one non-Eye term, d <= 32)
+  double* dI8Scale = nullptr;    // [dp16] sqrt(log2 e) * beta_k
+  double* dI8Centre = nullptr;   // [dp16] per-feature centre (active-set mean)
+  int* dI8Flags = nullptr;       // bit 0: coordinates out of fp16 operand range
+  uint8_t* dI8Zt = nullptr;      // active-set operand images
+  uint8_t* dI8Xt = nullptr;  size_t i8_xt_bytes = 0;   // point operand images (scratch)
+  float* dI8Ys = nullptr;    size_t i8_ys_bytes = 0;
   // tail / predict state
   double* dMagicVec = nullptr;   // m
   double* dMagicMat = nullptr;   // m x m
@@ -82,6 +90,8 @@ struct Ctx {
   int64_t launches = 0;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> gram_events;
   cudaEvent_t user_events[8] = {nullptr};
+  float* dbgT = nullptr;       // sgp_debug_i8_tile
+  uint32_t* dbgW = nullptr;
 };
 
 // error helpers ---------------------------------------------------------------------------------
@@ -111,6 +121,18 @@ cudaError_t launch_magic_matrix(double* out, const double* invA, const double* i
 cudaError_t launch_predict_finish(double* mean, double* var, const double* K /*n x m*/,
                                   const double* W /*n x m = K*M*/, const double* mv, double self_k,
                                   long long n, int m, cudaStream_t s);
+
+// tcgen05 path
+size_t i8_points_scratch_bytes(long long n, int nchunks);
+size_t i8_active_scratch_bytes(int m_pad, int nchunks);
+int i8_nchunks(int d);
+cudaError_t launch_i8_prep_active(uint8_t* Zt, const double* dZ, int m, int m_pad, int d, const double* dScale,
+                                  const double* dCentre, int* dFlags, cudaStream_t s);
+cudaError_t launch_i8_prep_points(uint8_t* Xt, float* ys, const void* dX, int x_is_f32, const double* dy, long long n,
+                                  int d, const double* dScale, const double* dCentre, int* dFlags, cudaStream_t s);
+cudaError_t launch_gram_i8(const uint8_t* Xt, const float* ys, const uint8_t* Zt, long long n, int d, int m_pad,
+                           int n_slices, double* Gpart, double* bpart, double C, float* dbg_T, uint32_t* dbg_w,
+                           cudaStream_t s);
 
 int run_tail(Ctx* c, double* magic_vector, double* magic_matrix);
 int run_predict(Ctx* c, const double* X, long long n, double* mean_out, double* var_out);

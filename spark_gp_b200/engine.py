@@ -31,6 +31,10 @@ class SgpError(RuntimeError):
     pass
 
 
+class OperandRangeError(SgpError):
+    """SGP_E_RANGE: the tcgen05 int8 path cannot represent these coordinates; rerun in SGP_PREC_F64."""
+
+
 def _make_desc(kernel: Kernel, d: int):
     terms = kernel.flatten()
     arr = (N.KernelTerm * len(terms))()
@@ -81,6 +85,8 @@ class ProjectedProcessEngine:
             raise MatrixSingularException(msg)
         if rc == N.SGP_E_BADARG:
             raise ValueError(msg)
+        if rc == N.SGP_E_RANGE:
+            raise OperandRangeError(msg)
         raise SgpError("sgp error %d: %s" % (rc, msg))
 
     # ---- configuration ---------------------------------------------------------------------------
@@ -167,6 +173,13 @@ class ProjectedProcessEngine:
         K = np.empty((len(X), self.m))
         self._check(self._lib.sgp_cross_kernel(self._h, N.ptr(X), len(X), N.ptr(K)))
         return K
+
+    def debug_i8_tile(self):
+        """Arms (first call) / reads back the SGP_PREC_I8 debug dump: (T [128x64] fp32, words [128x64] uint32)."""
+        T = np.zeros((128, 64), dtype=np.float32)
+        w = np.zeros((128, 64), dtype=np.uint32)
+        self._check(self._lib.sgp_debug_i8_tile(self._h, N.ptr(T), N.ptr(w)))
+        return T, w
 
     # ---- introspection ---------------------------------------------------------------------------------
     def launch_count(self) -> int:

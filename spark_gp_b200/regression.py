@@ -9,7 +9,8 @@ from __future__ import annotations
 
 import numpy as np
 
-from .engine import ProjectedProcessEngine
+from . import _native as N
+from .engine import ProjectedProcessEngine, OperandRangeError
 from .kernels import Kernel, RBFKernel, EyeKernel, const
 
 
@@ -127,10 +128,17 @@ class GaussianProcessRegression(GaussianProcessParams):
         active_set = self._activeSetProvider(self._activeSetSize, X, y, self.getKernel, theta, self._seed)
         kernel = self.getKernel().setHyperparameters(theta)
         eng = ProjectedProcessEngine(self._device)
-        eng.begin(kernel, active_set)                                   # PGPH:23 broadcast(activeSet)
-        for s in range(0, len(X), self._shard_points):                  # PGPH:25-35 seqOp over shards
-            eng.accumulate(X[s:s + self._shard_points], y[s:s + self._shard_points])
-        G, b = eng.finish()
+
+        def stats():
+            eng.begin(kernel, active_set)                               # PGPH:23 broadcast(activeSet)
+            for s in range(0, len(X), self._shard_points):              # PGPH:25-35 seqOp over shards
+                eng.accumulate(X[s:s + self._shard_points], y[s:s + self._shard_points])
+            return eng.finish()
+        try:
+            G, b = stats()
+        except OperandRangeError:                                       # still on the GPU: fp64 DMMA kernel
+            eng.set_precision(N.SGP_PREC_F64)
+            G, b = stats()
         mv, mm = eng.magic()                                            # PGPH:49-60
         self.last_stats = (G, b)
         return GaussianProcessRegressionModel(GaussianProjectedProcessRawPredictor(eng, mv, mm, kernel, active_set),
