@@ -34,7 +34,7 @@ namespace sgp {
 namespace {
 
 constexpr int UP = 64;                  // points per pipeline unit
-constexpr int XSTAGES = 4;
+constexpr int XSTAGES_MAX = 4;          // operand ring depth: 4 stages with one K chunk, 3 with two (227 KB limit)
 constexpr int YSTAGES = 8;               // y ring is deeper than the operand ring: the epilogue reads y after the
                                         // operand stage of the same unit may already have been recycled
 constexpr int NTHREADS = 384;
@@ -281,6 +281,7 @@ struct I8Params {
   const uint8_t* Zt;    // [n_tiles_1d][nchunks][16384]
   long long n_units;
   int nchunks;          // 64-column K chunks of the distance contraction (1 or 2)
+  int xstages;          // operand ring depth
   int ksteps_last;      // 16-column k-steps used in the last chunk
   int m_pad, n_tiles_1d, n_slices;
   int flush_units;      // fold int32 accumulators into fp64 every this many units (<= 512)
@@ -300,11 +301,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_kernel(const I8Params
   // carve-up (all operand tiles 1024-byte aligned)
   const uint32_t s_panel = base;                                          // [2 panels][3 slices][16384]
   const uint32_t s_zt = s_panel + 6 * PANEL_BYTES;                        // [2][nchunks][16384]
-  const uint32_t s_xs = s_zt + 2 * p.nchunks * PANEL_BYTES;               // [XSTAGES][nchunks][8192]
-  const uint32_t s_ys = s_xs + XSTAGES * p.nchunks * XIMG_BYTES;          // [YSTAGES][64] float
+  const uint32_t s_xs = s_zt + 2 * p.nchunks * PANEL_BYTES;               // [xstages][nchunks][8192]
+  const uint32_t s_ys = s_xs + p.xstages * p.nchunks * XIMG_BYTES;        // [YSTAGES][64] float
   const uint32_t s_bred = s_ys + YSTAGES * UP * 4;                        // [2][128] double
   const uint32_t s_bar = s_bred + 2 * 128 * 8;                            // mbarriers
-  const uint32_t b_xfull = s_bar, b_xempty = s_bar + 8 * XSTAGES, b_qfull = b_xempty + 8 * XSTAGES,
+  const uint32_t b_xfull = s_bar, b_xempty = s_bar + 8 * XSTAGES_MAX, b_qfull = b_xempty + 8 * XSTAGES_MAX,
                  b_qempty = b_qfull + 16, b_pfull = b_qempty + 16, b_pempty = b_pfull + 16, b_accfull = b_pempty + 16,
                  b_accempty = b_accfull + 8, b_zfull = b_accempty + 8, s_tmem = b_zfull + 8;
   uint8_t* sm_panel = sm;
@@ -343,7 +344,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_kernel(const I8Params
 
   // ---- one-time setup -------------------------------------------------------------------------------
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < XSTAGES; ++s) { mbar_init(b_xfull + 8 * s, 1); mbar_init(b_xempty + 8 * s, 1); }
+    for (int s = 0; s < XSTAGES_MAX; ++s) { mbar_init(b_xfull + 8 * s, 1); mbar_init(b_xempty + 8 * s, 1); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(b_qfull + 8 * i, 1); mbar_init(b_qempty + 8 * i, 8);
       mbar_init(b_pfull + 8 * i, 8); mbar_init(b_pempty + 8 * i, 1);
@@ -371,8 +372,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_kernel(const I8Params
       }
       const uint32_t xbytes = static_cast<uint32_t>(p.nchunks * XIMG_BYTES);
       for (long long i = 0; i < nu; ++i) {
-        const int s = static_cast<int>(i & (XSTAGES - 1));
-        if (i >= XSTAGES) mbar_wait(b_xempty + 8 * s, static_cast<uint32_t>(((i / XSTAGES) - 1) & 1));
+        const int s = static_cast<int>(i % p.xstages);
+        if (i >= p.xstages) mbar_wait(b_xempty + 8 * s, static_cast<uint32_t>(((i / p.xstages) - 1) & 1));
         mbar_expect_tx(b_xfull + 8 * s, xbytes + UP * 4);
         bulk_g2s(s_xs + s * xbytes, p.Xt + static_cast<size_t>(u_lo + i) * xbytes, xbytes, b_xfull + 8 * s);
         bulk_g2s(s_ys + static_cast<uint32_t>(i & (YSTAGES - 1)) * UP * 4, p.ys + static_cast<size_t>(u_lo + i) * UP, UP * 4,
@@ -418,8 +419,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_kernel(const I8Params
       };
       mbar_wait(b_zfull, 0);
       for (long long i = 0; i < nu; ++i) {
-        const int s = static_cast<int>(i & (XSTAGES - 1));
-        mbar_wait(b_xfull + 8 * s, static_cast<uint32_t>((i / XSTAGES) & 1));
+        const int s = static_cast<int>(i % p.xstages);
+        mbar_wait(b_xfull + 8 * s, static_cast<uint32_t>((i / p.xstages) & 1));
         tc_fence_after();
         for (int P = 0; P < np; ++P) {
           const long long t = i * np + P;
@@ -612,7 +613,8 @@ cudaError_t launch_gram_i8(const uint8_t* Xt, const float* ys, const uint8_t* Zt
   p.gscale = C * C / (static_cast<double>(C0) * static_cast<double>(C0));
   p.bscale = C;
   p.dbg_T = dbg_T; p.dbg_w = dbg_w;
-  const size_t smem = 1024 + 6 * PANEL_BYTES + 2 * p.nchunks * PANEL_BYTES + XSTAGES * p.nchunks * XIMG_BYTES +
+  p.xstages = (p.nchunks == 1) ? 4 : 3;
+  const size_t smem = 1024 + 6 * PANEL_BYTES + 2 * p.nchunks * PANEL_BYTES + p.xstages * p.nchunks * XIMG_BYTES +
                       YSTAGES * UP * 4 + 2 * 128 * 8 + 256;
   static bool attr_set = false;
   if (!attr_set) {

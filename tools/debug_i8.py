@@ -30,11 +30,12 @@ def case(n, d, m, seed=0, check_dbg=False, label=""):
     rng = np.random.default_rng(seed)
     X = rng.random((n, d), dtype=np.float32)
     y = np.sin(X.astype(np.float64).sum(1)) + 0.1 * rng.standard_normal(n)
-    Z = X[rng.permutation(n)[:m]].astype(np.float64)
+    Z = rng.random((m, d))
     beta = np.full(d, np.sqrt(18.0 / d))
     C = 1.7
     k = C * sg.ARDRBFKernel(beta) + sg.const(1) * sg.EyeKernel() + sg.const(1e-4) * sg.EyeKernel()
     ok = lambda: C * oracle.ARDRBFKernel(beta) + oracle.const(1) * oracle.EyeKernel() + oracle.const(1e-4) * oracle.EyeKernel()
+    t00 = time.perf_counter()
     e = sg.ProjectedProcessEngine(0)
     e.set_precision(N.SGP_PREC_I8)
     if check_dbg:
@@ -60,7 +61,7 @@ def case(n, d, m, seed=0, check_dbg=False, label=""):
     eg = np.abs(G - G0).max() / np.abs(G0).max()
     eb = np.abs(b - b0).max() / np.abs(b0).max()
     sym = np.array_equal(G, G.T)
-    print("%-28s n=%-7d d=%-3d m=%-5d dG=%.2e db=%.2e sym=%s  (%.1f ms)" % (label, n, d, m, eg, eb, sym, dt * 1e3), flush=True)
+    print("%-28s n=%-7d d=%-3d m=%-5d dG=%.2e db=%.2e sym=%s  (%.1f ms; case wall %.1f s)" % (label, n, d, m, eg, eb, sym, dt * 1e3, time.perf_counter() - t00), flush=True)
     e.close()
     return eg, eb
 
@@ -73,3 +74,20 @@ if __name__ == "__main__":
     case(5000, 32, 384, label="d=32 (2 K chunks)")
     case(20000, 16, 1000, label="36 tiles x 4 slices")
     case(300000, 16, 256, label="flush boundary (>32768/slice)")
+    # throughput at BASELINE configs[1]
+    import ctypes as C
+    rng = np.random.default_rng(1)
+    n, d, m = 1_000_000, 16, 1000
+    X = rng.random((n, d), dtype=np.float32); y = rng.random(n)
+    Z = X[:m].astype(np.float64)
+    k = 1 * sg.ARDRBFKernel(np.full(d, np.sqrt(18.0 / d))) + sg.const(1) * sg.EyeKernel() + sg.const(1e-4) * sg.EyeKernel()
+    e = sg.ProjectedProcessEngine(0)
+    for mode, name in ((N.SGP_PREC_I8, "I8"), (N.SGP_PREC_F64, "F64")):
+        e.set_precision(mode)
+        for rep in range(3):
+            e.begin(k, Z)
+            t0 = time.perf_counter(); e.accumulate(X, y); G, b = e.finish(); dt = time.perf_counter() - t0
+            ms, nl = e.gram_kernel_time()
+            print("%s rep %d: host->G %.1f ms, gram kernels %.2f ms (%d launches) -> %.1f Mpts/s kernel-only" % (name, rep, dt * 1e3, ms, nl, n / ms / 1e3), flush=True)
+        if mode == N.SGP_PREC_I8: G8, b8 = G, b
+    print("I8 vs F64 at 1M: dG=%.2e db=%.2e" % (np.abs(G8 - G).max() / np.abs(G).max(), np.abs(b8 - b).max() / np.abs(b).max()))
