@@ -381,70 +381,93 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_kernel(const I8Params
       }
     }
   } else if (warp == 1) {
-    // ================= MMA issuer (one thread) =========================================================
-    if (lane == 0) {
-      constexpr uint32_t IDESC_D = idesc_f16_f32(128, UP);
-      const uint32_t xbytes = static_cast<uint32_t>(p.nchunks * XIMG_BYTES);
-      uint32_t flush_idx = 0;
-      auto gram = [&](long long j) {
-        const uint32_t h = static_cast<uint32_t>(j & 1);
-        mbar_wait(b_pfull + 8 * h, static_cast<uint32_t>((j >> 1) & 1));
-        tc_fence_after();
-        const bool first = (j % p.flush_units) == 0;
-        const uint32_t pa = s_panel, pb = s_panel + (diag ? 0 : 3 * PANEL_BYTES);
-        auto prod = [&](int a, int b, uint32_t acc_col, bool fresh) {
-          const uint32_t id = idesc_i8_s32(128, 128, a != 2, b != 2);
-#pragma unroll
-          for (uint32_t ks = 0; ks < 2; ++ks) {
-            const uint64_t da = umma_desc_sw128(pa + a * PANEL_BYTES + h * 64 + ks * 32);
-            const uint64_t db = umma_desc_sw128(pb + b * PANEL_BYTES + h * 64 + ks * 32);
-            mma_i8(tmem + acc_col, da, db, id, (fresh && ks == 0) ? 0u : 1u);
-          }
-        };
-        prod(2, 2, TM_ACC4, first);
-        prod(2, 1, TM_ACC3, first);
-        prod(1, 2, TM_ACC3, false);
-        prod(2, 0, TM_ACC2, first);
-        prod(0, 2, TM_ACC2, false);
-        prod(1, 1, TM_ACC2, false);
+    // ================= MMA issuer ======================================================================
+    // The whole warp runs this role (warp-uniform control flow keeps the 64-bit UMMA descriptors in uniform
+    // registers); one elected lane issues the tcgen05 instructions.  Issue cost matters: a divergent
+    // single-thread version measured 155 clk per MMA (descriptor arithmetic + R2UR), i.e. issue-bound.
+    uint32_t elected;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(elected));
+    constexpr uint32_t IDESC_D = idesc_f16_f32(128, UP);
+    constexpr uint32_t ID_UU = idesc_i8_s32(128, 128, false, false), ID_US = idesc_i8_s32(128, 128, false, true),
+                       ID_SU = idesc_i8_s32(128, 128, true, false), ID_SS = idesc_i8_s32(128, 128, true, true);
+    constexpr uint32_t DESC_HI = 64u | (1u << 14) | (2u << 29);     // SBO = 1024 B, version 1, SWIZZLE_128B
+    auto D = [](uint32_t lo) { return (static_cast<uint64_t>(DESC_HI) << 32) | lo; };
+    auto lo_of = [](uint32_t addr) { return ((addr & 0x3FFFFu) >> 4) | (1u << 16); };
+    const uint32_t zt_lo = lo_of(s_zt), xs_lo = lo_of(s_xs), pan_lo = lo_of(s_panel);
+    const uint32_t pb_off = diag ? 0u : 3u * (PANEL_BYTES >> 4);
+    constexpr uint32_t SL = PANEL_BYTES >> 4;                       // descriptor units between digit panels
+    uint32_t flush_idx = 0;
+
+    auto gram = [&](long long j) {
+      const uint32_t h = static_cast<uint32_t>(j & 1);
+      mbar_wait(b_pfull + 8 * h, static_cast<uint32_t>((j >> 1) & 1));
+      tc_fence_after();
+      const uint32_t fresh = ((j % p.flush_units) == 0) ? 0u : 1u;
+      const uint32_t pa = pan_lo + h * 4, pb = pa + pb_off;
+      if (elected) {
+        // weight 2^32 : S2'S2
+        mma_i8(tmem + TM_ACC4, D(pa + 2 * SL), D(pb + 2 * SL), ID_UU, fresh);
+        mma_i8(tmem + TM_ACC4, D(pa + 2 * SL + 2), D(pb + 2 * SL + 2), ID_UU, 1u);
+        // weight 2^24 : S2'S1 + S1'S2
+        mma_i8(tmem + TM_ACC3, D(pa + 2 * SL), D(pb + 1 * SL), ID_US, fresh);
+        mma_i8(tmem + TM_ACC3, D(pa + 2 * SL + 2), D(pb + 1 * SL + 2), ID_US, 1u);
+        mma_i8(tmem + TM_ACC3, D(pa + 1 * SL), D(pb + 2 * SL), ID_SU, 1u);
+        mma_i8(tmem + TM_ACC3, D(pa + 1 * SL + 2), D(pb + 2 * SL + 2), ID_SU, 1u);
+        // weight 2^16 : S2'S0 + S0'S2 + S1'S1
+        mma_i8(tmem + TM_ACC2, D(pa + 2 * SL), D(pb), ID_US, fresh);
+        mma_i8(tmem + TM_ACC2, D(pa + 2 * SL + 2), D(pb + 2), ID_US, 1u);
+        mma_i8(tmem + TM_ACC2, D(pa), D(pb + 2 * SL), ID_SU, 1u);
+        mma_i8(tmem + TM_ACC2, D(pa + 2), D(pb + 2 * SL + 2), ID_SU, 1u);
+        mma_i8(tmem + TM_ACC2, D(pa + 1 * SL), D(pb + 1 * SL), ID_SS, 1u);
+        mma_i8(tmem + TM_ACC2, D(pa + 1 * SL + 2), D(pb + 1 * SL + 2), ID_SS, 1u);
         tc_commit(b_pempty + 8 * h);
-        if (((j + 1) % p.flush_units) == 0 || j == nu - 1) {
-          tc_commit(b_accfull);
-          if (j != nu - 1) {
-            mbar_wait(b_accempty, flush_idx & 1);
-            tc_fence_after();
-          }
-          ++flush_idx;
+      }
+      if (((j + 1) % p.flush_units) == 0 || j == nu - 1) {
+        if (elected) tc_commit(b_accfull);
+        if (j != nu - 1) {
+          mbar_wait(b_accempty, flush_idx & 1);
+          tc_fence_after();
         }
-      };
-      mbar_wait(b_zfull, 0);
-      for (long long i = 0; i < nu; ++i) {
-        const int s = static_cast<int>(i % p.xstages);
-        mbar_wait(b_xfull + 8 * s, static_cast<uint32_t>((i / p.xstages) & 1));
-        tc_fence_after();
-        for (int P = 0; P < np; ++P) {
-          const long long t = i * np + P;
-          const uint32_t qb = static_cast<uint32_t>(t & 1);
-          if (t >= 2) {
-            mbar_wait(b_qempty + 8 * qb, static_cast<uint32_t>(((t >> 1) - 1) & 1));
-            tc_fence_after();
-          }
-          const uint32_t d_tmem = tmem + TM_Q0 + qb * UP;
-          for (int c = 0; c < p.nchunks; ++c) {
-            const int nks = (c == p.nchunks - 1) ? p.ksteps_last : 4;
-            for (int ks = 0; ks < nks; ++ks) {
-              const uint64_t da = umma_desc_sw128(s_zt + (P * p.nchunks + c) * PANEL_BYTES + ks * 32);
-              const uint64_t db = umma_desc_sw128(s_xs + s * xbytes + c * XIMG_BYTES + ks * 32);
-              mma_f16(d_tmem, da, db, IDESC_D, (c | ks) ? 1u : 0u);
-            }
+        ++flush_idx;
+      }
+    };
+
+    mbar_wait(b_zfull, 0);
+    const uint32_t xstride = static_cast<uint32_t>(p.nchunks) * (XIMG_BYTES >> 4);
+    for (long long i = 0; i < nu; ++i) {
+      const uint32_t s = static_cast<uint32_t>(i % p.xstages);
+      mbar_wait(b_xfull + 8 * s, static_cast<uint32_t>((i / p.xstages) & 1));
+      tc_fence_after();
+      for (int P = 0; P < np; ++P) {
+        const long long t = i * np + P;
+        const uint32_t qb = static_cast<uint32_t>(t & 1);
+        if (t >= 2) {
+          mbar_wait(b_qempty + 8 * qb, static_cast<uint32_t>(((t >> 1) - 1) & 1));
+          tc_fence_after();
+        }
+        const uint32_t d_tmem = tmem + TM_Q0 + qb * UP;
+        const uint32_t a0 = zt_lo + static_cast<uint32_t>(P * p.nchunks) * SL, b0 = xs_lo + s * xstride;
+        if (elected) {
+          // chunk 0 always has 4 k-steps unless it is also the last chunk
+          const int nks0 = (p.nchunks == 1) ? p.ksteps_last : 4;
+          mma_f16(d_tmem, D(a0), D(b0), IDESC_D, 0u);
+          if (nks0 > 1) mma_f16(d_tmem, D(a0 + 2), D(b0 + 2), IDESC_D, 1u);
+          if (nks0 > 2) mma_f16(d_tmem, D(a0 + 4), D(b0 + 4), IDESC_D, 1u);
+          if (nks0 > 3) mma_f16(d_tmem, D(a0 + 6), D(b0 + 6), IDESC_D, 1u);
+          if (p.nchunks == 2) {
+            const uint32_t a1 = a0 + SL, b1 = b0 + (XIMG_BYTES >> 4);
+            mma_f16(d_tmem, D(a1), D(b1), IDESC_D, 1u);
+            if (p.ksteps_last > 1) mma_f16(d_tmem, D(a1 + 2), D(b1 + 2), IDESC_D, 1u);
+            if (p.ksteps_last > 2) mma_f16(d_tmem, D(a1 + 4), D(b1 + 4), IDESC_D, 1u);
+            if (p.ksteps_last > 3) mma_f16(d_tmem, D(a1 + 6), D(b1 + 6), IDESC_D, 1u);
           }
           tc_commit(b_qfull + 8 * qb);
         }
-        tc_commit(b_xempty + 8 * s);
-        if (i >= 1) gram(i - 1);
       }
-      gram(nu - 1);
+      if (elected) tc_commit(b_xempty + 8 * s);
+      if (i >= 1) gram(i - 1);
     }
+    gram(nu - 1);
   } else if (warp >= 4) {
     // ================= epilogue warps ===================================================================
     const int ew = warp - 4;
