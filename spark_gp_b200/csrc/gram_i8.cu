@@ -37,7 +37,8 @@ constexpr int UP = 64;                  // points per pipeline unit
 constexpr int XSTAGES_MAX = 4;          // operand ring depth: 4 stages with one K chunk, 3 with two (227 KB limit)
 constexpr int YSTAGES = 8;               // y ring is deeper than the operand ring: the epilogue reads y after the
                                         // operand stage of the same unit may already have been recycled
-constexpr int EPI_WARPS = 16;             // 4 TMEM lane quarters x 4 column quarters of a distance tile
+constexpr int EPI_WARPS = 16;             // two groups of 8 (4 TMEM lane quarters x 2 column halves); group g owns
+                                        // the distance tiles with (tile index & 1) == g, i.e. TMEM buffer g
 constexpr int NTHREADS = 128 + EPI_WARPS * 32;
 constexpr uint32_t TM_ACC4 = 0, TM_ACC3 = 128, TM_ACC2 = 256, TM_Q0 = 384;   // TMEM column map
 constexpr float C0 = 8355000.0f;        // fixed-point scale: u <= C0*(1+8e-5) keeps u + 0x8080 < 2^23
@@ -350,8 +351,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_kernel(const I8Params
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < XSTAGES_MAX; ++s) { mbar_init(b_xfull + 8 * s, 1); mbar_init(b_xempty + 8 * s, 1); }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(b_qfull + 8 * i, 1); mbar_init(b_qempty + 8 * i, EPI_WARPS);
-      mbar_init(b_pfull + 8 * i, EPI_WARPS); mbar_init(b_pempty + 8 * i, 1);
+      mbar_init(b_qfull + 8 * i, 1); mbar_init(b_qempty + 8 * i, EPI_WARPS / 2);
+      mbar_init(b_pfull + 8 * i, diag ? EPI_WARPS / 2 : EPI_WARPS); mbar_init(b_pempty + 8 * i, 1);
     }
     mbar_init(b_accfull, 1); mbar_init(b_accempty, EPI_WARPS); mbar_init(b_zfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -375,13 +376,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_kernel(const I8Params
                  static_cast<uint32_t>(p.nchunks * PANEL_BYTES), b_zfull);
       }
       const uint32_t xbytes = static_cast<uint32_t>(p.nchunks * XIMG_BYTES);
+      uint32_t s = 0, e_phase = 1;      // parity of the x_empty completion to wait for (first lap: none)
       for (long long i = 0; i < nu; ++i) {
-        const int s = static_cast<int>(i % p.xstages);
-        if (i >= p.xstages) mbar_wait(b_xempty + 8 * s, static_cast<uint32_t>(((i / p.xstages) - 1) & 1));
+        if (i >= p.xstages) mbar_wait(b_xempty + 8 * s, e_phase);
         mbar_expect_tx(b_xfull + 8 * s, xbytes + UP * 4);
         bulk_g2s(s_xs + s * xbytes, p.Xt + static_cast<size_t>(u_lo + i) * xbytes, xbytes, b_xfull + 8 * s);
         bulk_g2s(s_ys + static_cast<uint32_t>(i & (YSTAGES - 1)) * UP * 4, p.ys + static_cast<size_t>(u_lo + i) * UP, UP * 4,
                  b_xfull + 8 * s);
+        if (++s == static_cast<uint32_t>(p.xstages)) { s = 0; e_phase ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -402,11 +404,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_kernel(const I8Params
     constexpr uint32_t SL = PANEL_BYTES >> 4;                       // descriptor units between digit panels
     uint32_t flush_idx = 0;
 
+    int g_until_flush = p.flush_units;   // units left before the accumulators are folded into fp64
+    bool g_fresh = true;                 // next Gram starts new accumulators
     auto gram = [&](long long j) {
       const uint32_t h = static_cast<uint32_t>(j & 1);
       mbar_wait(b_pfull + 8 * h, static_cast<uint32_t>((j >> 1) & 1));
       tc_fence_after();
-      const uint32_t fresh = ((j % p.flush_units) == 0) ? 0u : 1u;
+      const uint32_t fresh = g_fresh ? 0u : 1u;
+      g_fresh = false;
       const uint32_t pa = pan_lo + h * 4, pb = pa + pb_off;
       if (elected) {
         // weight 2^32 : S2'S2
@@ -426,7 +431,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_kernel(const I8Params
         mma_i8(tmem + TM_ACC2, D(pa + 1 * SL + 2), D(pb + 1 * SL + 2), ID_SS, 1u);
         tc_commit(b_pempty + 8 * h);
       }
-      if (((j + 1) % p.flush_units) == 0 || j == nu - 1) {
+      if (--g_until_flush == 0 || j == nu - 1) {
+        g_until_flush = p.flush_units;
+        g_fresh = true;
         if (elected) tc_commit(b_accfull);
         if (j != nu - 1) {
           mbar_wait(b_accempty, flush_idx & 1);
@@ -438,9 +445,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_kernel(const I8Params
 
     mbar_wait(b_zfull, 0);
     const uint32_t xstride = static_cast<uint32_t>(p.nchunks) * (XIMG_BYTES >> 4);
+    uint32_t s = 0, x_phase = 0;
     for (long long i = 0; i < nu; ++i) {
-      const uint32_t s = static_cast<uint32_t>(i % p.xstages);
-      mbar_wait(b_xfull + 8 * s, static_cast<uint32_t>((i / p.xstages) & 1));
+      mbar_wait(b_xfull + 8 * s, x_phase);
       tc_fence_after();
       for (int P = 0; P < np; ++P) {
         const long long t = i * np + P;
@@ -469,43 +476,50 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_kernel(const I8Params
         }
       }
       if (elected) tc_commit(b_xempty + 8 * s);
+      if (++s == static_cast<uint32_t>(p.xstages)) { s = 0; x_phase ^= 1; }
       if (i >= 1) gram(i - 1);
     }
     gram(nu - 1);
   } else if (warp >= 4) {
     // ================= epilogue warps ===================================================================
     const int ew = warp - 4;
+    const int grp = ew >> 3;            // epilogue group == parity of the distance tiles it consumes == TMEM buffer
     const int lq = ew & 3;              // TMEM lane quarter of this warp (== warp % 4)
-    const int cq = ew >> 2;             // which 16 of the 64 columns (points) of a distance tile
+    const int ch = (ew >> 2) & 1;       // which 32 of the 64 columns (points) of a distance tile
+    const int cq = ew >> 2;             // 0..3: which 32 of the 128 accumulator columns in a flush
     const int L = lq * 32 + lane;       // TMEM lane == active-set row inside the tile
     const uint32_t lane_bits = static_cast<uint32_t>(lq * 32) << 16;
+    const uint32_t q_taddr = tmem + lane_bits + TM_Q0 + grp * UP + ch * 32;
+    const int P = diag ? 0 : grp;       // off-diagonal tiles: group 0 builds panel I, group 1 panel J
+    uint8_t* const pan_base = sm_panel + P * 3 * PANEL_BYTES;
     double bsum = 0.0;
-    uint32_t flush_idx = 0;
+    uint32_t flush_idx = 0, q_phase = 0;
+    int until_flush = p.flush_units;
     bool first_flush = true;
     const bool dbg = DBG && (p.dbg_T != nullptr) && blockIdx.x == 0 && blockIdx.y == 0;
     for (long long i = 0; i < nu; ++i) {
       const uint32_t h = static_cast<uint32_t>(i & 1);
-      if (i >= 2) mbar_wait(b_pempty + 8 * h, static_cast<uint32_t>(((i >> 1) - 1) & 1));
-      for (int P = 0; P < np; ++P) {
-        const long long t = i * np + P;
-        const uint32_t qb = static_cast<uint32_t>(t & 1);
-        mbar_wait(b_qfull + 8 * qb, static_cast<uint32_t>((t >> 1) & 1));
+      if (!diag || h == static_cast<uint32_t>(grp)) {
+        // ---- one distance tile (128 active rows x 64 points) -> three int8 digit panels -------------------
+        if (i >= 2) mbar_wait(b_pempty + 8 * h, static_cast<uint32_t>(((i >> 1) - 1) & 1));
+        mbar_wait(b_qfull + 8 * grp, q_phase);
+        q_phase ^= 1;
         tc_fence_after();
-        uint32_t T[16];
-        tmem_ld16(tmem + lane_bits + TM_Q0 + qb * UP + cq * 16, T);
+        uint32_t T[32];
+        tmem_ld32(q_taddr, T);
         tmem_wait_ld();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(b_qempty + 8 * qb);
+        if (lane == 0) mbar_arrive(b_qempty + 8 * grp);
         if (DBG && dbg && i == 0 && P == 0) {
-          for (int k = 0; k < 16; ++k) p.dbg_T[L * UP + cq * 16 + k] = __uint_as_float(T[k]);
+          for (int k = 0; k < 32; ++k) p.dbg_T[L * UP + ch * 32 + k] = __uint_as_float(T[k]);
         }
         // kappa = 2^T ; fixed point: mantissa(kappa*C0 + MAGIC) = u + 0x8080
         if (diag) {
-          const float4* yv = reinterpret_cast<const float4*>(sm_ys + static_cast<int>(i & (YSTAGES - 1)) * UP + cq * 16);
+          const float4* yv = reinterpret_cast<const float4*>(sm_ys + static_cast<int>(i & (YSTAGES - 1)) * UP + ch * 32);
           float bacc = 0.f;
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
+          for (int g = 0; g < 8; ++g) {
             const float4 y4 = yv[g];
             const float e0 = ex2f(__uint_as_float(T[4 * g + 0])), e1 = ex2f(__uint_as_float(T[4 * g + 1])),
                         e2 = ex2f(__uint_as_float(T[4 * g + 2])), e3 = ex2f(__uint_as_float(T[4 * g + 3]));
@@ -517,33 +531,38 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_kernel(const I8Params
           bsum += static_cast<double>(bacc);
         } else {
 #pragma unroll
-          for (int k = 0; k < 16; ++k) T[k] = __float_as_uint(fmaf(ex2f(__uint_as_float(T[k])), C0, MAGIC));
+          for (int k = 0; k < 32; ++k) T[k] = __float_as_uint(fmaf(ex2f(__uint_as_float(T[k])), C0, MAGIC));
         }
         if (DBG && dbg && i == 0 && P == 0) {
-          for (int k = 0; k < 16; ++k) p.dbg_w[L * UP + cq * 16 + k] = T[k];
+          for (int k = 0; k < 32; ++k) p.dbg_w[L * UP + ch * 32 + k] = T[k];
         }
         // byte planes: 4 consecutive points -> one word per digit; 16 points -> one 16-byte store per digit
-        uint32_t d0[4], d1[4], d2[4];
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const uint32_t w0 = T[g * 4 + 0], w1 = T[g * 4 + 1], w2 = T[g * 4 + 2], w3 = T[g * 4 + 3];
-          const uint32_t t01 = prmt(w0, w1, 0x5140), t23 = prmt(w2, w3, 0x5140);
-          d0[g] = prmt(t01, t23, 0x5410) ^ 0x80808080u;     // s0 = byte0 - 128 (two's complement)
-          d1[g] = prmt(t01, t23, 0x7632) ^ 0x80808080u;     // s1 = byte1 - 128
-          const uint32_t u01 = prmt(w0, w1, 0x0062), u23 = prmt(w2, w3, 0x0062);
-          d2[g] = prmt(u01, u23, 0x5410);                   // s2 = byte2 (0..127)
+        for (int g16 = 0; g16 < 2; ++g16) {
+          uint32_t d0[4], d1[4], d2[4];
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const uint32_t w0 = T[g16 * 16 + g * 4 + 0], w1 = T[g16 * 16 + g * 4 + 1], w2 = T[g16 * 16 + g * 4 + 2],
+                           w3 = T[g16 * 16 + g * 4 + 3];
+            const uint32_t t01 = prmt(w0, w1, 0x5140), t23 = prmt(w2, w3, 0x5140);
+            d0[g] = prmt(t01, t23, 0x5410) ^ 0x80808080u;     // s0 = byte0 - 128 (two's complement)
+            d1[g] = prmt(t01, t23, 0x7632) ^ 0x80808080u;     // s1 = byte1 - 128
+            const uint32_t u01 = prmt(w0, w1, 0x0062), u23 = prmt(w2, w3, 0x0062);
+            d2[g] = prmt(u01, u23, 0x5410);                   // s2 = byte2 (0..127)
+          }
+          uint8_t* dst = pan_base + sw128_off(L, static_cast<int>(h * 4 + ch * 2 + g16));
+          *reinterpret_cast<uint4*>(dst + 0 * PANEL_BYTES) = make_uint4(d0[0], d0[1], d0[2], d0[3]);
+          *reinterpret_cast<uint4*>(dst + 1 * PANEL_BYTES) = make_uint4(d1[0], d1[1], d1[2], d1[3]);
+          *reinterpret_cast<uint4*>(dst + 2 * PANEL_BYTES) = make_uint4(d2[0], d2[1], d2[2], d2[3]);
         }
-        uint8_t* pan = sm_panel + P * 3 * PANEL_BYTES + sw128_off(L, static_cast<int>(h * 4 + cq));
-        *reinterpret_cast<uint4*>(pan + 0 * PANEL_BYTES) = make_uint4(d0[0], d0[1], d0[2], d0[3]);
-        *reinterpret_cast<uint4*>(pan + 1 * PANEL_BYTES) = make_uint4(d1[0], d1[1], d1[2], d1[3]);
-        *reinterpret_cast<uint4*>(pan + 2 * PANEL_BYTES) = make_uint4(d2[0], d2[1], d2[2], d2[3]);
+        fence_proxy_async();             // generic-proxy panel writes -> visible to the tensor core (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(b_pfull + 8 * h);
       }
-      fence_proxy_async();               // generic-proxy panel writes -> visible to the tensor core (async proxy)
-      __syncwarp();
-      if (lane == 0) mbar_arrive(b_pfull + 8 * h);
 
-      if (((i + 1) % p.flush_units) == 0 || i == nu - 1) {
-        // ---- fold the exact int32 accumulators into the fp64 partial tile --------------------------------
+      if (--until_flush == 0 || i == nu - 1) {
+        until_flush = p.flush_units;
+        // ---- fold the exact int32 accumulators into the fp64 partial tile (all 16 warps) -----------------
         mbar_wait(b_accfull, flush_idx & 1);
         tc_fence_after();
         double* grow = Gp + static_cast<size_t>(ti * kTile + L) * p.m_pad + tj * kTile;
@@ -581,7 +600,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_kernel(const I8Params
       }
     }
     if (diag) {
-      sm_bred[cq * 128 + L] = bsum;
+      sm_bred[cq * 128 + L] = bsum;      // (group, column half) -> 4 partial sums per row
       asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
       if (cq == 0) bp[ti * kTile + L] = p.bscale * (sm_bred[L] + sm_bred[128 + L] + sm_bred[256 + L] + sm_bred[384 + L]);
     }
