@@ -446,11 +446,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_kernel(const I8Params
     mbar_wait(b_zfull, 0);
     const uint32_t xstride = static_cast<uint32_t>(p.nchunks) * (XIMG_BYTES >> 4);
     uint32_t s = 0, x_phase = 0;
-    for (long long i = 0; i < nu; ++i) {
+    long long t_next = 0;                // index of the next distance tile
+    auto dist = [&](long long) {
       mbar_wait(b_xfull + 8 * s, x_phase);
       tc_fence_after();
       for (int P = 0; P < np; ++P) {
-        const long long t = i * np + P;
+        const long long t = t_next++;
         const uint32_t qb = static_cast<uint32_t>(t & 1);
         if (t >= 2) {
           mbar_wait(b_qempty + 8 * qb, static_cast<uint32_t>(((t >> 1) - 1) & 1));
@@ -459,7 +460,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_kernel(const I8Params
         const uint32_t d_tmem = tmem + TM_Q0 + qb * UP;
         const uint32_t a0 = zt_lo + static_cast<uint32_t>(P * p.nchunks) * SL, b0 = xs_lo + s * xstride;
         if (elected) {
-          // chunk 0 always has 4 k-steps unless it is also the last chunk
           const int nks0 = (p.nchunks == 1) ? p.ksteps_last : 4;
           mma_f16(d_tmem, D(a0), D(b0), IDESC_D, 0u);
           if (nks0 > 1) mma_f16(d_tmem, D(a0 + 2), D(b0 + 2), IDESC_D, 1u);
@@ -477,7 +477,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_kernel(const I8Params
       }
       if (elected) tc_commit(b_xempty + 8 * s);
       if (++s == static_cast<uint32_t>(p.xstages)) { s = 0; x_phase ^= 1; }
-      if (i >= 1) gram(i - 1);
+    };
+    // Issue order: the (short, latency-critical) distance MMAs of unit i+1 go into the tensor FIFO BEFORE the
+    // 12 Gram MMAs of unit i-1, so the epilogue's next input never queues behind 768 clk of Gram work.  At an
+    // accumulator-fold boundary the Gram goes first (the epilogue cannot free a distance buffer while it waits
+    // for the fold).
+    dist(0);
+    for (long long i = 0; i < nu; ++i) {
+      const bool fold_prev = (i >= 1) && (g_until_flush == 1);
+      if (i >= 1 && fold_prev) gram(i - 1);
+      if (i + 1 < nu) dist(i + 1);
+      if (i >= 1 && !fold_prev) gram(i - 1);
     }
     gram(nu - 1);
   } else if (warp >= 4) {
@@ -501,7 +511,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_kernel(const I8Params
       const uint32_t h = static_cast<uint32_t>(i & 1);
       if (!diag || h == static_cast<uint32_t>(grp)) {
         // ---- one distance tile (128 active rows x 64 points) -> three int8 digit panels -------------------
-        if (i >= 2) mbar_wait(b_pempty + 8 * h, static_cast<uint32_t>(((i >> 1) - 1) & 1));
         mbar_wait(b_qfull + 8 * grp, q_phase);
         q_phase ^= 1;
         tc_fence_after();
@@ -536,6 +545,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_kernel(const I8Params
         if (DBG && dbg && i == 0 && P == 0) {
           for (int k = 0; k < 32; ++k) p.dbg_w[L * UP + ch * 32 + k] = T[k];
         }
+        // the Gram MMAs that read this half of the panels two units ago must have drained before we overwrite it
+        if (i >= 2) mbar_wait(b_pempty + 8 * h, static_cast<uint32_t>(((i >> 1) - 1) & 1));
         // byte planes: 4 consecutive points -> one word per digit; 16 points -> one 16-byte store per digit
 #pragma unroll
         for (int g16 = 0; g16 < 2; ++g16) {
