@@ -116,7 +116,7 @@ static int launch_stats(Ctx* c, const void* dX, int x_is_f32, const double* dy, 
   SGP_CUDA(c, cudaEventRecord(e0, c->stream));
   if (use_i8)
     SGP_CUDA(c, launch_gram_i8(c->dI8Xt, c->dI8Ys, c->dI8Zt, n, c->d, c->m_pad, n_slices, c->dGpart, c->dBpart,
-                               c->kf.scale[0], c->dbgT, c->dbgW, c->stream));
+                               c->kf.scale[0], c->dbgT, c->dbgW, c->dbgClk, c->stream));
   else
     SGP_CUDA(c, launch_gram_f64(p, c->precision == SGP_PREC_F64_STRICT, c->stream));
   SGP_CUDA(c, cudaEventRecord(e1, c->stream));
@@ -182,7 +182,7 @@ int sgp_ctx_destroy(sgp_ctx* h) {
   for (auto& e : c->user_events) if (e) cudaEventDestroy(e);
   free_active_set(c);
   cudaFree(c->dGpart); cudaFree(c->dBpart);
-  cudaFree(c->dI8Xt); cudaFree(c->dI8Ys); cudaFree(c->dbgT); cudaFree(c->dbgW);
+  cudaFree(c->dI8Xt); cudaFree(c->dI8Ys); cudaFree(c->dbgT); cudaFree(c->dbgW); cudaFree(c->dbgClk);
   for (int i = 0; i < 2; ++i) {
     cudaFree(c->stageX[i]); cudaFree(c->stageY[i]);
     if (c->stage_free[i]) cudaEventDestroy(c->stage_free[i]);
@@ -460,10 +460,22 @@ int sgp_debug_i8_tile(sgp_ctx* h, float* T_out, uint32_t* w_out) {
     SGP_CUDA(c, cudaMalloc(&c->dbgW, 128 * 64 * 4));
     SGP_CUDA(c, cudaMemset(c->dbgT, 0, 128 * 64 * 4));
     SGP_CUDA(c, cudaMemset(c->dbgW, 0, 128 * 64 * 4));
+    SGP_CUDA(c, cudaMalloc(&c->dbgClk, 3 * 32 * 8 * 8));
+    SGP_CUDA(c, cudaMemset(c->dbgClk, 0, 3 * 32 * 8 * 8));
   }
   SGP_CUDA(c, cudaStreamSynchronize(c->stream));
   if (T_out) SGP_CUDA(c, cudaMemcpy(T_out, c->dbgT, 128 * 64 * 4, cudaMemcpyDeviceToHost));
   if (w_out) SGP_CUDA(c, cudaMemcpy(w_out, c->dbgW, 128 * 64 * 4, cudaMemcpyDeviceToHost));
+  return SGP_OK;
+}
+
+int sgp_debug_i8_timeline(sgp_ctx* h, long long* out) {
+  Ctx* c = reinterpret_cast<Ctx*>(h);
+  if (!c || !out) return SGP_E_BADARG;
+  if (!c->dbgClk) return fail(c, SGP_E_STATE, "arm with sgp_debug_i8_tile first");
+  SGP_CUDA(c, cudaSetDevice(c->device));
+  SGP_CUDA(c, cudaStreamSynchronize(c->stream));
+  SGP_CUDA(c, cudaMemcpy(out, c->dbgClk, 3 * 32 * 8 * 8, cudaMemcpyDeviceToHost));
   return SGP_OK;
 }
 

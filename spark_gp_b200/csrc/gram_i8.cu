@@ -295,7 +295,14 @@ struct I8Params {
   double bscale;        // C
   float* dbg_T;         // optional [128*64] : T of the first distance tile of CTA (0,0)
   uint32_t* dbg_w;      // optional [128*64] : fixed-point words of the same tile
+  long long* dbg_clk;   // optional [3 roles][32 units][8 events] clock64 timeline of CTA (1,0), units 64..95
 };
+
+#define SGP_TL(role, unit, ev)                                                                        \
+  do {                                                                                                \
+    if (DBG && tl && (unit) >= 64 && (unit) < 96 && lane == 0)                                        \
+      p.dbg_clk[((role) * 32 + static_cast<int>((unit) - 64)) * 8 + (ev)] = clock64();               \
+  } while (0)
 
 template <bool DBG>
 __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_kernel(const I8Params p) {
@@ -319,6 +326,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_kernel(const I8Params
   volatile uint32_t* sm_tmem = reinterpret_cast<volatile uint32_t*>(sm + (s_tmem - base));
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool tl = DBG && p.dbg_clk != nullptr && blockIdx.x == 1 && blockIdx.y == 0;   // timeline CTA (off-diagonal)
 
   int ti, tj;
   {
@@ -408,7 +416,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_kernel(const I8Params
     bool g_fresh = true;                 // next Gram starts new accumulators
     auto gram = [&](long long j) {
       const uint32_t h = static_cast<uint32_t>(j & 1);
+      SGP_TL(0, j, 3);
       mbar_wait(b_pfull + 8 * h, static_cast<uint32_t>((j >> 1) & 1));
+      SGP_TL(0, j, 4);
       tc_fence_after();
       const uint32_t fresh = g_fresh ? 0u : 1u;
       g_fresh = false;
@@ -431,6 +441,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_kernel(const I8Params
         mma_i8(tmem + TM_ACC2, D(pa + 1 * SL + 2), D(pb + 1 * SL + 2), ID_SS, 1u);
         tc_commit(b_pempty + 8 * h);
       }
+      SGP_TL(0, j, 5);
       if (--g_until_flush == 0 || j == nu - 1) {
         g_until_flush = p.flush_units;
         g_fresh = true;
@@ -447,8 +458,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_kernel(const I8Params
     const uint32_t xstride = static_cast<uint32_t>(p.nchunks) * (XIMG_BYTES >> 4);
     uint32_t s = 0, x_phase = 0;
     long long t_next = 0;                // index of the next distance tile
-    auto dist = [&](long long) {
+    auto dist = [&](long long iu) {
+      SGP_TL(0, iu, 0);
       mbar_wait(b_xfull + 8 * s, x_phase);
+      SGP_TL(0, iu, 1);
       tc_fence_after();
       for (int P = 0; P < np; ++P) {
         const long long t = t_next++;
@@ -477,6 +490,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_kernel(const I8Params
       }
       if (elected) tc_commit(b_xempty + 8 * s);
       if (++s == static_cast<uint32_t>(p.xstages)) { s = 0; x_phase ^= 1; }
+      SGP_TL(0, iu, 2);
     };
     // Issue order: the (short, latency-critical) distance MMAs of unit i+1 go into the tensor FIFO BEFORE the
     // 12 Gram MMAs of unit i-1, so the epilogue's next input never queues behind 768 clk of Gram work.  At an
@@ -511,12 +525,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_kernel(const I8Params
       const uint32_t h = static_cast<uint32_t>(i & 1);
       if (!diag || h == static_cast<uint32_t>(grp)) {
         // ---- one distance tile (128 active rows x 64 points) -> three int8 digit panels -------------------
+        const bool tle = tl && (ew & 7) == 0;
+        if (tle) SGP_TL(1 + grp, i, 0);
         mbar_wait(b_qfull + 8 * grp, q_phase);
+        if (tle) SGP_TL(1 + grp, i, 1);
         q_phase ^= 1;
         tc_fence_after();
         uint32_t T[32];
         tmem_ld32(q_taddr, T);
         tmem_wait_ld();
+        if (tle) SGP_TL(1 + grp, i, 2);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(b_qempty + 8 * grp);
@@ -546,7 +564,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_kernel(const I8Params
           for (int k = 0; k < 32; ++k) p.dbg_w[L * UP + ch * 32 + k] = T[k];
         }
         // the Gram MMAs that read this half of the panels two units ago must have drained before we overwrite it
+        if (tle) SGP_TL(1 + grp, i, 3);
         if (i >= 2) mbar_wait(b_pempty + 8 * h, static_cast<uint32_t>(((i >> 1) - 1) & 1));
+        if (tle) SGP_TL(1 + grp, i, 4);
         // byte planes: 4 consecutive points -> one word per digit; 16 points -> one 16-byte store per digit
 #pragma unroll
         for (int g16 = 0; g16 < 2; ++g16) {
@@ -569,6 +589,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_kernel(const I8Params
         fence_proxy_async();             // generic-proxy panel writes -> visible to the tensor core (async proxy)
         __syncwarp();
         if (lane == 0) mbar_arrive(b_pfull + 8 * h);
+        if (tle) SGP_TL(1 + grp, i, 5);
       }
 
       if (--until_flush == 0 || i == nu - 1) {
@@ -661,7 +682,7 @@ cudaError_t launch_i8_prep_points(uint8_t* Xt, float* ys, const void* dX, int x_
 
 cudaError_t launch_gram_i8(const uint8_t* Xt, const float* ys, const uint8_t* Zt, long long n, int d, int m_pad,
                            int n_slices, double* Gpart, double* bpart, double C, float* dbg_T, uint32_t* dbg_w,
-                           cudaStream_t s) {
+                           long long* dbg_clk, cudaStream_t s) {
   I8Params p{};
   const int dp = (d + 15) / 16 * 16;
   p.Xt = Xt; p.ys = ys; p.Zt = Zt;
@@ -673,7 +694,7 @@ cudaError_t launch_gram_i8(const uint8_t* Xt, const float* ys, const uint8_t* Zt
   p.Gpart = Gpart; p.bpart = bpart;
   p.gscale = C * C / (static_cast<double>(C0) * static_cast<double>(C0));
   p.bscale = C;
-  p.dbg_T = dbg_T; p.dbg_w = dbg_w;
+  p.dbg_T = dbg_T; p.dbg_w = dbg_w; p.dbg_clk = dbg_clk;
   p.xstages = (p.nchunks == 1) ? 4 : 3;
   const size_t smem = 1024 + 6 * PANEL_BYTES + 2 * p.nchunks * PANEL_BYTES + p.xstages * p.nchunks * XIMG_BYTES +
                       YSTAGES * UP * 4 + 4 * 128 * 8 + 256;

@@ -92,6 +92,7 @@ struct Ctx {
   cudaEvent_t user_events[8] = {nullptr};
   float* dbgT = nullptr;       // sgp_debug_i8_tile
   uint32_t* dbgW = nullptr;
+  long long* dbgClk = nullptr; // [3][32][8] clock64 timeline
 };
 
 // error helpers ---------------------------------------------------------------------------------
@@ -132,7 +133,7 @@ cudaError_t launch_i8_prep_points(uint8_t* Xt, float* ys, const void* dX, int x_
                                   int d, const double* dScale, const double* dCentre, int* dFlags, cudaStream_t s);
 cudaError_t launch_gram_i8(const uint8_t* Xt, const float* ys, const uint8_t* Zt, long long n, int d, int m_pad,
                            int n_slices, double* Gpart, double* bpart, double C, float* dbg_T, uint32_t* dbg_w,
-                           cudaStream_t s);
+                           long long* dbg_clk, cudaStream_t s);
 
 int run_tail(Ctx* c, double* magic_vector, double* magic_matrix);
 int run_predict(Ctx* c, const double* X, long long n, double* mean_out, double* var_out);

@@ -181,6 +181,11 @@ class ProjectedProcessEngine:
         self._check(self._lib.sgp_debug_i8_tile(self._h, N.ptr(T), N.ptr(w)))
         return T, w
 
+    def debug_i8_timeline(self):
+        out = np.zeros((3, 32, 8), dtype=np.int64)
+        self._check(self._lib.sgp_debug_i8_timeline(self._h, N.ptr(out)))
+        return out
+
     # ---- introspection ---------------------------------------------------------------------------------
     def launch_count(self) -> int:
         return int(self._lib.sgp_launch_count(self._h))
