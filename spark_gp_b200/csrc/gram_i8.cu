@@ -28,6 +28,8 @@
 //                       the int32 accumulators are folded into the fp64 partial tile (no overflow possible).
 #include <cuda_fp16.h>
 
+#include <cstdlib>
+
 #include "sgp_internal.h"
 
 namespace sgp {
@@ -295,6 +297,7 @@ struct I8Params {
   double bscale;        // C
   float* dbg_T;         // optional [128*64] : T of the first distance tile of CTA (0,0)
   uint32_t* dbg_w;      // optional [128*64] : fixed-point words of the same tile
+  int group_skew;       // clk: epilogue group 1 starts this much later than group 0 (0 = in phase)
   long long* dbg_clk;   // optional [3 roles][32 units][8 events] clock64 timeline of CTA (1,0), units 64..95
 };
 
@@ -521,6 +524,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_kernel(const I8Params
     int until_flush = p.flush_units;
     bool first_flush = true;
     const bool dbg = DBG && (p.dbg_T != nullptr) && blockIdx.x == 0 && blockIdx.y == 0;
+    // The two groups are self-clocked loops of equal period.  Started together they hit their barrier waits,
+    // their MUFU phase (XU pipe) and their PRMT phase (ALU pipe) simultaneously, leaving each pipe idle half the
+    // time (timeline: 1040 clk MUFU + 719 clk PRMT + ~500 clk waits per tile).  Skewing group 1 by about half a
+    // tile makes one group's exps overlap the other group's byte shuffles and waits.
+    auto skew = [&]() {
+      if (grp == 1 && !diag && p.group_skew > 0) {
+        const long long t0 = clock64();
+        while (clock64() - t0 < p.group_skew) {}
+      }
+    };
+    skew();
     for (long long i = 0; i < nu; ++i) {
       const uint32_t h = static_cast<uint32_t>(i & 1);
       if (!diag || h == static_cast<uint32_t>(grp)) {
@@ -541,66 +555,51 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_kernel(const I8Params
         if (DBG && dbg && i == 0 && P == 0) {
           for (int k = 0; k < 32; ++k) p.dbg_T[L * UP + ch * 32 + k] = __uint_as_float(T[k]);
         }
-        // kappa = 2^T (MUFU.EX2, XU pipe); fixed point: mantissa(kappa*C0 + MAGIC) = u + 0x8080 (one FFMA);
-        // byte planes: 4 consecutive points -> one word per digit (7 PRMT + 2 LOP, ALU pipe); 16 points -> one
-        // 16-byte store per digit.
-        // Scheduling: measured with exp-then-pack per tile: 1040 clk of pure MUFU phase followed by 719 clk of pure
-        // PRMT phase, all warps in lockstep (ptxas hoists the 32 MUFUs to the front, and a warp issues in order).
-        // To overlap the two pipes the exps of group g+2 are given a TRUE data dependency on the packed top-digit
-        // word of group g: `zero = d2 & 0x80808080` is always 0 (top digit <= 127) but opaque to the compiler, and
-        // T + as_float(zero) = T exactly.  Cost: one LOP3 per 4 points, one FADD per point on the idle FMA pipe.
-        const float4* yv = reinterpret_cast<const float4*>(sm_ys + static_cast<int>(i & (YSTAGES - 1)) * UP + ch * 32);
-        float bacc = 0.f;
-        uint32_t W[3][4];
-        uint32_t d0[4], d1[4], d2[4];
-        float zdep[2] = {0.f, 0.f};           // +0.0f carrying the dependency on group g-2's pack
-        auto stage_a = [&](int g) {           // exps + fixed point of points 4g..4g+3
-          const float z = zdep[g & 1];
-          const float e0 = ex2f(__uint_as_float(T[4 * g + 0]) + z), e1 = ex2f(__uint_as_float(T[4 * g + 1]) + z),
-                      e2 = ex2f(__uint_as_float(T[4 * g + 2]) + z), e3 = ex2f(__uint_as_float(T[4 * g + 3]) + z);
-          if (diag) {
+        // kappa = 2^T ; fixed point: mantissa(kappa*C0 + MAGIC) = u + 0x8080
+        if (diag) {
+          const float4* yv = reinterpret_cast<const float4*>(sm_ys + static_cast<int>(i & (YSTAGES - 1)) * UP + ch * 32);
+          float bacc = 0.f;
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
             const float4 y4 = yv[g];
+            const float e0 = ex2f(__uint_as_float(T[4 * g + 0])), e1 = ex2f(__uint_as_float(T[4 * g + 1])),
+                        e2 = ex2f(__uint_as_float(T[4 * g + 2])), e3 = ex2f(__uint_as_float(T[4 * g + 3]));
             bacc = fmaf(e0, y4.x, bacc); bacc = fmaf(e1, y4.y, bacc);
             bacc = fmaf(e2, y4.z, bacc); bacc = fmaf(e3, y4.w, bacc);
+            T[4 * g + 0] = __float_as_uint(fmaf(e0, C0, MAGIC)); T[4 * g + 1] = __float_as_uint(fmaf(e1, C0, MAGIC));
+            T[4 * g + 2] = __float_as_uint(fmaf(e2, C0, MAGIC)); T[4 * g + 3] = __float_as_uint(fmaf(e3, C0, MAGIC));
           }
-          W[g % 3][0] = __float_as_uint(fmaf(e0, C0, MAGIC)); W[g % 3][1] = __float_as_uint(fmaf(e1, C0, MAGIC));
-          W[g % 3][2] = __float_as_uint(fmaf(e2, C0, MAGIC)); W[g % 3][3] = __float_as_uint(fmaf(e3, C0, MAGIC));
-          if (DBG && dbg && i == 0 && P == 0)
-            for (int k = 0; k < 4; ++k) p.dbg_w[L * UP + ch * 32 + 4 * g + k] = W[g % 3][k];
-        };
-        auto stage_b = [&](int g) {           // byte planes of points 4g..4g+3
-          const uint32_t w0 = W[g % 3][0], w1 = W[g % 3][1], w2 = W[g % 3][2], w3 = W[g % 3][3];
-          const uint32_t t01 = prmt(w0, w1, 0x5140), t23 = prmt(w2, w3, 0x5140);
-          d0[g & 3] = prmt(t01, t23, 0x5410) ^ 0x80808080u;     // s0 = byte0 - 128 (two's complement)
-          d1[g & 3] = prmt(t01, t23, 0x7632) ^ 0x80808080u;     // s1 = byte1 - 128
-          const uint32_t u01 = prmt(w0, w1, 0x0062), u23 = prmt(w2, w3, 0x0062);
-          d2[g & 3] = prmt(u01, u23, 0x5410);                   // s2 = byte2 (0..127)
-          zdep[g & 1] = __uint_as_float(d2[g & 3] & 0x80808080u);
-        };
-        auto store16 = [&](int g16) {
+          bsum += static_cast<double>(bacc);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 32; ++k) T[k] = __float_as_uint(fmaf(ex2f(__uint_as_float(T[k])), C0, MAGIC));
+        }
+        if (DBG && dbg && i == 0 && P == 0) {
+          for (int k = 0; k < 32; ++k) p.dbg_w[L * UP + ch * 32 + k] = T[k];
+        }
+        // the Gram MMAs that read this half of the panels two units ago must have drained before we overwrite it
+        if (tle) SGP_TL(1 + grp, i, 3);
+        if (i >= 2) mbar_wait(b_pempty + 8 * h, static_cast<uint32_t>(((i >> 1) - 1) & 1));
+        if (tle) SGP_TL(1 + grp, i, 4);
+        // byte planes: 4 consecutive points -> one word per digit; 16 points -> one 16-byte store per digit
+#pragma unroll
+        for (int g16 = 0; g16 < 2; ++g16) {
+          uint32_t d0[4], d1[4], d2[4];
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const uint32_t w0 = T[g16 * 16 + g * 4 + 0], w1 = T[g16 * 16 + g * 4 + 1], w2 = T[g16 * 16 + g * 4 + 2],
+                           w3 = T[g16 * 16 + g * 4 + 3];
+            const uint32_t t01 = prmt(w0, w1, 0x5140), t23 = prmt(w2, w3, 0x5140);
+            d0[g] = prmt(t01, t23, 0x5410) ^ 0x80808080u;     // s0 = byte0 - 128 (two's complement)
+            d1[g] = prmt(t01, t23, 0x7632) ^ 0x80808080u;     // s1 = byte1 - 128
+            const uint32_t u01 = prmt(w0, w1, 0x0062), u23 = prmt(w2, w3, 0x0062);
+            d2[g] = prmt(u01, u23, 0x5410);                   // s2 = byte2 (0..127)
+          }
           uint8_t* dst = pan_base + sw128_off(L, static_cast<int>(h * 4 + ch * 2 + g16));
           *reinterpret_cast<uint4*>(dst + 0 * PANEL_BYTES) = make_uint4(d0[0], d0[1], d0[2], d0[3]);
           *reinterpret_cast<uint4*>(dst + 1 * PANEL_BYTES) = make_uint4(d1[0], d1[1], d1[2], d1[3]);
           *reinterpret_cast<uint4*>(dst + 2 * PANEL_BYTES) = make_uint4(d2[0], d2[1], d2[2], d2[3]);
-        };
-        // the Gram MMAs that read this half of the panels two units ago must have drained before we overwrite it
-        // (they were issued a whole unit ago: this wait is normally already satisfied)
-        if (tle) SGP_TL(1 + grp, i, 3);
-        if (i >= 2) mbar_wait(b_pempty + 8 * h, static_cast<uint32_t>(((i >> 1) - 1) & 1));
-        if (tle) SGP_TL(1 + grp, i, 4);
-        stage_a(0);
-        stage_a(1);
-        stage_b(0); stage_a(2);
-        stage_b(1); stage_a(3);
-        stage_b(2); stage_a(4);
-        stage_b(3); stage_a(5);
-        store16(0);
-        stage_b(4); stage_a(6);
-        stage_b(5); stage_a(7);
-        stage_b(6);
-        stage_b(7);
-        store16(1);
-        if (diag) bsum += static_cast<double>(bacc);
+        }
         fence_proxy_async();             // generic-proxy panel writes -> visible to the tensor core (async proxy)
         __syncwarp();
         if (lane == 0) mbar_arrive(b_pfull + 8 * h);
@@ -644,6 +643,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_kernel(const I8Params
         __syncwarp();
         if (lane == 0) mbar_arrive(b_accempty);
         ++flush_idx;
+        skew();
       }
     }
     if (diag) {
@@ -710,6 +710,10 @@ cudaError_t launch_gram_i8(const uint8_t* Xt, const float* ys, const uint8_t* Zt
   p.gscale = C * C / (static_cast<double>(C0) * static_cast<double>(C0));
   p.bscale = C;
   p.dbg_T = dbg_T; p.dbg_w = dbg_w; p.dbg_clk = dbg_clk;
+  {
+    const char* e = getenv("SGP_I8_SKEW");
+    p.group_skew = e ? atoi(e) : 900;
+  }
   p.xstages = (p.nchunks == 1) ? 4 : 3;
   const size_t smem = 1024 + 6 * PANEL_BYTES + 2 * p.nchunks * PANEL_BYTES + p.xstages * p.nchunks * XIMG_BYTES +
                       YSTAGES * UP * 4 + 4 * 128 * 8 + 256;
