@@ -16,13 +16,13 @@
 // 2^0) are zero-mean because the low digits are balanced: ~7e-9 per point relative to full scale.
 //
 // Pipeline of one CTA (owns G tile (I,J), I>=J, 128x128, and a slice of the shard's 64-point units):
-//   warp 0   producer : cp.async.bulk (TMA engine, UBLKCP) of pre-swizzled operand images, 4-stage ring
+//   warp 0   TMEM allocator (512 columns: 3 x 128 int32 accumulators + 2 x 64 distance tiles), then
+//            producer : cp.async.bulk (TMA engine, UBLKCP) of pre-swizzled operand images, 4-stage ring
 //   warp 1   MMA      : one thread issues  (a) distance MMAs  T[128 active x 64 points] (kind::f16, fp32 in
 //                       TMEM): -q*log2(e) as ONE contraction over the fp16 hi/lo split of the scaled,
 //                       centred coordinates with the row/column norms folded in as extra K columns;
 //                       (b) the 12 Gram MMAs (kind::i8) of the previous unit
-//   warp 2   TMEM allocator (512 columns: 3 x 128 int32 accumulators + 2 x 64 distance tiles)
-//   warps 4-11 epilogue: tcgen05.ld T -> ex2 -> fixed point via one FFMA against 2^23 -> byte planes (PRMT)
+//   warps 2-17 epilogue (two groups of 8, one per TMEM distance buffer): tcgen05.ld T -> ex2 -> fixed point via one FFMA against 2^23 -> byte planes (PRMT)
 //                       -> 16-byte stores into the K-major SWIZZLE_128B int8 operand panels in shared memory
 //                       (A/B operands of the Gram MMAs), b += kappa*y on diagonal tiles; every 32768 points
 //                       the int32 accumulators are folded into the fp64 partial tile (no overflow possible).
@@ -41,7 +41,8 @@ constexpr int YSTAGES = 8;               // y ring is deeper than the operand ri
                                         // operand stage of the same unit may already have been recycled
 constexpr int EPI_WARPS = 16;             // two groups of 8 (4 TMEM lane quarters x 2 column halves); group g owns
                                         // the distance tiles with (tile index & 1) == g, i.e. TMEM buffer g
-constexpr int NTHREADS = 128 + EPI_WARPS * 32;
+constexpr int FIRST_EPI_WARP = 2;       // warp 0: TMEM allocator + producer, warp 1: barrier init + MMA issuer
+constexpr int NTHREADS = (FIRST_EPI_WARP + EPI_WARPS) * 32;   // 576 threads -> up to 112 registers each
 constexpr uint32_t TM_ACC4 = 0, TM_ACC3 = 128, TM_ACC2 = 256, TM_Q0 = 384;   // TMEM column map
 constexpr float C0 = 8355000.0f;        // fixed-point scale: u <= C0*(1+8e-5) keeps u + 0x8080 < 2^23
 constexpr float MAGIC = 8388608.0f + 32896.0f;   // 2^23 + 0x8080: mantissa of (kappa*C0 + MAGIC) = u + 0x8080
@@ -368,7 +369,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_kernel(const I8Params
     mbar_init(b_accfull, 1); mbar_init(b_accempty, EPI_WARPS); mbar_init(b_zfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 2) {
+  if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_tmem), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -507,11 +508,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_kernel(const I8Params
       if (i >= 1 && !fold_prev) gram(i - 1);
     }
     gram(nu - 1);
-  } else if (warp >= 4) {
+  } else if (warp >= FIRST_EPI_WARP) {
     // ================= epilogue warps ===================================================================
-    const int ew = warp - 4;
+    const int ew = warp - FIRST_EPI_WARP;
     const int grp = ew >> 3;            // epilogue group == parity of the distance tiles it consumes == TMEM buffer
-    const int lq = ew & 3;              // TMEM lane quarter of this warp (== warp % 4)
+    const int lq = warp & 3;            // TMEM lane quarter a warp may access is fixed by warp % 4
     const int ch = (ew >> 2) & 1;       // which 32 of the 64 columns (points) of a distance tile
     const int cq = ew >> 2;             // 0..3: which 32 of the 128 accumulator columns in a flush
     const int L = lq * 32 + lane;       // TMEM lane == active-set row inside the tile
@@ -524,89 +525,127 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_kernel(const I8Params
     int until_flush = p.flush_units;
     bool first_flush = true;
     const bool dbg = DBG && (p.dbg_T != nullptr) && blockIdx.x == 0 && blockIdx.y == 0;
-    // The two groups are self-clocked loops of equal period.  Started together they hit their barrier waits,
-    // their MUFU phase (XU pipe) and their PRMT phase (ALU pipe) simultaneously, leaving each pipe idle half the
-    // time (timeline: 1040 clk MUFU + 719 clk PRMT + ~500 clk waits per tile).  Skewing group 1 by about half a
-    // tile makes one group's exps overlap the other group's byte shuffles and waits.
-    auto skew = [&]() {
-      if (grp == 1 && !diag && p.group_skew > 0) {
-        const long long t0 = clock64();
-        while (clock64() - t0 < p.group_skew) {}
+    const bool tle = tl && (ew & 7) == 0;
+    const bool tle2 = tl && (ew & 7) == 4;   // a lagging warp of the same group (timeline slot 6,7)
+
+    // Per tile and thread: 32 x { kappa = 2^T (MUFU.EX2, XU pipe); mantissa(kappa*C0 + MAGIC) = u + 0x8080 (FFMA) },
+    // then byte planes: 4 consecutive points -> one word per digit (7 PRMT + 2 LOP, ALU pipe), 16 points -> one
+    // 16-byte store per digit.  A warp issues in order and ptxas hoists the 32 MUFUs to the front, so a warp has an
+    // XU phase (~1040 clk with all 16 warps in it) followed by an ALU phase (~720 clk) -- measured, all warps in
+    // lockstep, each pipe idle half the time.  To overlap the pipes the column-half-1 warps of every group run one
+    // tile behind on the ALU side: when tile k arrives they first pack/store their words of tile k-1 (ALU) and only
+    // then load tile k and do its exps (XU), while the column-half-0 warps do exps of tile k first and pack after.
+    const bool lag = !diag && (ch == 1);
+    uint32_t Wold[32];
+    bool have_old = false;
+    long long i_old = 0;
+
+    auto exps = [&](uint32_t (&T)[32], long long iu) {
+      if (diag) {
+        const float4* yv = reinterpret_cast<const float4*>(sm_ys + static_cast<int>(iu & (YSTAGES - 1)) * UP + ch * 32);
+        float bacc = 0.f;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const float4 y4 = yv[g];
+          const float e0 = ex2f(__uint_as_float(T[4 * g + 0])), e1 = ex2f(__uint_as_float(T[4 * g + 1])),
+                      e2 = ex2f(__uint_as_float(T[4 * g + 2])), e3 = ex2f(__uint_as_float(T[4 * g + 3]));
+          bacc = fmaf(e0, y4.x, bacc); bacc = fmaf(e1, y4.y, bacc);
+          bacc = fmaf(e2, y4.z, bacc); bacc = fmaf(e3, y4.w, bacc);
+          T[4 * g + 0] = __float_as_uint(fmaf(e0, C0, MAGIC)); T[4 * g + 1] = __float_as_uint(fmaf(e1, C0, MAGIC));
+          T[4 * g + 2] = __float_as_uint(fmaf(e2, C0, MAGIC)); T[4 * g + 3] = __float_as_uint(fmaf(e3, C0, MAGIC));
+        }
+        bsum += static_cast<double>(bacc);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 32; ++k) T[k] = __float_as_uint(fmaf(ex2f(__uint_as_float(T[k])), C0, MAGIC));
       }
     };
-    skew();
+    auto pack_store = [&](const uint32_t (&W)[32], uint32_t hh) {   // 32 points of this row -> 3 digits x 2 x 16 bytes
+#pragma unroll
+      for (int g16 = 0; g16 < 2; ++g16) {
+        uint32_t d0[4], d1[4], d2[4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const uint32_t w0 = W[g16 * 16 + g * 4 + 0], w1 = W[g16 * 16 + g * 4 + 1], w2 = W[g16 * 16 + g * 4 + 2],
+                         w3 = W[g16 * 16 + g * 4 + 3];
+          const uint32_t t01 = prmt(w0, w1, 0x5140), t23 = prmt(w2, w3, 0x5140);
+          d0[g] = prmt(t01, t23, 0x5410) ^ 0x80808080u;     // s0 = byte0 - 128 (two's complement)
+          d1[g] = prmt(t01, t23, 0x7632) ^ 0x80808080u;     // s1 = byte1 - 128
+          const uint32_t u01 = prmt(w0, w1, 0x0062), u23 = prmt(w2, w3, 0x0062);
+          d2[g] = prmt(u01, u23, 0x5410);                   // s2 = byte2 (0..127)
+        }
+        uint8_t* dst = pan_base + sw128_off(L, static_cast<int>(hh * 4 + ch * 2 + g16));
+        *reinterpret_cast<uint4*>(dst + 0 * PANEL_BYTES) = make_uint4(d0[0], d0[1], d0[2], d0[3]);
+        *reinterpret_cast<uint4*>(dst + 1 * PANEL_BYTES) = make_uint4(d1[0], d1[1], d1[2], d1[3]);
+        *reinterpret_cast<uint4*>(dst + 2 * PANEL_BYTES) = make_uint4(d2[0], d2[1], d2[2], d2[3]);
+      }
+    };
+    auto publish = [&](uint32_t hh) {    // this warp's part of panel half hh is complete
+      fence_proxy_async();               // generic-proxy panel writes -> visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(b_pfull + 8 * hh);
+    };
+    auto wait_panel_free = [&](long long iu) {   // the Gram of unit iu-2 (same panel half) has drained
+      if (iu >= 2) mbar_wait(b_pempty + 8 * static_cast<uint32_t>(iu & 1), static_cast<uint32_t>(((iu >> 1) - 1) & 1));
+    };
+    auto load_tile = [&](uint32_t (&T)[32]) {
+      tc_fence_after();
+      tmem_ld32(q_taddr, T);
+      tmem_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(b_qempty + 8 * grp);
+    };
+
     for (long long i = 0; i < nu; ++i) {
-      const uint32_t h = static_cast<uint32_t>(i & 1);
-      if (!diag || h == static_cast<uint32_t>(grp)) {
-        // ---- one distance tile (128 active rows x 64 points) -> three int8 digit panels -------------------
-        const bool tle = tl && (ew & 7) == 0;
+      if (!diag || static_cast<int>(i & 1) == grp) {
+        // ---- one distance tile (128 active rows x 64 points) ------------------------------------------------
         if (tle) SGP_TL(1 + grp, i, 0);
         mbar_wait(b_qfull + 8 * grp, q_phase);
         if (tle) SGP_TL(1 + grp, i, 1);
         q_phase ^= 1;
-        tc_fence_after();
-        uint32_t T[32];
-        tmem_ld32(q_taddr, T);
-        tmem_wait_ld();
-        if (tle) SGP_TL(1 + grp, i, 2);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(b_qempty + 8 * grp);
-        if (DBG && dbg && i == 0 && P == 0) {
-          for (int k = 0; k < 32; ++k) p.dbg_T[L * UP + ch * 32 + k] = __uint_as_float(T[k]);
-        }
-        // kappa = 2^T ; fixed point: mantissa(kappa*C0 + MAGIC) = u + 0x8080
-        if (diag) {
-          const float4* yv = reinterpret_cast<const float4*>(sm_ys + static_cast<int>(i & (YSTAGES - 1)) * UP + ch * 32);
-          float bacc = 0.f;
-#pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            const float4 y4 = yv[g];
-            const float e0 = ex2f(__uint_as_float(T[4 * g + 0])), e1 = ex2f(__uint_as_float(T[4 * g + 1])),
-                        e2 = ex2f(__uint_as_float(T[4 * g + 2])), e3 = ex2f(__uint_as_float(T[4 * g + 3]));
-            bacc = fmaf(e0, y4.x, bacc); bacc = fmaf(e1, y4.y, bacc);
-            bacc = fmaf(e2, y4.z, bacc); bacc = fmaf(e3, y4.w, bacc);
-            T[4 * g + 0] = __float_as_uint(fmaf(e0, C0, MAGIC)); T[4 * g + 1] = __float_as_uint(fmaf(e1, C0, MAGIC));
-            T[4 * g + 2] = __float_as_uint(fmaf(e2, C0, MAGIC)); T[4 * g + 3] = __float_as_uint(fmaf(e3, C0, MAGIC));
-          }
-          bsum += static_cast<double>(bacc);
+        if (!lag) {
+          uint32_t T[32];
+          load_tile(T);
+          if (tle) SGP_TL(1 + grp, i, 2);
+          if (DBG && dbg && i == 0 && P == 0)
+            for (int k = 0; k < 32; ++k) p.dbg_T[L * UP + ch * 32 + k] = __uint_as_float(T[k]);
+          exps(T, i);
+          if (tle) SGP_TL(1 + grp, i, 3);
+          if (DBG && dbg && i == 0 && P == 0)
+            for (int k = 0; k < 32; ++k) p.dbg_w[L * UP + ch * 32 + k] = T[k];
+          wait_panel_free(i);
+          if (tle) SGP_TL(1 + grp, i, 4);
+          pack_store(T, static_cast<uint32_t>(i & 1));
+          publish(static_cast<uint32_t>(i & 1));
+          if (tle) SGP_TL(1 + grp, i, 5);
         } else {
-#pragma unroll
-          for (int k = 0; k < 32; ++k) T[k] = __float_as_uint(fmaf(ex2f(__uint_as_float(T[k])), C0, MAGIC));
-        }
-        if (DBG && dbg && i == 0 && P == 0) {
-          for (int k = 0; k < 32; ++k) p.dbg_w[L * UP + ch * 32 + k] = T[k];
-        }
-        // the Gram MMAs that read this half of the panels two units ago must have drained before we overwrite it
-        if (tle) SGP_TL(1 + grp, i, 3);
-        if (i >= 2) mbar_wait(b_pempty + 8 * h, static_cast<uint32_t>(((i >> 1) - 1) & 1));
-        if (tle) SGP_TL(1 + grp, i, 4);
-        // byte planes: 4 consecutive points -> one word per digit; 16 points -> one 16-byte store per digit
-#pragma unroll
-        for (int g16 = 0; g16 < 2; ++g16) {
-          uint32_t d0[4], d1[4], d2[4];
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const uint32_t w0 = T[g16 * 16 + g * 4 + 0], w1 = T[g16 * 16 + g * 4 + 1], w2 = T[g16 * 16 + g * 4 + 2],
-                           w3 = T[g16 * 16 + g * 4 + 3];
-            const uint32_t t01 = prmt(w0, w1, 0x5140), t23 = prmt(w2, w3, 0x5140);
-            d0[g] = prmt(t01, t23, 0x5410) ^ 0x80808080u;     // s0 = byte0 - 128 (two's complement)
-            d1[g] = prmt(t01, t23, 0x7632) ^ 0x80808080u;     // s1 = byte1 - 128
-            const uint32_t u01 = prmt(w0, w1, 0x0062), u23 = prmt(w2, w3, 0x0062);
-            d2[g] = prmt(u01, u23, 0x5410);                   // s2 = byte2 (0..127)
+          if (have_old) {
+            wait_panel_free(i_old);
+            pack_store(Wold, static_cast<uint32_t>(i_old & 1));
+            publish(static_cast<uint32_t>(i_old & 1));
           }
-          uint8_t* dst = pan_base + sw128_off(L, static_cast<int>(h * 4 + ch * 2 + g16));
-          *reinterpret_cast<uint4*>(dst + 0 * PANEL_BYTES) = make_uint4(d0[0], d0[1], d0[2], d0[3]);
-          *reinterpret_cast<uint4*>(dst + 1 * PANEL_BYTES) = make_uint4(d1[0], d1[1], d1[2], d1[3]);
-          *reinterpret_cast<uint4*>(dst + 2 * PANEL_BYTES) = make_uint4(d2[0], d2[1], d2[2], d2[3]);
+          if (tle2) SGP_TL(1 + grp, i, 6);
+          load_tile(Wold);
+          if (DBG && dbg && i == 0 && P == 0)
+            for (int k = 0; k < 32; ++k) p.dbg_T[L * UP + ch * 32 + k] = __uint_as_float(Wold[k]);
+          exps(Wold, i);
+          if (DBG && dbg && i == 0 && P == 0)
+            for (int k = 0; k < 32; ++k) p.dbg_w[L * UP + ch * 32 + k] = Wold[k];
+          if (tle2) SGP_TL(1 + grp, i, 7);
+          have_old = true;
+          i_old = i;
         }
-        fence_proxy_async();             // generic-proxy panel writes -> visible to the tensor core (async proxy)
-        __syncwarp();
-        if (lane == 0) mbar_arrive(b_pfull + 8 * h);
-        if (tle) SGP_TL(1 + grp, i, 5);
       }
 
-      if (--until_flush == 0 || i == nu - 1) {
+      const bool fold_now = (--until_flush == 0) || (i == nu - 1);
+      if (fold_now && have_old) {        // drain: the Gram of the last tile must run before the fold
+        wait_panel_free(i_old);
+        pack_store(Wold, static_cast<uint32_t>(i_old & 1));
+        publish(static_cast<uint32_t>(i_old & 1));
+        have_old = false;
+      }
+      if (fold_now) {
         until_flush = p.flush_units;
         // ---- fold the exact int32 accumulators into the fp64 partial tile (all 16 warps) -----------------
         mbar_wait(b_accfull, flush_idx & 1);
@@ -643,7 +682,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_kernel(const I8Params
         __syncwarp();
         if (lane == 0) mbar_arrive(b_accempty);
         ++flush_idx;
-        skew();
       }
     }
     if (diag) {
@@ -656,7 +694,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_kernel(const I8Params
   // ---- teardown ----------------------------------------------------------------------------------------
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) {
+  if (warp == 0) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
   }
 }
