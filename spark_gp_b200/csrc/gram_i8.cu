@@ -16,17 +16,16 @@
 // 2^0) are zero-mean because the low digits are balanced: ~7e-9 per point relative to full scale.
 //
 // Pipeline of one CTA (owns G tile (I,J), I>=J, 128x128, and a slice of the shard's 64-point units):
-//   warp 0   TMEM allocator (512 columns: 3 x 128 int32 accumulators + 2 x 64 distance tiles), then
-//            producer : cp.async.bulk (TMA engine, UBLKCP) of pre-swizzled operand images, 4-stage ring
+//   warp 0   producer : cp.async.bulk (TMA engine, UBLKCP) of pre-swizzled operand images, 4-stage ring
 //   warp 1   MMA      : one thread issues  (a) distance MMAs  T[128 active x 64 points] (kind::f16, fp32 in
 //                       TMEM): -q*log2(e) as ONE contraction over the fp16 hi/lo split of the scaled,
 //                       centred coordinates with the row/column norms folded in as extra K columns;
 //                       (b) the 12 Gram MMAs (kind::i8) of the previous unit
-//   warps 2-9   exp warps : tcgen05.ld T -> ex2 (MUFU, XU pipe) -> fixed point via one FFMA against 2^23 ->
-//                tcgen05.st the words back into the same TMEM columns; b += kappa*y on diagonal tiles
-//   warps 10-17 pack warps: tcgen05.ld words -> byte planes (PRMT, ALU pipe) -> 16-byte stores into the K-major
-//                SWIZZLE_128B int8 operand panels in shared memory (A/B operands of the Gram MMAs)
-//   all 16:      every 32768 points the int32 accumulators are folded into the fp64 partial tile (no overflow).
+//   warp 2   TMEM allocator (512 columns: 3 x 128 int32 accumulators + 2 x 64 distance tiles)
+//   warps 4-11 epilogue: tcgen05.ld T -> ex2 -> fixed point via one FFMA against 2^23 -> byte planes (PRMT)
+//                       -> 16-byte stores into the K-major SWIZZLE_128B int8 operand panels in shared memory
+//                       (A/B operands of the Gram MMAs), b += kappa*y on diagonal tiles; every 32768 points
+//                       the int32 accumulators are folded into the fp64 partial tile (no overflow possible).
 #include <cuda_fp16.h>
 
 #include "sgp_internal.h"
@@ -38,9 +37,9 @@ constexpr int UP = 64;                  // points per pipeline unit
 constexpr int XSTAGES_MAX = 4;          // operand ring depth: 4 stages with one K chunk, 3 with two (227 KB limit)
 constexpr int YSTAGES = 8;               // y ring is deeper than the operand ring: the epilogue reads y after the
                                         // operand stage of the same unit may already have been recycled
-constexpr int EPI_WARPS = 16;             // 8 exp warps + 8 pack warps (each 4 TMEM lane quarters x 2 column halves)
-constexpr int FIRST_EPI_WARP = 2;       // warp 0: TMEM allocator + producer, warp 1: barrier init + MMA issuer
-constexpr int NTHREADS = (FIRST_EPI_WARP + EPI_WARPS) * 32;
+constexpr int EPI_WARPS = 16;             // two groups of 8 (4 TMEM lane quarters x 2 column halves); group g owns
+                                        // the distance tiles with (tile index & 1) == g, i.e. TMEM buffer g
+constexpr int NTHREADS = 128 + EPI_WARPS * 32;
 constexpr uint32_t TM_ACC4 = 0, TM_ACC3 = 128, TM_ACC2 = 256, TM_Q0 = 384;   // TMEM column map
 constexpr float C0 = 8355000.0f;        // fixed-point scale: u <= C0*(1+8e-5) keeps u + 0x8080 < 2^23
 constexpr float MAGIC = 8388608.0f + 32896.0f;   // 2^23 + 0x8080: mantissa of (kappa*C0 + MAGIC) = u + 0x8080
@@ -126,18 +125,6 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "r"(taddr)
       : "memory");
 }
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
-      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
-        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
-        "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
-        "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
-      : "memory");
-}
-__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ float ex2f(float x) {
   float y;
@@ -332,7 +319,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_kernel(const I8Params
   const uint32_t s_bar = s_bred + 4 * 128 * 8;                            // mbarriers
   const uint32_t b_xfull = s_bar, b_xempty = s_bar + 8 * XSTAGES_MAX, b_qfull = b_xempty + 8 * XSTAGES_MAX,
                  b_qempty = b_qfull + 16, b_pfull = b_qempty + 16, b_pempty = b_pfull + 16, b_accfull = b_pempty + 16,
-                 b_accempty = b_accfull + 8, b_zfull = b_accempty + 8, b_wfull = b_zfull + 8, s_tmem = b_wfull + 16;
+                 b_accempty = b_accfull + 8, b_zfull = b_accempty + 8, s_tmem = b_zfull + 8;
   uint8_t* sm_panel = sm;
   float* sm_ys = reinterpret_cast<float*>(sm + (s_ys - base));
   double* sm_bred = reinterpret_cast<double*>(sm + (s_bred - base));
@@ -373,13 +360,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_kernel(const I8Params
     for (int s = 0; s < XSTAGES_MAX; ++s) { mbar_init(b_xfull + 8 * s, 1); mbar_init(b_xempty + 8 * s, 1); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(b_qfull + 8 * i, 1); mbar_init(b_qempty + 8 * i, EPI_WARPS / 2);
-      mbar_init(b_wfull + 8 * i, EPI_WARPS / 2);
       mbar_init(b_pfull + 8 * i, diag ? EPI_WARPS / 2 : EPI_WARPS); mbar_init(b_pempty + 8 * i, 1);
     }
     mbar_init(b_accfull, 1); mbar_init(b_accempty, EPI_WARPS); mbar_init(b_zfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 0) {
+  if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_tmem), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -472,156 +458,147 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_kernel(const I8Params
     const uint32_t xstride = static_cast<uint32_t>(p.nchunks) * (XIMG_BYTES >> 4);
     uint32_t s = 0, x_phase = 0;
     long long t_next = 0;                // index of the next distance tile
-    auto dist = [&](long long iu) {
-      SGP_TL(0, iu, 0);
-      mbar_wait(b_xfull + 8 * s, x_phase);
-      SGP_TL(0, iu, 1);
-      tc_fence_after();
-      for (int P = 0; P < np; ++P) {
-        const long long t = t_next++;
-        const uint32_t qb = static_cast<uint32_t>(t & 1);
-        if (t >= 2) {
-          mbar_wait(b_qempty + 8 * qb, static_cast<uint32_t>(((t >> 1) - 1) & 1));
-          tc_fence_after();
-        }
-        const uint32_t d_tmem = tmem + TM_Q0 + qb * UP;
-        const uint32_t a0 = zt_lo + static_cast<uint32_t>(P * p.nchunks) * SL, b0 = xs_lo + s * xstride;
-        if (elected) {
-          const int nks0 = (p.nchunks == 1) ? p.ksteps_last : 4;
-          mma_f16(d_tmem, D(a0), D(b0), IDESC_D, 0u);
-          if (nks0 > 1) mma_f16(d_tmem, D(a0 + 2), D(b0 + 2), IDESC_D, 1u);
-          if (nks0 > 2) mma_f16(d_tmem, D(a0 + 4), D(b0 + 4), IDESC_D, 1u);
-          if (nks0 > 3) mma_f16(d_tmem, D(a0 + 6), D(b0 + 6), IDESC_D, 1u);
-          if (p.nchunks == 2) {
-            const uint32_t a1 = a0 + SL, b1 = b0 + (XIMG_BYTES >> 4);
-            mma_f16(d_tmem, D(a1), D(b1), IDESC_D, 1u);
-            if (p.ksteps_last > 1) mma_f16(d_tmem, D(a1 + 2), D(b1 + 2), IDESC_D, 1u);
-            if (p.ksteps_last > 2) mma_f16(d_tmem, D(a1 + 4), D(b1 + 4), IDESC_D, 1u);
-            if (p.ksteps_last > 3) mma_f16(d_tmem, D(a1 + 6), D(b1 + 6), IDESC_D, 1u);
-          }
-          tc_commit(b_qfull + 8 * qb);
-        }
+    // One distance tile = panel P of unit iu (4..7 kind::f16 MMAs, N = 64 points).
+    auto dist_tile = [&](long long iu, int P) {
+      if (P == 0) {
+        SGP_TL(0, iu, 0);
+        mbar_wait(b_xfull + 8 * s, x_phase);
+        SGP_TL(0, iu, 1);
+        tc_fence_after();
       }
-      if (elected) tc_commit(b_xempty + 8 * s);
-      if (++s == static_cast<uint32_t>(p.xstages)) { s = 0; x_phase ^= 1; }
-      SGP_TL(0, iu, 2);
+      const long long t = t_next++;
+      const uint32_t qb = static_cast<uint32_t>(t & 1);
+      if (t >= 2) {
+        mbar_wait(b_qempty + 8 * qb, static_cast<uint32_t>(((t >> 1) - 1) & 1));
+        tc_fence_after();
+      }
+      const uint32_t d_tmem = tmem + TM_Q0 + qb * UP;
+      const uint32_t a0 = zt_lo + static_cast<uint32_t>(P * p.nchunks) * SL, b0 = xs_lo + s * xstride;
+      if (elected) {
+        const int nks0 = (p.nchunks == 1) ? p.ksteps_last : 4;
+        mma_f16(d_tmem, D(a0), D(b0), IDESC_D, 0u);
+        if (nks0 > 1) mma_f16(d_tmem, D(a0 + 2), D(b0 + 2), IDESC_D, 1u);
+        if (nks0 > 2) mma_f16(d_tmem, D(a0 + 4), D(b0 + 4), IDESC_D, 1u);
+        if (nks0 > 3) mma_f16(d_tmem, D(a0 + 6), D(b0 + 6), IDESC_D, 1u);
+        if (p.nchunks == 2) {
+          const uint32_t a1 = a0 + SL, b1 = b0 + (XIMG_BYTES >> 4);
+          mma_f16(d_tmem, D(a1), D(b1), IDESC_D, 1u);
+          if (p.ksteps_last > 1) mma_f16(d_tmem, D(a1 + 2), D(b1 + 2), IDESC_D, 1u);
+          if (p.ksteps_last > 2) mma_f16(d_tmem, D(a1 + 4), D(b1 + 4), IDESC_D, 1u);
+          if (p.ksteps_last > 3) mma_f16(d_tmem, D(a1 + 6), D(b1 + 6), IDESC_D, 1u);
+        }
+        tc_commit(b_qfull + 8 * qb);
+      }
+      if (P == np - 1) {
+        if (elected) tc_commit(b_xempty + 8 * s);
+        if (++s == static_cast<uint32_t>(p.xstages)) { s = 0; x_phase ^= 1; }
+        SGP_TL(0, iu, 2);
+      }
     };
-    // Issue order: the (short, latency-critical) distance MMAs of unit i+1 go into the tensor FIFO BEFORE the
-    // 12 Gram MMAs of unit i-1, so the epilogue's next input never queues behind 768 clk of Gram work.  At an
-    // accumulator-fold boundary the Gram goes first (the epilogue cannot free a distance buffer while it waits
+    // Issue order per unit:  dist I(i+1) | gram(i-1) | dist J(i+1).
+    // The two epilogue groups (I tiles / J tiles) are self-clocked by the arrival of their tiles; putting the 768-clk
+    // Gram block BETWEEN the two distance tiles in the tensor FIFO runs the groups about half a period out of phase,
+    // so the MUFU phase of one overlaps the PRMT phase (and barrier latencies) of the other.  (Issued back to back,
+    // both groups do their exps, then their byte shuffles, in lockstep: XU and ALU each idle half the time.)
+    // At an accumulator-fold boundary the Gram goes first (the epilogue cannot free a distance buffer while it waits
     // for the fold).
-    dist(0);
+    dist_tile(0, 0);
+    if (np == 2) dist_tile(0, 1);
     for (long long i = 0; i < nu; ++i) {
+      const bool has_next = (i + 1 < nu);
       const bool fold_prev = (i >= 1) && (g_until_flush == 1);
       if (i >= 1 && fold_prev) gram(i - 1);
-      if (i + 1 < nu) dist(i + 1);
+      if (has_next) dist_tile(i + 1, 0);
       if (i >= 1 && !fold_prev) gram(i - 1);
+      if (has_next && np == 2) dist_tile(i + 1, 1);
     }
     gram(nu - 1);
-  } else if (warp >= FIRST_EPI_WARP) {
-    // ================= epilogue: 8 exp warps (XU pipe) + 8 pack warps (ALU pipe / LSU) =======================
-    // Measured with one set of warps doing exp-then-pack: ~1040 clk of pure MUFU phase followed by ~720 clk of pure
-    // PRMT phase per tile, all warps in lockstep (a warp issues in order and ptxas front-loads the MUFUs), i.e. XU
-    // and ALU each idle half the time.  Splitting by function pipelines them one tile apart: the exp warps turn the
-    // distance tile T into fixed-point words IN PLACE in tensor memory (tcgen05.ld -> ex2/FFMA -> tcgen05.st), the
-    // pack warps turn the words of the previous tile into the three int8 digit panels.
-    const int ew = warp - FIRST_EPI_WARP;
-    const bool is_pack = ew >= 8;
-    const int lq = warp & 3;            // TMEM lane quarter a warp may access is fixed by warp % 4
+  } else if (warp >= 4) {
+    // ================= epilogue warps ===================================================================
+    const int ew = warp - 4;
+    const int grp = ew >> 3;            // epilogue group == parity of the distance tiles it consumes == TMEM buffer
+    const int lq = ew & 3;              // TMEM lane quarter of this warp (== warp % 4)
     const int ch = (ew >> 2) & 1;       // which 32 of the 64 columns (points) of a distance tile
-    const int cq = ew >> 2;             // 0..3: which 32 of the 128 accumulator columns in a fold
+    const int cq = ew >> 2;             // 0..3: which 32 of the 128 accumulator columns in a flush
     const int L = lq * 32 + lane;       // TMEM lane == active-set row inside the tile
     const uint32_t lane_bits = static_cast<uint32_t>(lq * 32) << 16;
+    const uint32_t q_taddr = tmem + lane_bits + TM_Q0 + grp * UP + ch * 32;
+    const int P = diag ? 0 : grp;       // off-diagonal tiles: group 0 builds panel I, group 1 panel J
+    uint8_t* const pan_base = sm_panel + P * 3 * PANEL_BYTES;
     double bsum = 0.0;
-    uint32_t flush_idx = 0;
+    uint32_t flush_idx = 0, q_phase = 0;
     int until_flush = p.flush_units;
     bool first_flush = true;
     const bool dbg = DBG && (p.dbg_T != nullptr) && blockIdx.x == 0 && blockIdx.y == 0;
-    const bool tle = tl && (ew & 7) == 0;
-    const int role = is_pack ? 2 : 1;
-
-    long long t = 0;                    // running distance-tile index (np per unit)
     for (long long i = 0; i < nu; ++i) {
-      for (int P = 0; P < np; ++P, ++t) {
-        const uint32_t qb = static_cast<uint32_t>(t & 1);
-        const uint32_t par = static_cast<uint32_t>((t >> 1) & 1);
-        const uint32_t q_taddr = tmem + lane_bits + TM_Q0 + qb * UP + ch * 32;
+      const uint32_t h = static_cast<uint32_t>(i & 1);
+      if (!diag || h == static_cast<uint32_t>(grp)) {
+        // ---- one distance tile (128 active rows x 64 points) -> three int8 digit panels -------------------
+        const bool tle = tl && (ew & 7) == 0;
+        if (tle) SGP_TL(1 + grp, i, 0);
+        mbar_wait(b_qfull + 8 * grp, q_phase);
+        if (tle) SGP_TL(1 + grp, i, 1);
+        q_phase ^= 1;
+        tc_fence_after();
         uint32_t T[32];
-        if (!is_pack) {
-          // ---------- exp warp: T = -q*log2(e)  ->  word = bits(kappa*C0 + MAGIC), kappa = 2^T --------------------
-          if (tle) SGP_TL(role, i, 2 * P);
-          mbar_wait(b_qfull + 8 * qb, par);
-          tc_fence_after();
-          tmem_ld32(q_taddr, T);
-          tmem_wait_ld();
-          if (DBG && dbg && t == 0)
-            for (int k = 0; k < 32; ++k) p.dbg_T[L * UP + ch * 32 + k] = __uint_as_float(T[k]);
-          if (diag) {
-            const float4* yv = reinterpret_cast<const float4*>(sm_ys + static_cast<int>(i & (YSTAGES - 1)) * UP + ch * 32);
-            float bacc = 0.f;
-#pragma unroll
-            for (int g = 0; g < 8; ++g) {
-              const float4 y4 = yv[g];
-              const float e0 = ex2f(__uint_as_float(T[4 * g + 0])), e1 = ex2f(__uint_as_float(T[4 * g + 1])),
-                          e2 = ex2f(__uint_as_float(T[4 * g + 2])), e3 = ex2f(__uint_as_float(T[4 * g + 3]));
-              bacc = fmaf(e0, y4.x, bacc); bacc = fmaf(e1, y4.y, bacc);
-              bacc = fmaf(e2, y4.z, bacc); bacc = fmaf(e3, y4.w, bacc);
-              T[4 * g + 0] = __float_as_uint(fmaf(e0, C0, MAGIC)); T[4 * g + 1] = __float_as_uint(fmaf(e1, C0, MAGIC));
-              T[4 * g + 2] = __float_as_uint(fmaf(e2, C0, MAGIC)); T[4 * g + 3] = __float_as_uint(fmaf(e3, C0, MAGIC));
-            }
-            bsum += static_cast<double>(bacc);
-          } else {
-#pragma unroll
-            for (int k = 0; k < 32; ++k) T[k] = __float_as_uint(fmaf(ex2f(__uint_as_float(T[k])), C0, MAGIC));
-          }
-          if (DBG && dbg && t == 0)
-            for (int k = 0; k < 32; ++k) p.dbg_w[L * UP + ch * 32 + k] = T[k];
-          tmem_st32(q_taddr, T);
-          tmem_wait_st();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(b_wfull + 8 * qb);
-          if (tle) SGP_TL(role, i, 2 * P + 1);
-        } else {
-          // ---------- pack warp: words -> three int8 digit panels (K-major SWIZZLE_128B operand of the Gram MMAs) ----
-          if (tle) SGP_TL(role, i, 4 * P);
-          mbar_wait(b_wfull + 8 * qb, par);
-          tc_fence_after();
-          tmem_ld32(q_taddr, T);
-          tmem_wait_ld();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(b_qempty + 8 * qb);     // the MMA warp may overwrite this distance buffer
-          if (tle) SGP_TL(role, i, 4 * P + 1);
-          const uint32_t h = static_cast<uint32_t>(i & 1);
-          // the Gram MMAs that read this half of the panels two units ago must have drained before we overwrite it
-          if (i >= 2) mbar_wait(b_pempty + 8 * h, static_cast<uint32_t>(((i >> 1) - 1) & 1));
-          if (tle) SGP_TL(role, i, 4 * P + 2);
-          uint8_t* const pan_base = sm_panel + P * 3 * PANEL_BYTES;
-          // byte planes: 4 consecutive points -> one word per digit (7 PRMT + 2 LOP); 16 points -> one 16-byte store
-#pragma unroll
-          for (int g16 = 0; g16 < 2; ++g16) {
-            uint32_t d0[4], d1[4], d2[4];
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const uint32_t w0 = T[g16 * 16 + g * 4 + 0], w1 = T[g16 * 16 + g * 4 + 1], w2 = T[g16 * 16 + g * 4 + 2],
-                             w3 = T[g16 * 16 + g * 4 + 3];
-              const uint32_t t01 = prmt(w0, w1, 0x5140), t23 = prmt(w2, w3, 0x5140);
-              d0[g] = prmt(t01, t23, 0x5410) ^ 0x80808080u;     // s0 = byte0 - 128 (two's complement)
-              d1[g] = prmt(t01, t23, 0x7632) ^ 0x80808080u;     // s1 = byte1 - 128
-              const uint32_t u01 = prmt(w0, w1, 0x0062), u23 = prmt(w2, w3, 0x0062);
-              d2[g] = prmt(u01, u23, 0x5410);                   // s2 = byte2 (0..127)
-            }
-            uint8_t* dst = pan_base + sw128_off(L, static_cast<int>(h * 4 + ch * 2 + g16));
-            *reinterpret_cast<uint4*>(dst + 0 * PANEL_BYTES) = make_uint4(d0[0], d0[1], d0[2], d0[3]);
-            *reinterpret_cast<uint4*>(dst + 1 * PANEL_BYTES) = make_uint4(d1[0], d1[1], d1[2], d1[3]);
-            *reinterpret_cast<uint4*>(dst + 2 * PANEL_BYTES) = make_uint4(d2[0], d2[1], d2[2], d2[3]);
-          }
-          fence_proxy_async();           // generic-proxy panel writes -> visible to the tensor core (async proxy)
-          __syncwarp();
-          if (lane == 0) mbar_arrive(b_pfull + 8 * h);
-          if (tle) SGP_TL(role, i, 4 * P + 3);
+        tmem_ld32(q_taddr, T);
+        tmem_wait_ld();
+        if (tle) SGP_TL(1 + grp, i, 2);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(b_qempty + 8 * grp);
+        if (DBG && dbg && i == 0 && P == 0) {
+          for (int k = 0; k < 32; ++k) p.dbg_T[L * UP + ch * 32 + k] = __uint_as_float(T[k]);
         }
+        // kappa = 2^T ; fixed point: mantissa(kappa*C0 + MAGIC) = u + 0x8080
+        if (diag) {
+          const float4* yv = reinterpret_cast<const float4*>(sm_ys + static_cast<int>(i & (YSTAGES - 1)) * UP + ch * 32);
+          float bacc = 0.f;
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const float4 y4 = yv[g];
+            const float e0 = ex2f(__uint_as_float(T[4 * g + 0])), e1 = ex2f(__uint_as_float(T[4 * g + 1])),
+                        e2 = ex2f(__uint_as_float(T[4 * g + 2])), e3 = ex2f(__uint_as_float(T[4 * g + 3]));
+            bacc = fmaf(e0, y4.x, bacc); bacc = fmaf(e1, y4.y, bacc);
+            bacc = fmaf(e2, y4.z, bacc); bacc = fmaf(e3, y4.w, bacc);
+            T[4 * g + 0] = __float_as_uint(fmaf(e0, C0, MAGIC)); T[4 * g + 1] = __float_as_uint(fmaf(e1, C0, MAGIC));
+            T[4 * g + 2] = __float_as_uint(fmaf(e2, C0, MAGIC)); T[4 * g + 3] = __float_as_uint(fmaf(e3, C0, MAGIC));
+          }
+          bsum += static_cast<double>(bacc);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 32; ++k) T[k] = __float_as_uint(fmaf(ex2f(__uint_as_float(T[k])), C0, MAGIC));
+        }
+        if (DBG && dbg && i == 0 && P == 0) {
+          for (int k = 0; k < 32; ++k) p.dbg_w[L * UP + ch * 32 + k] = T[k];
+        }
+        // the Gram MMAs that read this half of the panels two units ago must have drained before we overwrite it
+        if (tle) SGP_TL(1 + grp, i, 3);
+        if (i >= 2) mbar_wait(b_pempty + 8 * h, static_cast<uint32_t>(((i >> 1) - 1) & 1));
+        if (tle) SGP_TL(1 + grp, i, 4);
+        // byte planes: 4 consecutive points -> one word per digit; 16 points -> one 16-byte store per digit
+#pragma unroll
+        for (int g16 = 0; g16 < 2; ++g16) {
+          uint32_t d0[4], d1[4], d2[4];
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const uint32_t w0 = T[g16 * 16 + g * 4 + 0], w1 = T[g16 * 16 + g * 4 + 1], w2 = T[g16 * 16 + g * 4 + 2],
+                           w3 = T[g16 * 16 + g * 4 + 3];
+            const uint32_t t01 = prmt(w0, w1, 0x5140), t23 = prmt(w2, w3, 0x5140);
+            d0[g] = prmt(t01, t23, 0x5410) ^ 0x80808080u;     // s0 = byte0 - 128 (two's complement)
+            d1[g] = prmt(t01, t23, 0x7632) ^ 0x80808080u;     // s1 = byte1 - 128
+            const uint32_t u01 = prmt(w0, w1, 0x0062), u23 = prmt(w2, w3, 0x0062);
+            d2[g] = prmt(u01, u23, 0x5410);                   // s2 = byte2 (0..127)
+          }
+          uint8_t* dst = pan_base + sw128_off(L, static_cast<int>(h * 4 + ch * 2 + g16));
+          *reinterpret_cast<uint4*>(dst + 0 * PANEL_BYTES) = make_uint4(d0[0], d0[1], d0[2], d0[3]);
+          *reinterpret_cast<uint4*>(dst + 1 * PANEL_BYTES) = make_uint4(d1[0], d1[1], d1[2], d1[3]);
+          *reinterpret_cast<uint4*>(dst + 2 * PANEL_BYTES) = make_uint4(d2[0], d2[1], d2[2], d2[3]);
+        }
+        fence_proxy_async();             // generic-proxy panel writes -> visible to the tensor core (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(b_pfull + 8 * h);
+        if (tle) SGP_TL(1 + grp, i, 5);
       }
 
       if (--until_flush == 0 || i == nu - 1) {
@@ -663,17 +640,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_kernel(const I8Params
         ++flush_idx;
       }
     }
-    if (diag && !is_pack) {              // b: two column halves per row, held by the exp warps
-      sm_bred[ch * 128 + L] = bsum;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (ch == 0) bp[ti * kTile + L] = p.bscale * (sm_bred[L] + sm_bred[128 + L]);
+    if (diag) {
+      sm_bred[cq * 128 + L] = bsum;      // (group, column half) -> 4 partial sums per row
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+      if (cq == 0) bp[ti * kTile + L] = p.bscale * (sm_bred[L] + sm_bred[128 + L] + sm_bred[256 + L] + sm_bred[384 + L]);
     }
   }
 
   // ---- teardown ----------------------------------------------------------------------------------------
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) {
+  if (warp == 2) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
   }
 }

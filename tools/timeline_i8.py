@@ -17,19 +17,16 @@ tl = e.debug_i8_timeline()
 t0 = tl[tl > 0].min()
 tl = np.where(tl > 0, tl - t0, -1)
 names = {0: ["dist:wait_x", "dist:x_ok", "dist:issued", "gram:wait_p", "gram:p_ok", "gram:issued"],
-         1: ["I:start", "I:done", "J:start", "J:done"],
-         2: ["I:start", "I:loaded", "I:pempty_ok", "I:stored", "J:start", "J:loaded", "J:pempty_ok", "J:stored"]}
-for u in range(4, 10):
+         1: ["q_wait", "q_ok", "ld_done", "compute_done", "pempty_ok", "stored"], 2: None}
+names[2] = names[1]
+for u in range(4, 12):
     print("unit %d" % (64 + u))
-    for role, rn in ((0, "MMA "), (1, "EXP "), (2, "PACK")):
-        print("   %s  " % rn + "  ".join("%s=%d" % (names[role][ev], tl[role, u, ev]) for ev in range(len(names[role]))))
-per = np.diff(tl[2, 2:30, 7])
-print("pack 'J stored' period per unit: mean %.0f  min %d max %d" % (per.mean(), per.min(), per.max()))
-a = tl[1, 2:30]
-print("EXP  mean: I tile %.0f  gap %.0f  J tile %.0f" % ((a[:, 1] - a[:, 0]).mean(), (a[:, 2] - a[:, 1]).mean(), (a[:, 3] - a[:, 2]).mean()))
-a = tl[2, 2:30]
-print("PACK mean: I wait+load %.0f  pempty %.0f  pack+store %.0f | J wait+load %.0f pempty %.0f pack+store %.0f" % (
-    (a[:, 1] - a[:, 0]).mean(), (a[:, 2] - a[:, 1]).mean(), (a[:, 3] - a[:, 2]).mean(),
-    (a[:, 5] - a[:, 4]).mean(), (a[:, 6] - a[:, 5]).mean(), (a[:, 7] - a[:, 6]).mean()))
+    for role, rn in ((0, "MMA "), (1, "EPI0"), (2, "EPI1")):
+        print("   %s  " % rn + "  ".join("%s=%d" % (names[role][ev], tl[role, u, ev]) for ev in range(6)))
+per = np.diff(tl[1, 2:30, 5])
+print("epi0 'stored' period per unit: mean %.0f  min %d max %d" % (per.mean(), per.min(), per.max()))
+for role in (1, 2):
+    a = tl[role, 2:30]
+    print("EPI%d mean: q_wait %.0f  ld %.0f  compute %.0f  pempty_wait %.0f  store %.0f" % (role - 1, (a[:, 1] - a[:, 0]).mean(), (a[:, 2] - a[:, 1]).mean(), (a[:, 3] - a[:, 2]).mean(), (a[:, 4] - a[:, 3]).mean(), (a[:, 5] - a[:, 4]).mean()))
 a = tl[0, 2:30]
 print("MMA mean: dist wait_x %.0f  dist issue(+q_empty waits) %.0f   gram wait_p %.0f  gram issue %.0f" % ((a[:, 1] - a[:, 0]).mean(), (a[:, 2] - a[:, 1]).mean(), (a[:, 4] - a[:, 3]).mean(), (a[:, 5] - a[:, 4]).mean()))
