@@ -522,13 +522,77 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_kernel(const I8Params
       }
     };
 
+    // The 12 Gram MMAs of a unit are issued one product (2 MMAs) per scheduler round: the tensor FIFO is shallow and
+    // issuing all 12 blocks the thread ~800 clk (measured), during which freed distance buffers would go unserved.
+    bool g_active = false;
+    int g_step = 0;
+    uint32_t g_fresh_flag = 0, g_pa = 0, g_pb = 0, g_h = 0;
+    auto gram_step = [&]() {
+      if (!g_active) {
+        const long long j = gram_next;
+        if (!mbar_test(b_pfull + 8 * static_cast<uint32_t>(j & 1), static_cast<uint32_t>((j >> 1) & 1))) return;
+        tc_fence_after();
+        SGP_TL(0, j, 4);
+        g_active = true; g_step = 0;
+        g_h = static_cast<uint32_t>(j & 1);
+        g_fresh_flag = g_fresh ? 0u : 1u;
+        g_fresh = false;
+        g_pa = pan_lo + g_h * 4; g_pb = g_pa + pb_off;
+      }
+      if (elected) {
+        switch (g_step) {
+          case 0:   // weight 2^32 : S2'S2
+            mma_i8(tmem + TM_ACC4, D(g_pa + 2 * SL), D(g_pb + 2 * SL), ID_UU, g_fresh_flag);
+            mma_i8(tmem + TM_ACC4, D(g_pa + 2 * SL + 2), D(g_pb + 2 * SL + 2), ID_UU, 1u);
+            break;
+          case 1:   // weight 2^24 : S2'S1 + S1'S2
+            mma_i8(tmem + TM_ACC3, D(g_pa + 2 * SL), D(g_pb + 1 * SL), ID_US, g_fresh_flag);
+            mma_i8(tmem + TM_ACC3, D(g_pa + 2 * SL + 2), D(g_pb + 1 * SL + 2), ID_US, 1u);
+            break;
+          case 2:
+            mma_i8(tmem + TM_ACC3, D(g_pa + 1 * SL), D(g_pb + 2 * SL), ID_SU, 1u);
+            mma_i8(tmem + TM_ACC3, D(g_pa + 1 * SL + 2), D(g_pb + 2 * SL + 2), ID_SU, 1u);
+            break;
+          case 3:   // weight 2^16 : S2'S0 + S0'S2 + S1'S1
+            mma_i8(tmem + TM_ACC2, D(g_pa + 2 * SL), D(g_pb), ID_US, g_fresh_flag);
+            mma_i8(tmem + TM_ACC2, D(g_pa + 2 * SL + 2), D(g_pb + 2), ID_US, 1u);
+            break;
+          case 4:
+            mma_i8(tmem + TM_ACC2, D(g_pa), D(g_pb + 2 * SL), ID_SU, 1u);
+            mma_i8(tmem + TM_ACC2, D(g_pa + 2), D(g_pb + 2 * SL + 2), ID_SU, 1u);
+            break;
+          default:
+            mma_i8(tmem + TM_ACC2, D(g_pa + 1 * SL), D(g_pb + 1 * SL), ID_SS, 1u);
+            mma_i8(tmem + TM_ACC2, D(g_pa + 1 * SL + 2), D(g_pb + 1 * SL + 2), ID_SS, 1u);
+            tc_commit(b_pempty + 8 * g_h);
+            break;
+        }
+      }
+      if (++g_step == 6) {
+        const long long j = gram_next;
+        SGP_TL(0, j, 5);
+        g_active = false;
+        ++gram_next;
+        if (--g_until_flush == 0 || j == nu - 1) {
+          g_until_flush = p.flush_units;
+          g_fresh = true;
+          if (elected) tc_commit(b_accfull);
+          if (j != nu - 1) {
+            mbar_wait(b_accempty, flush_idx & 1);
+            tc_fence_after();
+          }
+          ++flush_idx;
+        }
+      }
+    };
+
     while (gram_next < nu) {
       // operand stages that have landed
       while (x_seen < nu && x_seen < x_committed + p.xstages && mbar_test(b_xfull + 8 * xs_stage, xs_phase)) {
         ++x_seen;
         if (++xs_stage == static_cast<uint32_t>(p.xstages)) { xs_stage = 0; xs_phase ^= 1; }
       }
-      // distance tiles
+      // distance tiles first (short and latency critical)
 #pragma unroll
       for (int g = 0; g < 2; ++g) {
         const long long t = t_iss[g];
@@ -537,11 +601,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_kernel(const I8Params
           if (u < x_seen && (t < 2 || mbar_test(b_qempty + 8 * g, static_cast<uint32_t>(((t >> 1) - 1) & 1)))) issue_tile(g);
         }
       }
-      // Gram blocks (in unit order)
-      if (mbar_test(b_pfull + 8 * static_cast<uint32_t>(gram_next & 1), static_cast<uint32_t>((gram_next >> 1) & 1))) {
-        gram(gram_next);
-        ++gram_next;
-      }
+      // then one product of the pending Gram block
+      gram_step();
     }
   } else if (warp >= 4) {
     // ================= epilogue warps ===================================================================
