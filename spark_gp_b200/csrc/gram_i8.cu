@@ -71,17 +71,6 @@ __device__ __forceinline__ uint32_t mbar_try(uint32_t bar, uint32_t parity) {
       : "memory");
   return done;
 }
-__device__ __forceinline__ uint32_t mbar_test(uint32_t bar, uint32_t parity) {   // non-blocking
-  uint32_t done;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(done)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return done;
-}
 // Bounded spin: a protocol bug must not hang the GPU box -- trap after ~4 s instead.
 __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
   const long long t0 = clock64();
@@ -427,6 +416,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_kernel(const I8Params
     bool g_fresh = true;                 // next Gram starts new accumulators
     auto gram = [&](long long j) {
       const uint32_t h = static_cast<uint32_t>(j & 1);
+      SGP_TL(0, j, 3);
+      mbar_wait(b_pfull + 8 * h, static_cast<uint32_t>((j >> 1) & 1));
       SGP_TL(0, j, 4);
       tc_fence_after();
       const uint32_t fresh = g_fresh ? 0u : 1u;
@@ -467,29 +458,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_kernel(const I8Params
     const uint32_t xstride = static_cast<uint32_t>(p.nchunks) * (XIMG_BYTES >> 4);
     uint32_t s = 0, x_phase = 0;
     long long t_next = 0;                // index of the next distance tile
-    // ---- event-driven issue ----------------------------------------------------------------------------------
-    // Three independent streams feed the tensor FIFO: distance tiles for epilogue group 0 (TMEM buffer 0), distance
-    // tiles for group 1 (buffer 1), and the Gram blocks.  Issuing them in a fixed program order with blocking waits
-    // couples the two epilogue groups (each waits ~500 clk for its next tile behind the other group's barrier); here
-    // the warp polls the barriers (non-blocking test_wait) and issues whichever stream is ready, so the groups run as
-    // free self-clocked loops, out of phase, and XU (exp) work of one overlaps ALU (byte shuffle) work of the other.
-    const long long n_tiles = nu * np;
-    long long t_iss[2] = {0, 1};         // next tile of buffer/group 0 and 1 (tile t uses buffer t & 1)
-    long long x_seen = 0;                // units whose operand stage has landed (x_full observed), in order
-    uint32_t xs_stage = 0, xs_phase = 0; // stage / parity of the next x_full to observe
-    long long x_committed = 0;           // units whose stage has been handed back (x_empty committed)
-    uint32_t xc_stage = 0;
-    long long gram_next = 0;
-    uint32_t st_of[2] = {0, 0};          // operand stage of the unit of t_iss[g]  (np==2: both start at unit 0)
-    if (np == 1) st_of[1] = (p.xstages > 1) ? 1u : 0u;
-
-    auto issue_tile = [&](int g) {
-      const long long t = t_iss[g];
-      const long long u = (np == 2) ? (t >> 1) : t;
-      const int P = (np == 2) ? g : 0;
-      const uint32_t d_tmem = tmem + TM_Q0 + static_cast<uint32_t>(g) * UP;
-      const uint32_t a0 = zt_lo + static_cast<uint32_t>(P * p.nchunks) * SL, b0 = xs_lo + st_of[g] * xstride;
-      tc_fence_after();
+    // One distance tile = panel P of unit iu (4..7 kind::f16 MMAs, N = 64 points).
+    auto dist_tile = [&](long long iu, int P) {
+      if (P == 0) {
+        SGP_TL(0, iu, 0);
+        mbar_wait(b_xfull + 8 * s, x_phase);
+        SGP_TL(0, iu, 1);
+        tc_fence_after();
+      }
+      const long long t = t_next++;
+      const uint32_t qb = static_cast<uint32_t>(t & 1);
+      if (t >= 2) {
+        mbar_wait(b_qempty + 8 * qb, static_cast<uint32_t>(((t >> 1) - 1) & 1));
+        tc_fence_after();
+      }
+      const uint32_t d_tmem = tmem + TM_Q0 + qb * UP;
+      const uint32_t a0 = zt_lo + static_cast<uint32_t>(P * p.nchunks) * SL, b0 = xs_lo + s * xstride;
       if (elected) {
         const int nks0 = (p.nchunks == 1) ? p.ksteps_last : 4;
         mma_f16(d_tmem, D(a0), D(b0), IDESC_D, 0u);
@@ -503,107 +487,32 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_kernel(const I8Params
           if (p.ksteps_last > 2) mma_f16(d_tmem, D(a1 + 4), D(b1 + 4), IDESC_D, 1u);
           if (p.ksteps_last > 3) mma_f16(d_tmem, D(a1 + 6), D(b1 + 6), IDESC_D, 1u);
         }
-        tc_commit(b_qfull + 8 * g);
+        tc_commit(b_qfull + 8 * qb);
       }
-      SGP_TL(0, u, g);                                   // timeline: events 0/1 = tile of group g issued
-      // advance this group's cursor: next tile of the same buffer is 2 tiles later = 1 unit (np==2) or 2 units (np==1)
-      t_iss[g] = t + 2;
-      const uint32_t adv = (np == 2) ? 1u : 2u;
-      st_of[g] += adv;
-      while (st_of[g] >= static_cast<uint32_t>(p.xstages)) st_of[g] -= p.xstages;
-      // hand operand stages back once every tile of a unit has been issued (units complete in order)
-      const long long u0 = (np == 2) ? (t_iss[0] >> 1) : t_iss[0], u1 = (np == 2) ? (t_iss[1] >> 1) : t_iss[1];
-      long long done_units = u0 < u1 ? u0 : u1;
-      if (done_units > nu) done_units = nu;
-      while (x_committed < done_units) {
-        if (elected) tc_commit(b_xempty + 8 * xc_stage);
-        if (++xc_stage == static_cast<uint32_t>(p.xstages)) xc_stage = 0;
-        ++x_committed;
+      if (P == np - 1) {
+        if (elected) tc_commit(b_xempty + 8 * s);
+        if (++s == static_cast<uint32_t>(p.xstages)) { s = 0; x_phase ^= 1; }
+        SGP_TL(0, iu, 2);
       }
     };
-
-    // The 12 Gram MMAs of a unit are issued one product (2 MMAs) per scheduler round: the tensor FIFO is shallow and
-    // issuing all 12 blocks the thread ~800 clk (measured), during which freed distance buffers would go unserved.
-    bool g_active = false;
-    int g_step = 0;
-    uint32_t g_fresh_flag = 0, g_pa = 0, g_pb = 0, g_h = 0;
-    auto gram_step = [&]() {
-      if (!g_active) {
-        const long long j = gram_next;
-        if (!mbar_test(b_pfull + 8 * static_cast<uint32_t>(j & 1), static_cast<uint32_t>((j >> 1) & 1))) return;
-        tc_fence_after();
-        SGP_TL(0, j, 4);
-        g_active = true; g_step = 0;
-        g_h = static_cast<uint32_t>(j & 1);
-        g_fresh_flag = g_fresh ? 0u : 1u;
-        g_fresh = false;
-        g_pa = pan_lo + g_h * 4; g_pb = g_pa + pb_off;
-      }
-      if (elected) {
-        switch (g_step) {
-          case 0:   // weight 2^32 : S2'S2
-            mma_i8(tmem + TM_ACC4, D(g_pa + 2 * SL), D(g_pb + 2 * SL), ID_UU, g_fresh_flag);
-            mma_i8(tmem + TM_ACC4, D(g_pa + 2 * SL + 2), D(g_pb + 2 * SL + 2), ID_UU, 1u);
-            break;
-          case 1:   // weight 2^24 : S2'S1 + S1'S2
-            mma_i8(tmem + TM_ACC3, D(g_pa + 2 * SL), D(g_pb + 1 * SL), ID_US, g_fresh_flag);
-            mma_i8(tmem + TM_ACC3, D(g_pa + 2 * SL + 2), D(g_pb + 1 * SL + 2), ID_US, 1u);
-            break;
-          case 2:
-            mma_i8(tmem + TM_ACC3, D(g_pa + 1 * SL), D(g_pb + 2 * SL), ID_SU, 1u);
-            mma_i8(tmem + TM_ACC3, D(g_pa + 1 * SL + 2), D(g_pb + 2 * SL + 2), ID_SU, 1u);
-            break;
-          case 3:   // weight 2^16 : S2'S0 + S0'S2 + S1'S1
-            mma_i8(tmem + TM_ACC2, D(g_pa + 2 * SL), D(g_pb), ID_US, g_fresh_flag);
-            mma_i8(tmem + TM_ACC2, D(g_pa + 2 * SL + 2), D(g_pb + 2), ID_US, 1u);
-            break;
-          case 4:
-            mma_i8(tmem + TM_ACC2, D(g_pa), D(g_pb + 2 * SL), ID_SU, 1u);
-            mma_i8(tmem + TM_ACC2, D(g_pa + 2), D(g_pb + 2 * SL + 2), ID_SU, 1u);
-            break;
-          default:
-            mma_i8(tmem + TM_ACC2, D(g_pa + 1 * SL), D(g_pb + 1 * SL), ID_SS, 1u);
-            mma_i8(tmem + TM_ACC2, D(g_pa + 1 * SL + 2), D(g_pb + 1 * SL + 2), ID_SS, 1u);
-            tc_commit(b_pempty + 8 * g_h);
-            break;
-        }
-      }
-      if (++g_step == 6) {
-        const long long j = gram_next;
-        SGP_TL(0, j, 5);
-        g_active = false;
-        ++gram_next;
-        if (--g_until_flush == 0 || j == nu - 1) {
-          g_until_flush = p.flush_units;
-          g_fresh = true;
-          if (elected) tc_commit(b_accfull);
-          if (j != nu - 1) {
-            mbar_wait(b_accempty, flush_idx & 1);
-            tc_fence_after();
-          }
-          ++flush_idx;
-        }
-      }
-    };
-
-    while (gram_next < nu) {
-      // operand stages that have landed
-      while (x_seen < nu && x_seen < x_committed + p.xstages && mbar_test(b_xfull + 8 * xs_stage, xs_phase)) {
-        ++x_seen;
-        if (++xs_stage == static_cast<uint32_t>(p.xstages)) { xs_stage = 0; xs_phase ^= 1; }
-      }
-      // distance tiles first (short and latency critical)
-#pragma unroll
-      for (int g = 0; g < 2; ++g) {
-        const long long t = t_iss[g];
-        if (t < n_tiles) {
-          const long long u = (np == 2) ? (t >> 1) : t;
-          if (u < x_seen && (t < 2 || mbar_test(b_qempty + 8 * g, static_cast<uint32_t>(((t >> 1) - 1) & 1)))) issue_tile(g);
-        }
-      }
-      // then one product of the pending Gram block
-      gram_step();
+    // Issue order per unit:  dist I(i+1) | gram(i-1) | dist J(i+1).
+    // The two epilogue groups (I tiles / J tiles) are self-clocked by the arrival of their tiles; putting the 768-clk
+    // Gram block BETWEEN the two distance tiles in the tensor FIFO runs the groups about half a period out of phase,
+    // so the MUFU phase of one overlaps the PRMT phase (and barrier latencies) of the other.  (Issued back to back,
+    // both groups do their exps, then their byte shuffles, in lockstep: XU and ALU each idle half the time.)
+    // At an accumulator-fold boundary the Gram goes first (the epilogue cannot free a distance buffer while it waits
+    // for the fold).
+    dist_tile(0, 0);
+    if (np == 2) dist_tile(0, 1);
+    for (long long i = 0; i < nu; ++i) {
+      const bool has_next = (i + 1 < nu);
+      const bool fold_prev = (i >= 1) && (g_until_flush == 1);
+      if (i >= 1 && fold_prev) gram(i - 1);
+      if (has_next) dist_tile(i + 1, 0);
+      if (i >= 1 && !fold_prev) gram(i - 1);
+      if (has_next && np == 2) dist_tile(i + 1, 1);
     }
+    gram(nu - 1);
   } else if (warp >= 4) {
     // ================= epilogue warps ===================================================================
     const int ew = warp - 4;

@@ -16,7 +16,7 @@ e.begin(k, Z); e.accumulate(X[:500_000], y[:500_000]); e.finish(copy_out=False)
 tl = e.debug_i8_timeline()
 t0 = tl[tl > 0].min()
 tl = np.where(tl > 0, tl - t0, -1)
-names = {0: ["tileI:issued", "tileJ:issued", "-", "-", "gram:start", "gram:issued"],
+names = {0: ["dist:wait_x", "dist:x_ok", "dist:issued", "gram:wait_p", "gram:p_ok", "gram:issued"],
          1: ["q_wait", "q_ok", "ld_done", "compute_done", "pempty_ok", "stored"], 2: None}
 names[2] = names[1]
 for u in range(4, 12):
@@ -29,4 +29,4 @@ for role in (1, 2):
     a = tl[role, 2:30]
     print("EPI%d mean: q_wait %.0f  ld %.0f  compute %.0f  pempty_wait %.0f  store %.0f" % (role - 1, (a[:, 1] - a[:, 0]).mean(), (a[:, 2] - a[:, 1]).mean(), (a[:, 3] - a[:, 2]).mean(), (a[:, 4] - a[:, 3]).mean(), (a[:, 5] - a[:, 4]).mean()))
 a = tl[0, 2:30]
-print("MMA mean: tileJ-tileI issue gap %.0f   gram issue duration %.0f   gram(i) start - tileI(i) issue %.0f" % ((a[:, 1] - a[:, 0]).mean(), (a[:, 5] - a[:, 4]).mean(), (a[:, 4] - a[:, 0]).mean()))
+print("MMA mean: dist wait_x %.0f  dist issue(+q_empty waits) %.0f   gram wait_p %.0f  gram issue %.0f" % ((a[:, 1] - a[:, 0]).mean(), (a[:, 2] - a[:, 1]).mean(), (a[:, 4] - a[:, 3]).mean(), (a[:, 5] - a[:, 4]).mean()))
