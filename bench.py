@@ -30,6 +30,10 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# dram__bytes_read.sum + dram__bytes_write.sum of one kmn_gram_i8_kernel launch over the 1M-point shard, from the
+# committed `ncu --set full` capture (profiles/); None until measured
+TRAFFIC_BYTES_PER_LAUNCH = None
+
 METRIC = "train_points_per_sec"
 UNIT = "points/s"
 N_PER_GPU, D, M, N_E = 1_000_000, 16, 1000, 100
@@ -42,7 +46,9 @@ def workload_config(n_gpus: int) -> dict:
                         % (N_PER_GPU, D, M, N_E, D),
             "stage": "stats (K_mn + K_mn K_nm + K_mn y, all-reduced)", "n_per_gpu": N_PER_GPU, "d": D, "m": M,
             "n_total": N_PER_GPU * n_gpus, "parallelism": "points sharded over %d GPU(s), one ncclAllReduce of [G;b]" % n_gpus,
-            "l2": "flushed between timed steps (256 MiB memset)", "precision_mode": "SGP_PREC_F64"}
+            "l2": "flushed between timed steps (256 MiB memset)",
+            "precision_mode": "SGP_PREC_AUTO -> tcgen05 int8 exact-accumulation kernel (fp16-split distance contraction, "
+                              "23-bit fixed-point elements, int32 accumulators folded into fp64)"}
 
 
 def make_shard(rank: int):
@@ -265,11 +271,12 @@ def run_ours(args):
         peak_tf, peak_src = measured_peaks()
         launch_ms = kern_ms / max(kern_n, 1)
         achieved_tf = algorithmic_flops_per_point() * N_PER_GPU / (launch_ms / 1e3) / 1e12
-        roof = {"bound": "tensor", "kernel": "kmn_gram_f64_kernel<float>", "achieved": achieved_tf, "peak": peak_tf,
+        roof = {"bound": "tensor", "kernel": "kmn_gram_i8_kernel", "achieved": achieved_tf, "peak": peak_tf,
                 "unit": "TFLOP/s", "frac": achieved_tf / peak_tf, "peak_source": peak_src,
-                "traffic": None, "launch_ms": launch_ms, "launches_timed": kern_n,
+                "traffic": TRAFFIC_BYTES_PER_LAUNCH, "launch_ms": launch_ms, "launches_timed": kern_n,
                 "algorithmic_flops_per_launch": algorithmic_flops_per_point() * N_PER_GPU,
-                "note": "fp64 DMMA path: the bf16 tensor peak is the stated denominator, fp64 peak is ~40 TFLOP/s"}
+                "note": "algorithmic flops = N*(2md + m(m+1) + 2m); the kernel executes 6 int8 products per Gram "
+                        "tile pair (exact 23-bit arithmetic) + recomputed distance tiles, none of which is credited"}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             import oracle
