@@ -255,6 +255,7 @@ def run_ours(args):
     eng.begin(kernel, Z)
     eng.accumulate_ptr(Xd.data_ptr(), True, yd.data_ptr(), N_PER_GPU, device=True)
     eng.finish(copy_out=False)
+    eng.magic(copy_out=False)                       # first call pays cuSOLVER's lazy initialisation
     t0 = time.perf_counter()
     eng.magic(copy_out=False)
     tail_ms = 1e3 * (time.perf_counter() - t0)

@@ -21,10 +21,27 @@ from .ppa import group_for_experts, get_matrix_kmn_knm_and_vector_kmny
 
 
 def usable_cores() -> int:
+    """Cores this process may really use: the affinity mask, capped by the cgroup CPU quota (a container that sees
+    128 logical CPUs but has a 16-CPU quota thrashes with 128 workers)."""
     try:
-        return len(os.sched_getaffinity(0))
+        n = len(os.sched_getaffinity(0))
     except Exception:                                     # pragma: no cover
-        return os.cpu_count() or 1
+        n = os.cpu_count() or 1
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    n = min(n, max(1, int(float(txt[0]) / float(txt[1]) + 0.5)))
+            else:
+                q = int(txt[0])
+                if q > 0:
+                    per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+                    n = min(n, max(1, int(q / per + 0.5)))
+            break
+        except Exception:
+            continue
+    return n
 
 
 def _worker(w, workers, shm_name, m, X, y, Z, kernel_factory, theta, n_e, start_evt, done_q):

@@ -89,7 +89,12 @@ static int launch_stats(Ctx* c, const void* dX, int x_is_f32, const double* dy, 
   p.Gpart = c->dGpart; p.bpart = c->dBpart;
   p.n_slices = n_slices; p.n_tiles_1d = nt1;
 
-  const bool use_i8 = c->i8_ok && (c->precision == SGP_PREC_I8 || c->precision == SGP_PREC_AUTO);
+  // AUTO: the tcgen05 int8 kernel for large shards; small shards (< 65536 points) stay on the fp64 DMMA kernel, whose
+  // elements are ~10x more accurate (direct-form fp32 distances vs the fp32 accumulator of the tensor-core distance
+  // contraction: <= 1.2e-6 relative).  The element roundings are independent, so on large shards they average out
+  // (1M points: G within 1.5e-7, predictions within TOL 1e-5 of the all-fp64 mode -- tests/test_gpu_parity.py); on a
+  // 1k-point ill-conditioned problem they do not (measured 1.5e-5 on the posterior mean).
+  const bool use_i8 = c->i8_ok && (c->precision == SGP_PREC_I8 || (c->precision == SGP_PREC_AUTO && n >= 65536));
   if (c->precision == SGP_PREC_I8 && !c->i8_ok)
     return fail(c, SGP_E_BADARG, "SGP_PREC_I8 needs a kernel with exactly one non-Eye term and d <= 32");
   if (use_i8) {
@@ -263,16 +268,25 @@ int sgp_stats_begin(sgp_ctx* h, const sgp_kernel_desc* k, const double* Z, int32
     }
     kf.scale[kf.n_terms++] = term.scale;
   }
-  free_active_set(c);
+  // device buffers are kept across begin() calls with the same (m, d, term count): cudaMalloc/cudaFree are
+  // synchronising and cost milliseconds -- more than the whole statistics pass on a B200
+  const int nt = kf.n_terms > 0 ? kf.n_terms : 1;
+  const bool same_shape = c->dZ && c->m == m && c->d == d && c->alloc_terms == nt;
+  if (!same_shape) {
+    SGP_CUDA(c, cudaStreamSynchronize(c->stream));
+    free_active_set(c);
+  }
   c->m = m; c->d = d; c->dpad = dpad; c->m_pad = (m + kTile - 1) / kTile * kTile; c->kf = kf;
   const size_t mm = static_cast<size_t>(m) * m;
-  const int nt = kf.n_terms > 0 ? kf.n_terms : 1;
-  SGP_CUDA(c, cudaMalloc(&c->dZ, static_cast<size_t>(m) * d * 8));
-  SGP_CUDA(c, cudaMalloc(&c->dZs, static_cast<size_t>(nt) * c->m_pad * dpad * 8));
-  SGP_CUDA(c, cudaMalloc(&c->dBeta, static_cast<size_t>(kMaxTerms) * dpad * 8));
-  SGP_CUDA(c, cudaMalloc(&c->dGb, (mm + m) * 8));
-  SGP_CUDA(c, cudaMalloc(&c->dMagicVec, static_cast<size_t>(m) * 8));
-  SGP_CUDA(c, cudaMalloc(&c->dMagicMat, mm * 8));
+  if (!same_shape) {
+    c->alloc_terms = nt;
+    SGP_CUDA(c, cudaMalloc(&c->dZ, static_cast<size_t>(m) * d * 8));
+    SGP_CUDA(c, cudaMalloc(&c->dZs, static_cast<size_t>(nt) * c->m_pad * dpad * 8));
+    SGP_CUDA(c, cudaMalloc(&c->dBeta, static_cast<size_t>(kMaxTerms) * dpad * 8));
+    SGP_CUDA(c, cudaMalloc(&c->dGb, (mm + m) * 8));
+    SGP_CUDA(c, cudaMalloc(&c->dMagicVec, static_cast<size_t>(m) * 8));
+    SGP_CUDA(c, cudaMalloc(&c->dMagicMat, mm * 8));
+  }
   SGP_CUDA(c, cudaMemcpyAsync(c->dZ, Z, static_cast<size_t>(m) * d * 8, cudaMemcpyHostToDevice, c->stream));
   SGP_CUDA(c, cudaMemcpyAsync(c->dBeta, beta.data(), beta.size() * 8, cudaMemcpyHostToDevice, c->stream));
   SGP_CUDA(c, cudaMemsetAsync(c->dGb, 0, (mm + m) * 8, c->stream));
@@ -293,10 +307,12 @@ int sgp_stats_begin(sgp_ctx* h, const sgp_kernel_desc* k, const double* Z, int32
       for (int i = 0; i < m; ++i) acc += Z[static_cast<size_t>(i) * d + j];
       ctr[j] = acc / m;                                          // distances are translation invariant
     }
-    SGP_CUDA(c, cudaMalloc(&c->dI8Scale, dp16 * 8));
-    SGP_CUDA(c, cudaMalloc(&c->dI8Centre, dp16 * 8));
-    SGP_CUDA(c, cudaMalloc(&c->dI8Flags, sizeof(int)));
-    SGP_CUDA(c, cudaMalloc(&c->dI8Zt, i8_active_scratch_bytes(c->m_pad, i8_nchunks(d))));
+    if (!c->dI8Scale) {
+      SGP_CUDA(c, cudaMalloc(&c->dI8Scale, dp16 * 8));
+      SGP_CUDA(c, cudaMalloc(&c->dI8Centre, dp16 * 8));
+      SGP_CUDA(c, cudaMalloc(&c->dI8Flags, sizeof(int)));
+      SGP_CUDA(c, cudaMalloc(&c->dI8Zt, i8_active_scratch_bytes(c->m_pad, i8_nchunks(d))));
+    }
     SGP_CUDA(c, cudaMemcpyAsync(c->dI8Scale, sc.data(), dp16 * 8, cudaMemcpyHostToDevice, c->stream));
     SGP_CUDA(c, cudaMemcpyAsync(c->dI8Centre, ctr.data(), dp16 * 8, cudaMemcpyHostToDevice, c->stream));
     SGP_CUDA(c, cudaMemsetAsync(c->dI8Flags, 0, sizeof(int), c->stream));

@@ -59,6 +59,7 @@ struct Ctx {
   // active set / kernel (valid after begin)
   bool begun = false, finished = false, has_magic = false;
   int m = 0, d = 0, dpad = 0, m_pad = 0;
+  int alloc_terms = 0;   // term count the active-set buffers were sized for
   KernelFlat kf;
   double* dZ = nullptr;      // m x d raw active set (fp64)
   double* dZs = nullptr;     // [n_terms][m_pad][dpad]
