@@ -132,6 +132,8 @@ int sgp_gram_kernel_time(sgp_ctx* ctx, double* total_ms, int64_t* launches);
  * stream).  slot in [0, 8): sgp_event_record enqueues an event; sgp_event_elapsed_ms waits for both. */
 int sgp_event_record(sgp_ctx* ctx, int slot);
 int sgp_event_elapsed_ms(sgp_ctx* ctx, int slot_start, int slot_stop, double* ms);
+/* Which kernel the last statistics launch used: SGP_PREC_F64, SGP_PREC_F64_STRICT or SGP_PREC_I8 (-1: none yet). */
+int sgp_last_path(const sgp_ctx* ctx);
 /* Debug aid for SGP_PREC_I8: the first call arms a dump; later calls return, for the first 64-point unit of
  * the first CTA of the last launch, T = -q*log2(e) (128 active rows x 64 points, fp32) and the fixed-point words
  * (0x4B000000 | (u + 0x8080)). */

@@ -21,7 +21,7 @@ EXPORTS = ["sgp_ctx_create", "sgp_ctx_destroy", "sgp_last_error", "sgp_set_preci
            "sgp_comm_unique_id", "sgp_comm_init", "sgp_stats_begin", "sgp_stats_accumulate",
            "sgp_stats_accumulate_device", "sgp_stats_finish", "sgp_sync", "sgp_magic", "sgp_predict",
            "sgp_launch_count", "sgp_gram_kernel_time", "sgp_cross_kernel", "sgp_event_record",
-           "sgp_event_elapsed_ms", "sgp_debug_i8_tile", "sgp_debug_i8_timeline"]
+           "sgp_event_elapsed_ms", "sgp_debug_i8_tile", "sgp_debug_i8_timeline", "sgp_last_path"]
 
 
 class KernelTerm(C.Structure):
@@ -66,6 +66,7 @@ def load() -> C.CDLL:
     lib.sgp_cross_kernel.argtypes = [vp, vp, i64, vp]
     lib.sgp_event_record.argtypes = [vp, C.c_int]
     lib.sgp_debug_i8_tile.argtypes = [vp, vp, vp]
+    lib.sgp_last_path.argtypes = [vp]
     lib.sgp_debug_i8_timeline.argtypes = [vp, vp]
     lib.sgp_event_elapsed_ms.argtypes = [vp, C.c_int, C.c_int, dp]
     for name in EXPORTS:

@@ -47,7 +47,8 @@ int fail(Ctx* c, int code, const std::string& msg) {
 static void free_active_set(Ctx* c) {
   cudaFree(c->dZ); cudaFree(c->dZs); cudaFree(c->dBeta); cudaFree(c->dGb);
   cudaFree(c->dMagicVec); cudaFree(c->dMagicMat);
-  cudaFree(c->dI8Scale); cudaFree(c->dI8Centre); cudaFree(c->dI8Flags); cudaFree(c->dI8Zt);
+  cudaFree(c->dI8Scale); cudaFree(c->dI8Centre); cudaFree(c->dI8Flags); cudaFree(c->dI8Zt); cudaFree(c->dI8NormSum);
+  c->dI8NormSum = nullptr;
   c->dZ = c->dZs = c->dBeta = c->dGb = c->dMagicVec = c->dMagicMat = nullptr;
   c->dI8Scale = c->dI8Centre = nullptr; c->dI8Flags = nullptr; c->dI8Zt = nullptr; c->i8_ok = false;
 }
@@ -94,7 +95,7 @@ static int launch_stats(Ctx* c, const void* dX, int x_is_f32, const double* dy, 
   // contraction: <= 1.2e-6 relative).  The element roundings are independent, so on large shards they average out
   // (1M points: G within 1.5e-7, predictions within TOL 1e-5 of the all-fp64 mode -- tests/test_gpu_parity.py); on a
   // 1k-point ill-conditioned problem they do not (measured 1.5e-5 on the posterior mean).
-  const bool use_i8 = c->i8_ok && (c->precision == SGP_PREC_I8 || (c->precision == SGP_PREC_AUTO && n >= 65536));
+  bool use_i8 = c->i8_ok && (c->precision == SGP_PREC_I8 || (c->precision == SGP_PREC_AUTO && n >= 65536));
   if (c->precision == SGP_PREC_I8 && !c->i8_ok)
     return fail(c, SGP_E_BADARG, "SGP_PREC_I8 needs a kernel with exactly one non-Eye term and d <= 32");
   if (use_i8) {
@@ -111,10 +112,23 @@ static int launch_stats(Ctx* c, const void* dX, int x_is_f32, const double* dy, 
       SGP_CUDA(c, cudaMalloc(&c->dI8Ys, yb));
       c->i8_ys_bytes = yb;
     }
+    const bool gate = (c->precision == SGP_PREC_AUTO);
+    if (gate) SGP_CUDA(c, cudaMemsetAsync(c->dI8NormSum, 0, sizeof(double), c->stream));
     SGP_CUDA(c, launch_i8_prep_points(c->dI8Xt, c->dI8Ys, dX, x_is_f32, dy, n, c->d, c->dI8Scale, c->dI8Centre,
-                                      c->dI8Flags, c->stream));
+                                      c->dI8Flags, gate ? c->dI8NormSum : nullptr, c->stream));
     c->launches += 1;
+    if (gate) {
+      // AUTO's magnitude gate.  The distance contraction accumulates 2 x^.z^ - |x^|^2 - |z^|^2 in fp32 in tensor
+      // memory; its rounding (toward zero, measured) scales with those magnitudes: at mean|x^|^2 + mean|z^|^2 ~ 4.4
+      // the elements are good to 2.7e-7 rms (parity holds, tests), at ~12 (airfoil: norms up to 40) they are not
+      // (posterior mean off by 5e-4).  Above the budget the shard goes to the fp64 DMMA kernel instead.
+      double xsum = 0.0;
+      SGP_CUDA(c, cudaMemcpyAsync(&xsum, c->dI8NormSum, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+      SGP_CUDA(c, cudaStreamSynchronize(c->stream));
+      if (xsum / static_cast<double>(n) + c->i8_z_norm_mean > c->i8_norm_budget) use_i8 = false;
+    }
   }
+  c->last_path = use_i8 ? SGP_PREC_I8 : (c->precision == SGP_PREC_F64_STRICT ? SGP_PREC_F64_STRICT : SGP_PREC_F64);
   cudaEvent_t e0, e1;
   SGP_CUDA(c, cudaEventCreate(&e0));
   SGP_CUDA(c, cudaEventCreate(&e1));
@@ -311,7 +325,18 @@ int sgp_stats_begin(sgp_ctx* h, const sgp_kernel_desc* k, const double* Z, int32
       SGP_CUDA(c, cudaMalloc(&c->dI8Scale, dp16 * 8));
       SGP_CUDA(c, cudaMalloc(&c->dI8Centre, dp16 * 8));
       SGP_CUDA(c, cudaMalloc(&c->dI8Flags, sizeof(int)));
+      SGP_CUDA(c, cudaMalloc(&c->dI8NormSum, sizeof(double)));
       SGP_CUDA(c, cudaMalloc(&c->dI8Zt, i8_active_scratch_bytes(c->m_pad, i8_nchunks(d))));
+    }
+    {
+      double zsum = 0.0;
+      for (int i = 0; i < m; ++i)
+        for (int j = 0; j < d; ++j) {
+          const double v = (Z[static_cast<size_t>(i) * d + j] - ctr[j]) * sc[j];
+          zsum += v * v;
+        }
+      c->i8_z_norm_mean = zsum / m;
+      if (const char* e = getenv("SGP_I8_NORM_BUDGET")) c->i8_norm_budget = atof(e);
     }
     SGP_CUDA(c, cudaMemcpyAsync(c->dI8Scale, sc.data(), dp16 * 8, cudaMemcpyHostToDevice, c->stream));
     SGP_CUDA(c, cudaMemcpyAsync(c->dI8Centre, ctr.data(), dp16 * 8, cudaMemcpyHostToDevice, c->stream));
@@ -465,6 +490,11 @@ int sgp_gram_kernel_time(sgp_ctx* h, double* total_ms, int64_t* launches) {
   if (total_ms) *total_ms = tot;
   if (launches) *launches = static_cast<int64_t>(c->gram_events.size());
   return SGP_OK;
+}
+
+int sgp_last_path(const sgp_ctx* h) {
+  const Ctx* c = reinterpret_cast<const Ctx*>(h);
+  return c ? c->last_path : -1;
 }
 
 int sgp_debug_i8_tile(sgp_ctx* h, float* T_out, uint32_t* w_out) {

@@ -219,7 +219,8 @@ __device__ __forceinline__ __half operand_col(const SplitRow& s, int dp, int L, 
 __global__ void prep_points_kernel(uint8_t* __restrict__ Xt, float* __restrict__ ys, const void* __restrict__ X,
                                    int x_is_f32, const double* __restrict__ y, long long n, long long n_units,
                                    int d, int dp, int nchunks, const double* __restrict__ scale /*[dp]*/,
-                                   const double* __restrict__ centre /*[dp]*/, int* __restrict__ flags) {
+                                   const double* __restrict__ centre /*[dp]*/, int* __restrict__ flags,
+                                   double* __restrict__ norm_sum) {
   const long long pt = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (pt >= n_units * UP) return;
   const bool valid = pt < n;
@@ -237,6 +238,11 @@ __global__ void prep_points_kernel(uint8_t* __restrict__ Xt, float* __restrict__
   double norm2;
   split_row(v, dp, s, norm2);
   if (valid && !(norm2 <= 16384.0)) atomicOr(flags, 1);          // out of the fp16 operand range -> caller falls back
+  if (norm_sum) {                                                // sum of scaled squared norms (AUTO's magnitude gate)
+    double v2 = valid ? norm2 : 0.0;
+    for (int o = 16; o > 0; o >>= 1) v2 += __shfl_xor_sync(0xffffffffu, v2, o);
+    if ((threadIdx.x & 31) == 0 && v2 > 0.0) atomicAdd(norm_sum, v2);
+  }
   ys[pt] = valid ? static_cast<float>(y[pt]) : 0.f;
   const long long unit = pt / UP;
   const int r = static_cast<int>(pt % UP);
@@ -680,12 +686,14 @@ cudaError_t launch_i8_prep_active(uint8_t* Zt, const double* dZ, int m, int m_pa
 }
 
 cudaError_t launch_i8_prep_points(uint8_t* Xt, float* ys, const void* dX, int x_is_f32, const double* dy, long long n,
-                                  int d, const double* dScale, const double* dCentre, int* dFlags, cudaStream_t s) {
+                                  int d, const double* dScale, const double* dCentre, int* dFlags, double* dNormSum,
+                                  cudaStream_t s) {
   const int dp = (d + 15) / 16 * 16;
   const long long units = (n + UP - 1) / UP;
   const long long threads = units * UP;
   prep_points_kernel<<<static_cast<unsigned>((threads + 127) / 128), 128, 0, s>>>(Xt, ys, dX, x_is_f32, dy, n, units, d, dp,
-                                                                                i8_nchunks(d), dScale, dCentre, dFlags);
+                                                                                i8_nchunks(d), dScale, dCentre, dFlags,
+                                                                                dNormSum);
   return cudaGetLastError();
 }
 

@@ -47,6 +47,7 @@ struct GramParams {
 struct Ctx {
   int device = 0;
   int precision = SGP_PREC_AUTO;
+  int last_path = -1;    // arithmetic path of the last statistics launch (SGP_PREC_F64 / _STRICT / _I8)
   std::string err;
   cudaStream_t stream = nullptr;       // compute
   cudaStream_t copy_stream = nullptr;  // H2D staging
@@ -73,6 +74,9 @@ struct Ctx {
   double* dI8Scale = nullptr;    // [dp16] sqrt(log2 e) * beta_k
   double* dI8Centre = nullptr;   // [dp16] per-feature centre (active-set mean)
   int* dI8Flags = nullptr;       // bit 0: coordinates out of fp16 operand range
+  double* dI8NormSum = nullptr;  // sum over the current shard of |x^|^2 (scaled, centred)
+  double i8_z_norm_mean = 0.0;   // mean over the active set of |z^|^2
+  double i8_norm_budget = 8.0;   // AUTO: int8 path only if mean|x^|^2 + mean|z^|^2 <= budget
   uint8_t* dI8Zt = nullptr;      // active-set operand images
   uint8_t* dI8Xt = nullptr;  size_t i8_xt_bytes = 0;   // point operand images (scratch)
   float* dI8Ys = nullptr;    size_t i8_ys_bytes = 0;
@@ -131,7 +135,8 @@ int i8_nchunks(int d);
 cudaError_t launch_i8_prep_active(uint8_t* Zt, const double* dZ, int m, int m_pad, int d, const double* dScale,
                                   const double* dCentre, int* dFlags, cudaStream_t s);
 cudaError_t launch_i8_prep_points(uint8_t* Xt, float* ys, const void* dX, int x_is_f32, const double* dy, long long n,
-                                  int d, const double* dScale, const double* dCentre, int* dFlags, cudaStream_t s);
+                                  int d, const double* dScale, const double* dCentre, int* dFlags, double* dNormSum,
+                                  cudaStream_t s);
 cudaError_t launch_gram_i8(const uint8_t* Xt, const float* ys, const uint8_t* Zt, long long n, int d, int m_pad,
                            int n_slices, double* Gpart, double* bpart, double C, float* dbg_T, uint32_t* dbg_w,
                            long long* dbg_clk, cudaStream_t s);

@@ -187,6 +187,10 @@ class ProjectedProcessEngine:
         return out
 
     # ---- introspection ---------------------------------------------------------------------------------
+    def last_path(self) -> int:
+        """SGP_PREC_F64 / SGP_PREC_F64_STRICT / SGP_PREC_I8: the kernel the last statistics launch ran."""
+        return int(self._lib.sgp_last_path(self._h))
+
     def launch_count(self) -> int:
         return int(self._lib.sgp_launch_count(self._h))
 

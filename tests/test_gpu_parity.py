@@ -166,6 +166,29 @@ def test_airfoil_golden(eng, mode):
         assert np.abs(var / c["var"] - 1).max() < TOL_PRED
 
 
+def test_auto_magnitude_gate(eng):
+    """AUTO picks the tcgen05 int8 kernel only for large shards whose scaled squared norms are small (the fp32
+    accumulator of the distance contraction rounds in proportion to them).  Airfoil (mean scaled squared norm ~6 for
+    points and active set, maxima ~40) stays on the fp64 kernel even when the shard is large; the benchmark's unit
+    cube (mean ~2.2) runs the int8 kernel."""
+    c = np.load(os.path.join(GOLD, "airfoil_case.npz"))
+    kernel = (1 * sg.ARDRBFKernel(5) + sg.const(1) * sg.EyeKernel() + sg.const(float(c["sigma2"])) * sg.EyeKernel())
+    kernel.setHyperparameters(c["theta"])
+    reps = 52                                               # 70k points
+    X, y = np.tile(c["X"], (reps, 1)), np.tile(c["y"], reps)
+    G, b = run_stats(eng, kernel, X, y, c["Z"], N.SGP_PREC_AUTO)
+    assert eng.last_path() == N.SGP_PREC_F64
+    assert np.abs(np.diag(G) - reps * c["G_diag"]).max() / (reps * np.abs(c["G_diag"]).max()) < TOL_STATS
+    assert rel(b, reps * c["b"]) < TOL_STATS
+    rng = np.random.default_rng(2)
+    Xu = rng.random((70000, 16), dtype=np.float32)
+    ku = 1 * sg.ARDRBFKernel(np.full(16, np.sqrt(18.0 / 16))) + sg.const(1) * sg.EyeKernel()
+    run_stats(eng, ku, Xu, rng.random(70000), Xu[:256].astype(np.float64), N.SGP_PREC_AUTO)
+    assert eng.last_path() == N.SGP_PREC_I8
+    run_stats(eng, ku, Xu[:5000], rng.random(5000), Xu[:256].astype(np.float64), N.SGP_PREC_AUTO)
+    assert eng.last_path() == N.SGP_PREC_F64                # small shard
+
+
 # ---------------- seeded inputs vs the oracle, edge cases ---------------------------------------------
 @pytest.mark.parametrize("n,d,m", [(1, 1, 1), (15, 2, 3), (16, 4, 128), (17, 5, 129), (257, 7, 256), (1000, 33, 200),
                                    (2048, 16, 384), (333, 70, 50)])
