@@ -128,6 +128,7 @@ static int launch_stats(Ctx* c, const void* dX, int x_is_f32, const double* dy, 
       if (xsum / static_cast<double>(n) + c->i8_z_norm_mean > c->i8_norm_budget) use_i8 = false;
     }
   }
+  if (use_i8) c->i8_used = true;
   c->last_path = use_i8 ? SGP_PREC_I8 : (c->precision == SGP_PREC_F64_STRICT ? SGP_PREC_F64_STRICT : SGP_PREC_F64);
   cudaEvent_t e0, e1;
   SGP_CUDA(c, cudaEventCreate(&e0));
@@ -348,7 +349,7 @@ int sgp_stats_begin(sgp_ctx* h, const sgp_kernel_desc* k, const double* Z, int32
   }
   SGP_CUDA(c, cudaStreamSynchronize(c->stream));   // Z / beta are host temporaries of the caller
   drop_gram_events(c);
-  c->begun = true; c->finished = false; c->has_magic = false;
+  c->begun = true; c->finished = false; c->has_magic = false; c->i8_used = false;
   return SGP_OK;
 }
 
@@ -413,7 +414,7 @@ int sgp_stats_finish(sgp_ctx* h, double* G_out, double* b_out) {
   if (!c->begun) return fail(c, SGP_E_STATE, "sgp_stats_begin should have been called first");
   SGP_CUDA(c, cudaSetDevice(c->device));
   const size_t mm = static_cast<size_t>(c->m) * c->m;
-  if (!c->finished && c->i8_ok && c->dI8Flags) {
+  if (!c->finished && c->i8_ok && c->i8_used && c->dI8Flags) {
     int flags = 0;
     SGP_CUDA(c, cudaMemcpyAsync(&flags, c->dI8Flags, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     SGP_CUDA(c, cudaStreamSynchronize(c->stream));

@@ -71,6 +71,7 @@ struct Ctx {
   int n_slices = 1;
   // tcgen05 int8 path (gram_i8.cu)
   bool i8_ok = false;            // kernel/shape qualifies (one non-Eye term, d <= 32)
+  bool i8_used = false;          // an int8 launch contributed to the current statistics
   double* dI8Scale = nullptr;    // [dp16] sqrt(log2 e) * beta_k
   double* dI8Centre = nullptr;   // [dp16] per-feature centre (active-set mean)
   int* dI8Flags = nullptr;       // bit 0: coordinates out of fp16 operand range

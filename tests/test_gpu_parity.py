@@ -245,6 +245,7 @@ def test_empty_shard_and_only_eye_kernel(eng):
     rng = np.random.default_rng(3)
     X, y, Z = rng.standard_normal((40, 3)), rng.standard_normal(40), rng.standard_normal((5, 3))
     k = 1 * sg.ARDRBFKernel(3) + sg.const(0.1) * sg.EyeKernel()
+    eng.set_precision(N.SGP_PREC_AUTO)                      # (the engine fixture is shared: pin the mode)
     eng.begin(k, Z)
     eng.accumulate(X[:0], y[:0])                            # empty shard is a no-op
     eng.accumulate(X, y)
