@@ -73,7 +73,7 @@ enum {
   SGP_PREC_I8 = 2,         /* tcgen05 path: distance contraction on fp16 hi/lo splits (fp32 in TMEM), kernel elements
                               as 23-bit fixed point in three balanced int8 digits, Gram = six kind::i8 products with
                               EXACT int32 accumulation, folded into fp64.  Kernels with one non-Eye term, d <= 32. */
-  SGP_PREC_AUTO = 3        /* default: SGP_PREC_I8 when the kernel/shape qualifies AND the shard has >= 65536 points,
+  SGP_PREC_AUTO = 3        /* default: SGP_PREC_I8 when the kernel/shape qualifies AND the shard has >= 262144 points,
                               else SGP_PREC_F64 ('precision')                                     */
 };
 

@@ -90,12 +90,11 @@ static int launch_stats(Ctx* c, const void* dX, int x_is_f32, const double* dy, 
   p.Gpart = c->dGpart; p.bpart = c->dBpart;
   p.n_slices = n_slices; p.n_tiles_1d = nt1;
 
-  // AUTO: the tcgen05 int8 kernel for large shards; small shards (< 65536 points) stay on the fp64 DMMA kernel, whose
-  // elements are ~10x more accurate (direct-form fp32 distances vs the fp32 accumulator of the tensor-core distance
-  // contraction: <= 1.2e-6 relative).  The element roundings are independent, so on large shards they average out
-  // (1M points: G within 1.5e-7, predictions within TOL 1e-5 of the all-fp64 mode -- tests/test_gpu_parity.py); on a
-  // 1k-point ill-conditioned problem they do not (measured 1.5e-5 on the posterior mean).
-  bool use_i8 = c->i8_ok && (c->precision == SGP_PREC_I8 || (c->precision == SGP_PREC_AUTO && n >= 65536));
+  // AUTO: the tcgen05 int8 kernel only inside its measured parity envelope -- shards of >= 262144 points (posterior
+  // mean within 5.6e-6 .. 9.3e-6 of the all-fp64 kernel for N = 250k .. 4M, profiles/r01_i8_scaling.txt; the limit
+  // is the two dropped low-order digit products, tools/i8_error_model.py) and small scaled norms (gate below).
+  // Smaller shards stay on the fp64 DMMA kernel (2e-7), which is fast enough at that size.
+  bool use_i8 = c->i8_ok && (c->precision == SGP_PREC_I8 || (c->precision == SGP_PREC_AUTO && n >= 262144));
   if (c->precision == SGP_PREC_I8 && !c->i8_ok)
     return fail(c, SGP_E_BADARG, "SGP_PREC_I8 needs a kernel with exactly one non-Eye term and d <= 32");
   if (use_i8) {

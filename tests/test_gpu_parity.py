@@ -174,16 +174,16 @@ def test_auto_magnitude_gate(eng):
     c = np.load(os.path.join(GOLD, "airfoil_case.npz"))
     kernel = (1 * sg.ARDRBFKernel(5) + sg.const(1) * sg.EyeKernel() + sg.const(float(c["sigma2"])) * sg.EyeKernel())
     kernel.setHyperparameters(c["theta"])
-    reps = 52                                               # 70k points
+    reps = 200                                              # 270k points
     X, y = np.tile(c["X"], (reps, 1)), np.tile(c["y"], reps)
     G, b = run_stats(eng, kernel, X, y, c["Z"], N.SGP_PREC_AUTO)
     assert eng.last_path() == N.SGP_PREC_F64
     assert np.abs(np.diag(G) - reps * c["G_diag"]).max() / (reps * np.abs(c["G_diag"]).max()) < TOL_STATS
     assert rel(b, reps * c["b"]) < TOL_STATS
     rng = np.random.default_rng(2)
-    Xu = rng.random((70000, 16), dtype=np.float32)
+    Xu = rng.random((300000, 16), dtype=np.float32)
     ku = 1 * sg.ARDRBFKernel(np.full(16, np.sqrt(18.0 / 16))) + sg.const(1) * sg.EyeKernel()
-    run_stats(eng, ku, Xu, rng.random(70000), Xu[:256].astype(np.float64), N.SGP_PREC_AUTO)
+    run_stats(eng, ku, Xu, rng.random(300000), Xu[:256].astype(np.float64), N.SGP_PREC_AUTO)
     assert eng.last_path() == N.SGP_PREC_I8
     run_stats(eng, ku, Xu[:5000], rng.random(5000), Xu[:256].astype(np.float64), N.SGP_PREC_AUTO)
     assert eng.last_path() == N.SGP_PREC_F64                # small shard
@@ -236,9 +236,9 @@ def test_i8_operand_range_falls_back(eng):
     from spark_gp_b200.regression import ExplicitActiveSetProvider
     gp = (sg.GaussianProcessRegression().setKernel(lambda: 1 * sg.ARDRBFKernel(4)).setSigma2(1e-2)
           .setActiveSetProvider(ExplicitActiveSetProvider(Z)).setMaxIter(0))
-    Xbig, ybig = np.tile(X, (140, 1)), np.tile(y, 140)     # 70k points: AUTO tries the int8 kernel, falls back
+    Xbig, ybig = np.tile(X, (600, 1)), np.tile(y, 600)     # 300k points: AUTO considers the int8 kernel, falls back
     gp.fit(Xbig, ybig)
-    assert rel(gp.last_stats[0], 140.0 * G0) < TOL_STATS
+    assert rel(gp.last_stats[0], 600.0 * G0) < TOL_STATS
 
 
 def test_empty_shard_and_only_eye_kernel(eng):
