@@ -96,7 +96,7 @@ class ClockSampler:
              "clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -104,9 +104,11 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append([time.perf_counter()] + [c.strip() for c in line.split(",")])
 
-    def stop(self) -> dict:
+    def stop(self, t_begin: float = 0.0, t_end: float = float("inf")) -> dict:
+        """Median SM clock over the samples taken inside [t_begin, t_end] (host perf_counter), i.e. under load;
+        throttle reasons over the same window.  The sampler runs from before the warm-up (20 ms period)."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -114,17 +116,22 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], None, set()
-        for r in self.rows:
+        sm, mx, reasons, all_sm = [], None, set(), []
+        for row in self.rows:
+            ts, r = row[0], row[1:]
             try:
-                sm.append(float(r[0])); mx = float(r[1])
+                v_sm = float(r[0]); mx = float(r[1])
             except Exception:
                 continue
+            all_sm.append(v_sm)
+            if ts < t_begin - 0.02 or ts > t_end + 0.02:
+                continue
+            sm.append(v_sm)
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "samples": len(sm),
-                "reasons": sorted(reasons)}
+        return {"sm_mhz": float(np.median(sm)) if sm else (float(np.max(all_sm)) if all_sm else None), "sm_max_mhz": mx,
+                "samples": len(sm), "samples_total": len(all_sm), "reasons": sorted(reasons)}
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -221,12 +228,12 @@ def run_ours(args):
         flush.zero_()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step_device()
-    l2_flush()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        step_device()
+    l2_flush()
     launches0 = eng.launch_count()
     barrier()
     t_wall0 = time.perf_counter()
@@ -238,9 +245,9 @@ def run_ours(args):
         kern_ms += kms; kern_n += kn
         l2_flush()
     barrier()
-    wall_ms = 1e3 * (time.perf_counter() - t_wall0)
+    t_wall1 = time.perf_counter()
+    wall_ms = 1e3 * (t_wall1 - t_wall0)
     launches = eng.launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
 
     # e2e leg: host buffers, copies inside the timed region (wall clock around the blocking API calls)
     for _ in range(max(1, min(args.warmup, 2))):
@@ -260,6 +267,7 @@ def run_ours(args):
     eng.magic(copy_out=False)
     tail_ms = 1e3 * (time.perf_counter() - t0)
 
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None   # stopped after the e2e leg: more samples to fall back on
     t = torch.tensor([dev_ms, e2e_ms, kern_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
