@@ -117,6 +117,29 @@ int sgp_sync(sgp_ctx* ctx);
 int sgp_magic(sgp_ctx* ctx, const double* G_in, const double* b_in,
               double* magic_vector /* m */, double* magic_matrix /* m x m */);
 
+/* ---- the hyper-parameter objective:  GPR:55-68 summed over experts as GPC:73-78 ----------------- */
+/* Experts of this rank, packed expert-major: expert e owns rows offsets[e] .. offsets[e+1]-1 of X (row-major, d
+ * columns, fp64) and of y.  Kept on the device until replaced (the L-BFGS-B loop evaluates the objective many times). */
+int sgp_experts_upload(sgp_ctx* ctx, const double* X, const double* y, const int64_t* offsets, int64_t n_experts, int32_t d);
+
+/* One hyper-parameter, in the order of Kernel.getHyperparameters (depth first, trainable scalar prepended). */
+enum { SGP_HYPER_SCALE = 0, SGP_HYPER_ARD_BETA = 1, SGP_HYPER_RBF_SIGMA = 2 };
+typedef struct {
+  int32_t kind;        /* SGP_HYPER_*                                                                            */
+  int32_t term;        /* ARD_BETA / RBF_SIGMA: index into sgp_kernel_desc.terms                                  */
+  int32_t dim;         /* ARD_BETA: feature index                                                                 */
+  int32_t reserved;
+  double value;        /* ARD_BETA: beta_k ; RBF_SIGMA: sigma                                                     */
+  const double* coef;  /* SCALE: kernel->n_terms entries, d(terms[t].scale)/d(this scalar)  (TrainableScalarTimesKernel,
+                          kernel/ScalarTimesKernel.scala:93-97: the derivative is the inner kernel matrix)        */
+} sgp_hyper;
+
+/* nll = sum_e [ 1/2 y_e^T K_e^-1 y_e + 1/2 log|det K_e| ]  and its gradient (n_hypers entries), summed over the
+ * uploaded experts and over ranks (ncclAllReduce of 1 + n_hypers doubles if a communicator exists).
+ * SGP_E_NOT_PD if some expert's kernel matrix has a non-positive Cholesky pivot. */
+int sgp_bcm_nll(sgp_ctx* ctx, const sgp_kernel_desc* kernel, const sgp_hyper* hypers, int32_t n_hypers,
+                double* nll_out, double* grad_out);
+
 /* ---- prediction:  GPC:121-125 for a block of test vectors ----------------------------------- */
 /* mean_t = k(x_t, Z) . magicVector ;  var_t = selfKernel + k(x_t,Z) magicMatrix k(x_t,Z)^T.
  * X: n x d row-major fp64 host.  var_out may be NULL. */

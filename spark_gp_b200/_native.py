@@ -21,12 +21,21 @@ EXPORTS = ["sgp_ctx_create", "sgp_ctx_destroy", "sgp_last_error", "sgp_set_preci
            "sgp_comm_unique_id", "sgp_comm_init", "sgp_stats_begin", "sgp_stats_accumulate",
            "sgp_stats_accumulate_device", "sgp_stats_finish", "sgp_sync", "sgp_magic", "sgp_predict",
            "sgp_launch_count", "sgp_gram_kernel_time", "sgp_cross_kernel", "sgp_event_record",
-           "sgp_event_elapsed_ms", "sgp_debug_i8_tile", "sgp_debug_i8_timeline", "sgp_last_path"]
+           "sgp_event_elapsed_ms", "sgp_debug_i8_tile", "sgp_debug_i8_timeline", "sgp_last_path", "sgp_experts_upload",
+           "sgp_bcm_nll"]
 
 
 class KernelTerm(C.Structure):
     _fields_ = [("type", C.c_int32), ("reserved", C.c_int32), ("scale", C.c_double), ("sigma", C.c_double),
                 ("beta", C.POINTER(C.c_double))]
+
+
+class Hyper(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("term", C.c_int32), ("dim", C.c_int32), ("reserved", C.c_int32),
+                ("value", C.c_double), ("coef", C.POINTER(C.c_double))]
+
+
+SGP_HYPER_SCALE, SGP_HYPER_ARD_BETA, SGP_HYPER_RBF_SIGMA = 0, 1, 2
 
 
 class KernelDesc(C.Structure):
@@ -67,6 +76,8 @@ def load() -> C.CDLL:
     lib.sgp_event_record.argtypes = [vp, C.c_int]
     lib.sgp_debug_i8_tile.argtypes = [vp, vp, vp]
     lib.sgp_last_path.argtypes = [vp]
+    lib.sgp_experts_upload.argtypes = [vp, vp, vp, vp, i64, i32]
+    lib.sgp_bcm_nll.argtypes = [vp, C.POINTER(KernelDesc), vp, i32, dp, vp]
     lib.sgp_debug_i8_timeline.argtypes = [vp, vp]
     lib.sgp_event_elapsed_ms.argtypes = [vp, C.c_int, C.c_int, dp]
     for name in EXPORTS:

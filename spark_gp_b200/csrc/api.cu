@@ -201,6 +201,7 @@ int sgp_ctx_destroy(sgp_ctx* h) {
   for (auto& e : c->user_events) if (e) cudaEventDestroy(e);
   free_active_set(c);
   cudaFree(c->dGpart); cudaFree(c->dBpart);
+  cudaFree(c->dEx); cudaFree(c->dEy); cudaFree(c->dEoff); cudaFree(c->dNllPer); cudaFree(c->dNllScratch);
   cudaFree(c->dI8Xt); cudaFree(c->dI8Ys); cudaFree(c->dbgT); cudaFree(c->dbgW); cudaFree(c->dbgClk);
   for (int i = 0; i < 2; ++i) {
     cudaFree(c->stageX[i]); cudaFree(c->stageY[i]);
@@ -489,6 +490,135 @@ int sgp_gram_kernel_time(sgp_ctx* h, double* total_ms, int64_t* launches) {
   }
   if (total_ms) *total_ms = tot;
   if (launches) *launches = static_cast<int64_t>(c->gram_events.size());
+  return SGP_OK;
+}
+
+int sgp_experts_upload(sgp_ctx* h, const double* X, const double* y, const int64_t* offsets, int64_t E, int32_t d) {
+  Ctx* c = reinterpret_cast<Ctx*>(h);
+  if (!c) return SGP_E_BADARG;
+  if (!X || !y || !offsets || E <= 0 || d <= 0) return fail(c, SGP_E_BADARG, "sgp_experts_upload: null or empty argument");
+  SGP_CUDA(c, cudaSetDevice(c->device));
+  const long long n = offsets[E];
+  int nmax = 0;
+  for (int64_t e = 0; e < E; ++e) {
+    const long long ne = offsets[e + 1] - offsets[e];
+    if (ne <= 0) return fail(c, SGP_E_BADARG, "empty expert");
+    if (ne > nmax) nmax = static_cast<int>(ne);
+  }
+  if (bcm_nll_smem_bytes(nmax) > 227 * 1024)
+    return fail(c, SGP_E_BADARG, "datasetSizeForExpert too large for the on-chip BCM kernel (max ~165 points per expert)");
+  SGP_CUDA(c, cudaStreamSynchronize(c->stream));
+  cudaFree(c->dEx); cudaFree(c->dEy); cudaFree(c->dEoff);
+  c->dEx = c->dEy = nullptr; c->dEoff = nullptr;
+  SGP_CUDA(c, cudaMalloc(&c->dEx, static_cast<size_t>(n) * d * 8));
+  SGP_CUDA(c, cudaMalloc(&c->dEy, static_cast<size_t>(n) * 8));
+  SGP_CUDA(c, cudaMalloc(&c->dEoff, static_cast<size_t>(E + 1) * 8));
+  SGP_CUDA(c, cudaMemcpyAsync(c->dEx, X, static_cast<size_t>(n) * d * 8, cudaMemcpyHostToDevice, c->stream));
+  SGP_CUDA(c, cudaMemcpyAsync(c->dEy, y, static_cast<size_t>(n) * 8, cudaMemcpyHostToDevice, c->stream));
+  SGP_CUDA(c, cudaMemcpyAsync(c->dEoff, offsets, static_cast<size_t>(E + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+  SGP_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->n_experts = E; c->ex_d = d; c->ex_nmax = nmax;
+  return SGP_OK;
+}
+
+int sgp_bcm_nll(sgp_ctx* h, const sgp_kernel_desc* k, const sgp_hyper* hypers, int32_t nh, double* nll_out,
+                double* grad_out) {
+  Ctx* c = reinterpret_cast<Ctx*>(h);
+  if (!c) return SGP_E_BADARG;
+  if (!c->dEx) return fail(c, SGP_E_STATE, "sgp_experts_upload should have been called first");
+  if (!k || !k->terms || k->n_terms <= 0 || nh < 0 || (nh > 0 && !hypers) || !nll_out || (nh > 0 && !grad_out))
+    return fail(c, SGP_E_BADARG, "sgp_bcm_nll: null argument");
+  if (nh > bcm_nll_max_hypers()) return fail(c, SGP_E_BADARG, "too many hyper-parameters");
+  SGP_CUDA(c, cudaSetDevice(c->device));
+  const int d = c->ex_d;
+  // flatten (same rules as sgp_stats_begin): Eye terms only add to the diagonal
+  KernelFlat kf;
+  std::vector<int> flat_of(k->n_terms, -1);
+  std::vector<double> beta(static_cast<size_t>(kMaxTerms) * d, 0.0);
+  for (int t = 0; t < k->n_terms; ++t) {
+    const sgp_kernel_term& term = k->terms[t];
+    if (!(term.scale >= 0.0)) return fail(c, SGP_E_BADARG, "requirement failed: C should be positive");
+    if (term.type == SGP_TERM_EYE) { kf.eye_sum += term.scale; continue; }
+    if (kf.n_terms == kMaxTerms) return fail(c, SGP_E_BADARG, "too many non-Eye kernel terms (max 4)");
+    double* bt = beta.data() + static_cast<size_t>(kf.n_terms) * d;
+    if (term.type == SGP_TERM_ARD) {
+      if (!term.beta) return fail(c, SGP_E_BADARG, "ARD term without beta");
+      for (int j = 0; j < d; ++j) bt[j] = term.beta[j];
+    } else if (term.type == SGP_TERM_RBF) {
+      if (!(term.sigma > 0.0)) return fail(c, SGP_E_BADARG, "RBF sigma must be > 0");
+      for (int j = 0; j < d; ++j) bt[j] = 1.0 / (std::sqrt(2.0) * term.sigma);
+    } else {
+      return fail(c, SGP_E_BADARG, "unknown kernel term type");
+    }
+    flat_of[t] = kf.n_terms;
+    kf.scale[kf.n_terms++] = term.scale;
+  }
+  // hyper descriptors -> flat device arrays
+  const int W = 1 + nh;
+  std::vector<int> kind(nh), hterm(nh, 0), hdim(nh, 0);
+  std::vector<double> coef(static_cast<size_t>(nh) * (kMaxTerms + 1), 0.0), value(nh, 0.0);
+  for (int i = 0; i < nh; ++i) {
+    kind[i] = hypers[i].kind;
+    value[i] = hypers[i].value;
+    if (hypers[i].kind == SGP_HYPER_SCALE) {
+      if (!hypers[i].coef) return fail(c, SGP_E_BADARG, "SCALE hyper-parameter without coef");
+      for (int t = 0; t < k->n_terms; ++t) {
+        if (flat_of[t] >= 0) coef[static_cast<size_t>(i) * (kMaxTerms + 1) + flat_of[t]] += hypers[i].coef[t];
+        else coef[static_cast<size_t>(i) * (kMaxTerms + 1) + kMaxTerms] += hypers[i].coef[t];
+      }
+    } else if (hypers[i].kind == SGP_HYPER_ARD_BETA || hypers[i].kind == SGP_HYPER_RBF_SIGMA) {
+      if (hypers[i].term < 0 || hypers[i].term >= k->n_terms || flat_of[hypers[i].term] < 0)
+        return fail(c, SGP_E_BADARG, "hyper-parameter refers to a bad term");
+      hterm[i] = flat_of[hypers[i].term];
+      hdim[i] = hypers[i].dim;
+      if (hypers[i].kind == SGP_HYPER_ARD_BETA && (hdim[i] < 0 || hdim[i] >= d)) return fail(c, SGP_E_BADARG, "bad ARD dim");
+    } else {
+      return fail(c, SGP_E_BADARG, "unknown hyper-parameter kind");
+    }
+  }
+  // one scratch allocation: [beta | coef | value | total] doubles, then [kind | term | dim | flags] ints
+  const size_t n_dbl = beta.size() + coef.size() + value.size() + W;
+  const size_t n_int = 3 * static_cast<size_t>(nh) + 1;
+  std::vector<double> hd(n_dbl, 0.0);
+  std::vector<int> hi(n_int, 0);
+  std::copy(beta.begin(), beta.end(), hd.begin());
+  std::copy(coef.begin(), coef.end(), hd.begin() + beta.size());
+  std::copy(value.begin(), value.end(), hd.begin() + beta.size() + coef.size());
+  std::copy(kind.begin(), kind.end(), hi.begin());
+  std::copy(hterm.begin(), hterm.end(), hi.begin() + nh);
+  std::copy(hdim.begin(), hdim.end(), hi.begin() + 2 * nh);
+  cudaFree(c->dNllScratch); c->dNllScratch = nullptr;
+  SGP_CUDA(c, cudaMalloc(&c->dNllScratch, n_dbl * 8 + n_int * 4));
+  double* dD = static_cast<double*>(c->dNllScratch);
+  int* dI = reinterpret_cast<int*>(dD + n_dbl);
+  SGP_CUDA(c, cudaMemcpyAsync(dD, hd.data(), n_dbl * 8, cudaMemcpyHostToDevice, c->stream));
+  SGP_CUDA(c, cudaMemcpyAsync(dI, hi.data(), n_int * 4, cudaMemcpyHostToDevice, c->stream));
+  const size_t per_bytes = static_cast<size_t>(c->n_experts) * W * 8;
+  if (per_bytes > c->nll_per_cap) {
+    cudaFree(c->dNllPer); c->dNllPer = nullptr; c->nll_per_cap = 0;
+    SGP_CUDA(c, cudaMalloc(&c->dNllPer, per_bytes));
+    c->nll_per_cap = per_bytes;
+  }
+  double* dBetaN = dD;
+  double* dCoef = dD + beta.size();
+  double* dValue = dCoef + coef.size();
+  double* dTotal = dValue + value.size();
+  SGP_CUDA(c, launch_bcm_nll(c->dEx, c->dEy, c->dEoff, c->n_experts, d, c->ex_nmax, kf, dBetaN, nh, dI, dI + nh, dI + 2 * nh,
+                             dCoef, dValue, c->dNllPer, dTotal, dI + 3 * nh, c->stream));
+  c->launches += 2;
+  if (c->comm && c->nranks > 1) {
+    ncclResult_t r = nccl().AllReduce(dTotal, dTotal, W, ncclDouble, ncclSum, c->comm, c->stream);
+    if (r != ncclSuccess) return fail(c, SGP_E_NCCL, std::string("ncclAllReduce: ") + nccl().GetErrorString(r));
+    c->launches += 1;
+  }
+  std::vector<double> tot(W);
+  int flags = 0;
+  SGP_CUDA(c, cudaMemcpyAsync(tot.data(), dTotal, static_cast<size_t>(W) * 8, cudaMemcpyDeviceToHost, c->stream));
+  SGP_CUDA(c, cudaMemcpyAsync(&flags, dI + 3 * nh, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  SGP_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (flags & 1) return fail(c, SGP_E_NOT_PD, "an expert's kernel matrix is not positive definite (increase sigma2)");
+  *nll_out = tot[0];
+  for (int i = 0; i < nh; ++i) grad_out[i] = tot[1 + i];
   return SGP_OK;
 }
 

@@ -81,6 +81,11 @@ struct Ctx {
   uint8_t* dI8Zt = nullptr;      // active-set operand images
   uint8_t* dI8Xt = nullptr;  size_t i8_xt_bytes = 0;   // point operand images (scratch)
   float* dI8Ys = nullptr;    size_t i8_ys_bytes = 0;
+  // BCM objective state (experts resident on the device)
+  double* dEx = nullptr; double* dEy = nullptr; long long* dEoff = nullptr;
+  long long n_experts = 0; int ex_d = 0; int ex_nmax = 0;
+  double* dNllPer = nullptr; size_t nll_per_cap = 0;
+  void* dNllScratch = nullptr;   // hyper descriptors + totals + flags
   // tail / predict state
   double* dMagicVec = nullptr;   // m
   double* dMagicMat = nullptr;   // m x m
@@ -141,6 +146,14 @@ cudaError_t launch_i8_prep_points(uint8_t* Xt, float* ys, const void* dX, int x_
 cudaError_t launch_gram_i8(const uint8_t* Xt, const float* ys, const uint8_t* Zt, long long n, int d, int m_pad,
                            int n_slices, double* Gpart, double* bpart, double C, float* dbg_T, uint32_t* dbg_w,
                            long long* dbg_clk, cudaStream_t s);
+
+// BCM objective (bcm_nll.cu)
+size_t bcm_nll_smem_bytes(int n_max);
+int bcm_nll_max_hypers();
+cudaError_t launch_bcm_nll(const double* dX, const double* dy, const long long* dOff, long long E, int d, int n_max,
+                           const KernelFlat& kf, const double* dBeta, int n_hypers, const int* dKind, const int* dTerm,
+                           const int* dDim, const double* dCoef, const double* dValue, double* dPerExpert,
+                           double* dTotal, int* dFlags, cudaStream_t s);
 
 int run_tail(Ctx* c, double* magic_vector, double* magic_matrix);
 int run_predict(Ctx* c, const double* X, long long n, double* mean_out, double* var_out);

@@ -142,6 +142,39 @@ class ProjectedProcessEngine:
     def sync(self):
         self._check(self._lib.sgp_sync(self._h))
 
+    # ---- the BCM hyper-parameter objective (GPR:55-68 over all experts, GPC:73-78) ----------------------------------
+    def experts_upload(self, X, y, offsets):
+        """Experts packed expert-major: expert e owns rows offsets[e]..offsets[e+1]-1."""
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        y = np.ascontiguousarray(y, dtype=np.float64)
+        off = np.ascontiguousarray(offsets, dtype=np.int64)
+        self._check(self._lib.sgp_experts_upload(self._h, N.ptr(X), N.ptr(y), N.ptr(off), len(off) - 1, X.shape[1]))
+        self._experts_d = X.shape[1]
+
+    def bcm_nll(self, kernel: Kernel):
+        """(sum over experts of 1/2 y'K^-1 y + 1/2 log|K|, gradient w.r.t. kernel.getHyperparameters())."""
+        desc, keep = _make_desc(kernel, self._experts_d)
+        hd = kernel.hyper_descriptors()
+        nterms = desc.n_terms
+        arr = (N.Hyper * max(len(hd), 1))()
+        coefs = []
+        for i, h in enumerate(hd):
+            arr[i].kind = h["kind"]
+            arr[i].term = h.get("term", 0)
+            arr[i].dim = h.get("dim", 0)
+            arr[i].value = h.get("value", 0.0)
+            if h["kind"] == N.SGP_HYPER_SCALE:
+                cf = np.zeros(nterms)
+                for t, v in h["coef"].items():
+                    cf[t] = v
+                coefs.append(cf)
+                arr[i].coef = cf.ctypes.data_as(C.POINTER(C.c_double))
+        nll = C.c_double()
+        grad = np.zeros(max(len(hd), 1))
+        self._check(self._lib.sgp_bcm_nll(self._h, C.byref(desc), arr, len(hd), C.byref(nll), N.ptr(grad)))
+        del keep, coefs
+        return nll.value, grad[:len(hd)]
+
     # ---- getMagicVector -------------------------------------------------------------------------------
     def magic(self, G=None, b=None, copy_out: bool = True):
         mv = np.empty(self.m) if copy_out else None

@@ -25,6 +25,12 @@ class Kernel:
     def hyperparameterBoundaries(self): raise NotImplementedError
     def flatten(self, scale: float = 1.0) -> list: raise NotImplementedError
 
+    def hyper_descriptors(self, scale: float = 1.0, term_offset: int = 0) -> list:
+        """One dict per hyper-parameter, in getHyperparameters order, saying how the kernel matrix depends on it
+        (consumed by sgp_bcm_nll): {"kind": SCALE, "coef": {term_index: d scale_t / d theta}} for a trainable scalar,
+        {"kind": ARD_BETA, "term": t, "dim": k, "value": beta_k}, {"kind": RBF_SIGMA, "term": t, "value": sigma}."""
+        raise NotImplementedError
+
     @property
     def whiteNoiseVar(self) -> float:
         return sum(t["scale"] for t in self.flatten() if t["type"] == N.SGP_TERM_EYE)
@@ -42,6 +48,7 @@ class EyeKernel(Kernel):
     def numberOfHyperparameters(self): return 0
     def hyperparameterBoundaries(self): return np.zeros(0), np.zeros(0)
     def flatten(self, scale=1.0): return [dict(type=N.SGP_TERM_EYE, scale=scale)]
+    def hyper_descriptors(self, scale=1.0, term_offset=0): return []
     def __str__(self): return "I"
 
 
@@ -66,6 +73,8 @@ class ARDRBFKernel(Kernel):
     def numberOfHyperparameters(self): return len(self.beta)
     def hyperparameterBoundaries(self): return self.lower, self.upper
     def flatten(self, scale=1.0): return [dict(type=N.SGP_TERM_ARD, scale=scale, beta=self.beta.copy())]
+    def hyper_descriptors(self, scale=1.0, term_offset=0):
+        return [dict(kind=N.SGP_HYPER_ARD_BETA, term=term_offset, dim=k, value=float(b)) for k, b in enumerate(self.beta)]
     def __str__(self): return "ARDRBFKernel(beta=[" + ", ".join("%1.1e" % e for e in self.beta) + "])"
 
 
@@ -82,6 +91,8 @@ class RBFKernel(Kernel):
     def numberOfHyperparameters(self): return 1
     def hyperparameterBoundaries(self): return np.array([self.lower]), np.array([self.upper])
     def flatten(self, scale=1.0): return [dict(type=N.SGP_TERM_RBF, scale=scale, sigma=self.sigma)]
+    def hyper_descriptors(self, scale=1.0, term_offset=0):
+        return [dict(kind=N.SGP_HYPER_RBF_SIGMA, term=term_offset, dim=0, value=self.sigma)]
     def __str__(self): return "RBFKernel(sigma=%1.1e)" % self.sigma
 
 
@@ -100,6 +111,8 @@ class ConstantTimesKernel(Kernel):
     def numberOfHyperparameters(self): return self.kernel.numberOfHyperparameters()
     def hyperparameterBoundaries(self): return self.kernel.hyperparameterBoundaries()
     def flatten(self, scale=1.0): return self.kernel.flatten(scale * self.C)
+    def hyper_descriptors(self, scale=1.0, term_offset=0):
+        return self.kernel.hyper_descriptors(scale * self.C, term_offset)
     def __str__(self): return ("%1.1e * %s" % (self.C, self.kernel)) if self.C != 0 else ""
 
 
@@ -120,6 +133,11 @@ class TrainableScalarTimesKernel(ConstantTimesKernel):
     def hyperparameterBoundaries(self):
         lo, up = self.kernel.hyperparameterBoundaries()
         return np.concatenate([[self.Clower], lo]), np.concatenate([[self.Cupper], up])
+    def hyper_descriptors(self, scale=1.0, term_offset=0):
+        # dK/dC = (outer scale) * inner kernel matrix  (ScalarTimesKernel.scala:93-97): per inner term, its scale without C
+        inner = self.kernel.flatten(scale)
+        own = dict(kind=N.SGP_HYPER_SCALE, coef={term_offset + i: t["scale"] for i, t in enumerate(inner)})
+        return [own] + self.kernel.hyper_descriptors(scale * self.C, term_offset)
 
 
 class Scalar:
@@ -179,4 +197,8 @@ class SumOfKernels(Kernel):
         l2, u2 = self.kernel2.hyperparameterBoundaries()
         return np.concatenate([l1, l2]), np.concatenate([u1, u2])
     def flatten(self, scale=1.0): return self.kernel1.flatten(scale) + self.kernel2.flatten(scale)
+    def hyper_descriptors(self, scale=1.0, term_offset=0):
+        n1 = len(self.kernel1.flatten(scale))
+        return (self.kernel1.hyper_descriptors(scale, term_offset)
+                + self.kernel2.hyper_descriptors(scale, term_offset + n1))
     def __str__(self): return " + ".join(s for s in (str(self.kernel1), str(self.kernel2)) if len(s) > 0)
