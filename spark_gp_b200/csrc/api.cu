@@ -70,7 +70,9 @@ static int ensure_partials(Ctx* c, int n_slices) {
 }
 
 // One fused-kernel launch over n device-resident points + the deterministic slice reduction.
-static int launch_stats(Ctx* c, const void* dX, int x_is_f32, const double* dy, long long n) {
+static int launch_stats(Ctx* c, const void* dX, int x_is_f32, const double* dy, long long n, long long n_call) {
+  // n: points of this launch; n_call: points of the whole accumulate call (AUTO's size gate looks at the call, so the
+  // chunks of one shard never mix kernels)
   if (n <= 0) return SGP_OK;
   const int nt1 = c->m_pad / kTile;
   const int ntiles = nt1 * (nt1 + 1) / 2;
@@ -94,7 +96,7 @@ static int launch_stats(Ctx* c, const void* dX, int x_is_f32, const double* dy, 
   // mean within 5.6e-6 .. 9.3e-6 of the all-fp64 kernel for N = 250k .. 4M, profiles/r01_i8_scaling.txt; the limit
   // is the two dropped low-order digit products, tools/i8_error_model.py) and small scaled norms (gate below).
   // Smaller shards stay on the fp64 DMMA kernel (2e-7), which is fast enough at that size.
-  bool use_i8 = c->i8_ok && (c->precision == SGP_PREC_I8 || (c->precision == SGP_PREC_AUTO && n >= 262144));
+  bool use_i8 = c->i8_ok && (c->precision == SGP_PREC_I8 || (c->precision == SGP_PREC_AUTO && n_call >= 262144));
   if (c->precision == SGP_PREC_I8 && !c->i8_ok)
     return fail(c, SGP_E_BADARG, "SGP_PREC_I8 needs a kernel with exactly one non-Eye term and d <= 32");
   if (use_i8) {
@@ -360,7 +362,7 @@ int sgp_stats_accumulate_device(sgp_ctx* h, const void* dX, int32_t x_is_f32, co
   if (n < 0 || (n > 0 && (!dX || !dy))) return fail(c, SGP_E_BADARG, "null shard");
   SGP_CUDA(c, cudaSetDevice(c->device));
   if (c->kf.n_terms == 0) return SGP_OK;   // only Eye terms: the cross kernel is identically zero
-  return launch_stats(c, dX, x_is_f32, dy, n);
+  return launch_stats(c, dX, x_is_f32, dy, n, n);
 }
 
 int sgp_stats_accumulate(sgp_ctx* h, const void* X, int32_t x_is_f32, const double* y, int64_t n) {
@@ -375,6 +377,10 @@ int sgp_stats_accumulate(sgp_ctx* h, const void* X, int32_t x_is_f32, const doub
   // chunk so that copy (PCIe) and compute overlap: ~32 MB of X per chunk, at least 64k points
   long long chunk = static_cast<long long>((32u << 20) / row);
   if (chunk < 65536) chunk = 65536;
+  {                                           // equal chunks (multiples of 64 points) instead of a short tail chunk
+    const long long nchunks = (n + chunk - 1) / chunk;
+    chunk = ((n + nchunks - 1) / nchunks + 63) / 64 * 64;
+  }
   if (chunk > n) chunk = n;
   if (chunk > c->stage_points || row * chunk > c->stage_bytes) {
     SGP_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -399,7 +405,7 @@ int sgp_stats_accumulate(sgp_ctx* h, const void* X, int32_t x_is_f32, const doub
                                 c->copy_stream));
     SGP_CUDA(c, cudaEventRecord(c->stage_ready[buf], c->copy_stream));
     SGP_CUDA(c, cudaStreamWaitEvent(c->stream, c->stage_ready[buf], 0));
-    int rc = launch_stats(c, c->stageX[buf], x_is_f32, c->stageY[buf], cn);
+    int rc = launch_stats(c, c->stageX[buf], x_is_f32, c->stageY[buf], cn, n);
     if (rc != SGP_OK) return rc;
     SGP_CUDA(c, cudaEventRecord(c->stage_free[buf], c->stream));
   }
