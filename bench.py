@@ -32,7 +32,7 @@ sys.path.insert(0, ROOT)
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one kmn_gram_i8_kernel launch over the 1M-point shard, from the
 # committed `ncu --set full` capture (profiles/); None until measured
-TRAFFIC_BYTES_PER_LAUNCH = None
+TRAFFIC_BYTES_PER_LAUNCH = 136_726_016   # profiles/r01_i8_gram_ncu_summary.txt: 132.35 MB read + 4.37 MB write
 
 METRIC = "train_points_per_sec"
 UNIT = "points/s"

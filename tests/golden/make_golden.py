@@ -74,6 +74,54 @@ def small_synthetic():
     print("small cases:", list(cases))
 
 
+def mnist68(n_rows=1500, m=500, n_e=100):
+    """BASELINE config 3 (mnist68 binary GP classification, active=500, RBFKernel(10), tol=1e-3 as
+    classification/examples/MNIST.scala:22-32), on the first `n_rows` rows (the full 11 769 x 784 set is 36 MB --
+    too large for a fixture).  Features are standardised with the FULL data set's mean / population std
+    (commons/util/Scaling.scala); stored as the raw uint8 pixels + the two 784-vectors.  The classification-specific
+    step -- the per-expert Laplace mode f (GaussianProcessClassifier.scala:74-129, run once at the initial theta as
+    GPCls:60 does after optimisation) -- comes from the oracle; the hot path then sees y := f (GPCls:62-65)."""
+    raw = np.loadtxt(os.path.join(REF_DATA, "mnist68.csv"), delimiter=",")
+    labels_raw, pix = raw[:, 0], raw[:, 1:]
+    n = float(len(pix))
+    mean = pix.sum(0) / n
+    var = ((pix - mean) ** 2).sum(0) / n
+    std = np.sqrt(np.where(var > 0, var, 1.0))
+    first = labels_raw[0]                                    # labels201: distinct().collect().zipWithIndex order is
+    y01 = (labels_raw != first).astype(np.float64)           # unspecified in Spark; we fix "first seen -> 0"
+    P8 = pix[:n_rows + 100].astype(np.uint8)
+    X = (P8.astype(np.float64) - mean) / std
+    Xtr, ytr, Xte = X[:n_rows], y01[:n_rows], X[n_rows:n_rows + 100]
+    from oracle.classification import classification_likelihood_and_gradient
+    from oracle import RBFKernel
+    factory = oracle.get_kernel(lambda: RBFKernel(10), 1e-3)
+    theta = factory().get_hyperparameters()
+    experts = oracle.get_expert_labels_and_kernels(Xtr, ytr, factory, n_e)
+    groups = oracle.group_for_experts(n_rows, n_e)
+    f_all = np.zeros(n_rows)
+    negLogZ = 0.0
+    fk = []
+    for (ye, ke), idx in zip(experts, groups):
+        f = np.zeros(len(ye))
+        nl, _ = classification_likelihood_and_gradient(ye, f, ke, theta, 1e-3)
+        negLogZ += nl
+        f_all[idx] = f
+        fk.append((f, ke))
+    rng = np.random.default_rng(68)
+    active_idx = np.sort(rng.permutation(n_rows)[:m])
+    Z = Xtr[active_idx]
+    pred, G, b = oracle.projected_process(fk, Z, factory, theta)
+    fstar, var = pred.predict_many(Xte)
+    np.savez_compressed(os.path.join(OUT, "mnist68_case.npz"), pixels=P8, mean=mean, std=std, y01=y01[:n_rows + 100],
+                        n_rows=n_rows, f=f_all, active_idx=active_idx, sigma=10.0, sigma2=1e-3, G_diag=np.diag(G).copy(),
+                        G_row0=G[0].copy(), b=b, fstar=fstar, var=var, neg_log_z=negLogZ)
+    acc = np.mean((fstar > 0) == (y01[n_rows:n_rows + 100] > 0.5))
+    print("mnist68: n=%d d=%d m=%d  -logZ=%.4f  hold-out accuracy of sign(f*)=%.2f  |f*|max=%.3f" %
+          (n_rows, X.shape[1], m, negLogZ, acc, np.abs(fstar).max()))
+
+
 if __name__ == "__main__":
-    airfoil()
-    small_synthetic()
+    which = sys.argv[1:] or ["airfoil", "small", "mnist68"]
+    if "airfoil" in which: airfoil()
+    if "small" in which: small_synthetic()
+    if "mnist68" in which: mnist68()

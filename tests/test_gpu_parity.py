@@ -436,3 +436,29 @@ def test_fit_with_hyperparameter_optimisation():
     f1, _ = obj(model.hyperparameters)
     eng.close()
     assert f1 <= f0
+
+
+# ---------------- BASELINE config 3: mnist68 binary classification path (d = 784, RBFKernel(10), y := Laplace mode f) ----
+def test_mnist68_classification_path_golden(eng):
+    """classification/GaussianProcessClassifier.scala:62-65: produceModel runs the SAME projected-process statistics
+    with the per-expert latent mode f in place of the labels.  f comes from the oracle's Laplace loop (fixture); the
+    statistics (d = 784 > 32 -> fp64 DMMA kernel with a chunked feature loop), the tail and the raw prediction f* run
+    on the GPU.  predictRaw = (-f*, f*), probability = sigmoid(f*) (GPCls:141-156)."""
+    c = np.load(os.path.join(GOLD, "mnist68_case.npz"))
+    n = int(c["n_rows"])
+    X = (c["pixels"].astype(np.float64) - c["mean"]) / c["std"]
+    Xtr, Xte = X[:n], X[n:n + 100]
+    Z = Xtr[c["active_idx"]]
+    kernel = sg.RBFKernel(float(c["sigma"])) + sg.const(float(c["sigma2"])) * sg.EyeKernel()
+    G, b = run_stats(eng, kernel, Xtr, c["f"], Z)
+    assert eng.last_path() == N.SGP_PREC_F64
+    gmax = np.abs(c["G_diag"]).max()
+    assert np.abs(np.diag(G) - c["G_diag"]).max() / gmax < TOL_STATS
+    assert np.abs(G[0] - c["G_row0"]).max() / gmax < TOL_STATS
+    assert rel(b, c["b"]) < TOL_STATS
+    eng.magic()
+    fstar, var = eng.predict(Xte)
+    assert rel(fstar, c["fstar"]) < TOL_PRED
+    assert np.abs(var / c["var"] - 1).max() < TOL_PRED
+    prob0 = 1.0 / (1.0 + np.exp(-fstar))                   # raw2probabilityInPlace: values(0) = sigmoid(f)  (GPCls:143-144)
+    assert np.all((prob0 > 0.5) == (c["fstar"] > 0))
