@@ -13,19 +13,24 @@
 // unsigned, s1,s0 in [-128,127] signed), and
 //     sum_n u_ni u_nj = 2^32 [S2'S2] + 2^24 [S2'S1 + S1'S2] + 2^16 [S2'S0 + S0'S2 + S1'S1] + (dropped)
 // is six int8 tensor-core products into three int32 TMEM accumulators.  The dropped products (weights 2^8,
-// 2^0) are zero-mean because the low digits are balanced: ~7e-9 per point relative to full scale.
+// 2^0) are zero-mean because the low digits are balanced (~4e-8 of full scale per point and pair); they are what
+// bounds this path's accuracy (posterior mean within 5.6e-6 .. 9.3e-6 of the all-fp64 kernel) --
+// a 4th accumulator for them does not fit: 4 x 128 int32 columns is all of TMEM at a 128x128 tile.
 //
 // Pipeline of one CTA (owns G tile (I,J), I>=J, 128x128, and a slice of the shard's 64-point units):
-//   warp 0   producer : cp.async.bulk (TMA engine, UBLKCP) of pre-swizzled operand images, 4-stage ring
-//   warp 1   MMA      : one thread issues  (a) distance MMAs  T[128 active x 64 points] (kind::f16, fp32 in
-//                       TMEM): -q*log2(e) as ONE contraction over the fp16 hi/lo split of the scaled,
-//                       centred coordinates with the row/column norms folded in as extra K columns;
-//                       (b) the 12 Gram MMAs (kind::i8) of the previous unit
+//   warp 0   producer : cp.async.bulk (TMA engine, UBLKCP) of pre-swizzled operand images, 3/4-stage mbarrier ring
+//   warp 1   MMA      : the whole warp runs the role (UMMA descriptors stay in uniform registers), an elect.sync lane
+//                       issues  (a) distance MMAs  T[128 active x 64 points] (kind::f16, fp32 in TMEM): -q*log2(e) as
+//                       ONE contraction over the fp16 hi/lo split of the scaled, centred coordinates with the row /
+//                       column norms folded in as extra K columns;  (b) the 12 Gram MMAs (kind::i8) of the previous
+//                       unit.  FIFO order per unit: dist I(i+1) | Gram(i-1) | dist J(i+1)
 //   warp 2   TMEM allocator (512 columns: 3 x 128 int32 accumulators + 2 x 64 distance tiles)
-//   warps 4-11 epilogue: tcgen05.ld T -> ex2 -> fixed point via one FFMA against 2^23 -> byte planes (PRMT)
-//                       -> 16-byte stores into the K-major SWIZZLE_128B int8 operand panels in shared memory
-//                       (A/B operands of the Gram MMAs), b += kappa*y on diagonal tiles; every 32768 points
-//                       the int32 accumulators are folded into the fp64 partial tile (no overflow possible).
+//   warps 4-19 epilogue, two groups of 8 (group g consumes the distance tiles of TMEM buffer g = panel I / panel J):
+//                       tcgen05.ld T -> ex2 -> fixed point via one FFMA against 2^23 -> byte planes (PRMT) -> 16-byte
+//                       stores into the K-major SWIZZLE_128B int8 operand panels in shared memory (A/B operands of
+//                       the Gram MMAs), b += kappa*y on diagonal tiles; every 32768 points all 16 warps fold the int32
+//                       accumulators into the fp64 partial tile (no overflow possible).
+// Measured history of this kernel: profiles/r01_i8_tuning_log.md.
 #include <cuda_fp16.h>
 
 #include "sgp_internal.h"

@@ -56,3 +56,60 @@ def test_params_defaults_and_getkernel():
         sg.Scalar(-1.0) * sg.RBFKernel()
     with pytest.raises(ValueError):
         sg.Scalar(1.0, 2.0, 1.0)
+
+
+# ---- hyper-parameter descriptors (what sgp_bcm_nll consumes) vs the oracle's trainingKernelAndDerivative ------------
+def _dense_from_descriptors(k, X):
+    """K and dK/dtheta_i rebuilt in numpy from (flatten(), hyper_descriptors()) exactly as csrc/bcm_nll.cu does."""
+    terms = k.flatten()
+    n, d = X.shape
+    kt, sq = [], []
+    for t in terms:
+        if t["type"] == N.SGP_TERM_EYE:
+            kt.append(np.eye(n)); sq.append(np.zeros((n, n))); continue
+        beta = t["beta"] if t["type"] == N.SGP_TERM_ARD else np.full(d, 1.0 / (np.sqrt(2.0) * t["sigma"]))
+        diff = X[:, None, :] - X[None, :, :]
+        kt.append(np.exp(-((diff * beta) ** 2).sum(2))); sq.append((diff ** 2).sum(2))
+    K = sum(t["scale"] * m for t, m in zip(terms, kt))
+    dK = []
+    for h in k.hyper_descriptors():
+        if h["kind"] == N.SGP_HYPER_SCALE:
+            dK.append(sum(c * kt[t] for t, c in h["coef"].items()))
+        elif h["kind"] == N.SGP_HYPER_ARD_BETA:
+            t, kk = h["term"], h["dim"]
+            dx2 = (X[:, None, kk] - X[None, :, kk]) ** 2
+            dK.append(terms[t]["scale"] * (-2.0 * h["value"] * dx2) * kt[t])
+        else:
+            t = h["term"]
+            dK.append(terms[t]["scale"] * sq[t] * kt[t] / h["value"] ** 3)
+    return K, dK
+
+
+@pytest.mark.parametrize("idx", range(5))
+def test_hyper_descriptors_match_oracle_derivatives(idx):
+    pairs = _pairs() + [
+        (lambda: 0.7 * (1.5 * sg.ARDRBFKernel(np.full(5, 0.9)) + 0.5 * sg.RBFKernel(2.0)) + sg.WhiteNoiseKernel(0.4, 0, 1) + sg.const(0.2) * sg.EyeKernel(),
+         lambda: 0.7 * (1.5 * oracle.ARDRBFKernel(np.full(5, 0.9)) + 0.5 * oracle.RBFKernel(2.0)) + oracle.WhiteNoiseKernel(0.4, 0, 1) + oracle.const(0.2) * oracle.EyeKernel())]
+    mk, mo = pairs[idx]
+    k, o = mk(), mo()
+    d = 2 if idx == 3 else 5
+    X = np.random.default_rng(idx).random((9, d))
+    K, dK = _dense_from_descriptors(k, X)
+    K0, dK0 = o.set_training_vectors(X).training_kernel_and_derivative()
+    assert len(dK) == len(dK0) == k.numberOfHyperparameters()
+    assert np.allclose(K, K0, rtol=1e-13, atol=1e-15)
+    for a, b in zip(dK, dK0):
+        assert np.allclose(a, b, rtol=1e-12, atol=1e-14)
+
+
+def test_expert_packing_matches_reference_grouping():
+    from spark_gp_b200.hyperopt import group_for_experts, pack_experts
+    for n, ne in ((1503, 100), (150, 100), (1000, 100), (999, 37)):
+        g1, g0 = group_for_experts(n, ne), oracle.group_for_experts(n, ne)
+        assert len(g1) == len(g0) and all(np.array_equal(a, b) for a, b in zip(g1, g0))
+    X = np.arange(30.0).reshape(15, 2); y = np.arange(15.0)
+    Xp, yp, off = pack_experts(X, y, 5)                     # E = 3 experts: points i % 3
+    assert list(off) == [0, 5, 10, 15]
+    assert np.array_equal(yp[:5], [0, 3, 6, 9, 12]) and np.array_equal(Xp[5], X[1])
+    with pytest.raises(ZeroDivisionError):
+        group_for_experts(40, 100)
