@@ -140,6 +140,15 @@ typedef struct {
 int sgp_bcm_nll(sgp_ctx* ctx, const sgp_kernel_desc* kernel, const sgp_hyper* hypers, int32_t n_hypers,
                 double* nll_out, double* grad_out);
 
+/* Binary classification (labels 0/1 in the uploaded y): per-expert Laplace approximation,
+ * classification/GaussianProcessClassifier.scala:74-129 -- Newton iteration for the mode with the reference's step
+ * halving, tolerance `tol` and warm start (the latent f of every uploaded point lives on the device, starts at zero
+ * and persists across calls), then -log Z and its gradient, summed over experts and ranks. */
+int sgp_laplace_nll(sgp_ctx* ctx, const sgp_kernel_desc* kernel, const sgp_hyper* hypers, int32_t n_hypers, double tol,
+                    double* neg_log_z_out, double* grad_out);
+/* The latent modes f (same packed expert-major order as the uploaded points): the `y := f` of GPCls:62-65. */
+int sgp_experts_get_f(sgp_ctx* ctx, double* f_out);
+
 /* ---- prediction:  GPC:121-125 for a block of test vectors ----------------------------------- */
 /* mean_t = k(x_t, Z) . magicVector ;  var_t = selfKernel + k(x_t,Z) magicMatrix k(x_t,Z)^T.
  * X: n x d row-major fp64 host.  var_out may be NULL. */

@@ -7,3 +7,4 @@ from .kernels import (Kernel, ARDRBFKernel, RBFKernel, EyeKernel, ConstantTimesK
 from .engine import (ProjectedProcessEngine, NotPositiveDefiniteException, TrainingVectorsNotInitializedException,
                      MatrixSingularException, SgpError, OperandRangeError)
 from .regression import GaussianProcessRegression, GaussianProcessRegressionModel, RandomActiveSetProvider
+from .classification import GaussianProcessClassifier, GaussianProcessClassificationModel

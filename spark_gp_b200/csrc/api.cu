@@ -203,7 +203,7 @@ int sgp_ctx_destroy(sgp_ctx* h) {
   for (auto& e : c->user_events) if (e) cudaEventDestroy(e);
   free_active_set(c);
   cudaFree(c->dGpart); cudaFree(c->dBpart);
-  cudaFree(c->dEx); cudaFree(c->dEy); cudaFree(c->dEoff); cudaFree(c->dNllPer); cudaFree(c->dNllScratch);
+  cudaFree(c->dEx); cudaFree(c->dEy); cudaFree(c->dEoff); cudaFree(c->dEf); cudaFree(c->dNllPer); cudaFree(c->dNllScratch);
   cudaFree(c->dI8Xt); cudaFree(c->dI8Ys); cudaFree(c->dbgT); cudaFree(c->dbgW); cudaFree(c->dbgClk);
   for (int i = 0; i < 2; ++i) {
     cudaFree(c->stageX[i]); cudaFree(c->stageY[i]);
@@ -514,30 +514,36 @@ int sgp_experts_upload(sgp_ctx* h, const double* X, const double* y, const int64
   if (bcm_nll_smem_bytes(nmax) > 227 * 1024)
     return fail(c, SGP_E_BADARG, "datasetSizeForExpert too large for the on-chip BCM kernel (max ~165 points per expert)");
   SGP_CUDA(c, cudaStreamSynchronize(c->stream));
-  cudaFree(c->dEx); cudaFree(c->dEy); cudaFree(c->dEoff);
-  c->dEx = c->dEy = nullptr; c->dEoff = nullptr;
+  cudaFree(c->dEx); cudaFree(c->dEy); cudaFree(c->dEoff); cudaFree(c->dEf);
+  c->dEx = c->dEy = c->dEf = nullptr; c->dEoff = nullptr;
   SGP_CUDA(c, cudaMalloc(&c->dEx, static_cast<size_t>(n) * d * 8));
   SGP_CUDA(c, cudaMalloc(&c->dEy, static_cast<size_t>(n) * 8));
   SGP_CUDA(c, cudaMalloc(&c->dEoff, static_cast<size_t>(E + 1) * 8));
+  SGP_CUDA(c, cudaMalloc(&c->dEf, static_cast<size_t>(n) * 8));
+  SGP_CUDA(c, cudaMemsetAsync(c->dEf, 0, static_cast<size_t>(n) * 8, c->stream));   // f = zeros (GPCls:54)
   SGP_CUDA(c, cudaMemcpyAsync(c->dEx, X, static_cast<size_t>(n) * d * 8, cudaMemcpyHostToDevice, c->stream));
   SGP_CUDA(c, cudaMemcpyAsync(c->dEy, y, static_cast<size_t>(n) * 8, cudaMemcpyHostToDevice, c->stream));
   SGP_CUDA(c, cudaMemcpyAsync(c->dEoff, offsets, static_cast<size_t>(E + 1) * 8, cudaMemcpyHostToDevice, c->stream));
   SGP_CUDA(c, cudaStreamSynchronize(c->stream));
-  c->n_experts = E; c->ex_d = d; c->ex_nmax = nmax;
+  c->n_experts = E; c->ex_d = d; c->ex_nmax = nmax; c->ex_n = n;
   return SGP_OK;
 }
 
-int sgp_bcm_nll(sgp_ctx* h, const sgp_kernel_desc* k, const sgp_hyper* hypers, int32_t nh, double* nll_out,
-                double* grad_out) {
-  Ctx* c = reinterpret_cast<Ctx*>(h);
-  if (!c) return SGP_E_BADARG;
+namespace {
+struct ObjectiveArgs {          // device-side view of (kernel, hyper-parameter descriptors) for the per-expert objectives
+  KernelFlat kf;
+  int W = 0;                    // 1 + n_hypers
+  double *dBeta = nullptr, *dCoef = nullptr, *dValue = nullptr, *dTotal = nullptr;
+  int *dKind = nullptr, *dTerm = nullptr, *dDim = nullptr, *dFlags = nullptr;
+};
+
+// Flattens the kernel (same rules as sgp_stats_begin: Eye terms only add to the diagonal), maps the hyper-parameter
+// descriptors onto the flattened terms and uploads everything into one scratch allocation.
+int objective_setup(Ctx* c, const sgp_kernel_desc* k, const sgp_hyper* hypers, int nh, ObjectiveArgs& o) {
   if (!c->dEx) return fail(c, SGP_E_STATE, "sgp_experts_upload should have been called first");
-  if (!k || !k->terms || k->n_terms <= 0 || nh < 0 || (nh > 0 && !hypers) || !nll_out || (nh > 0 && !grad_out))
-    return fail(c, SGP_E_BADARG, "sgp_bcm_nll: null argument");
+  if (!k || !k->terms || k->n_terms <= 0 || nh < 0 || (nh > 0 && !hypers)) return fail(c, SGP_E_BADARG, "null argument");
   if (nh > bcm_nll_max_hypers()) return fail(c, SGP_E_BADARG, "too many hyper-parameters");
-  SGP_CUDA(c, cudaSetDevice(c->device));
   const int d = c->ex_d;
-  // flatten (same rules as sgp_stats_begin): Eye terms only add to the diagonal
   KernelFlat kf;
   std::vector<int> flat_of(k->n_terms, -1);
   std::vector<double> beta(static_cast<size_t>(kMaxTerms) * d, 0.0);
@@ -559,7 +565,6 @@ int sgp_bcm_nll(sgp_ctx* h, const sgp_kernel_desc* k, const sgp_hyper* hypers, i
     flat_of[t] = kf.n_terms;
     kf.scale[kf.n_terms++] = term.scale;
   }
-  // hyper descriptors -> flat device arrays
   const int W = 1 + nh;
   std::vector<int> kind(nh), hterm(nh, 0), hdim(nh, 0);
   std::vector<double> coef(static_cast<size_t>(nh) * (kMaxTerms + 1), 0.0), value(nh, 0.0);
@@ -569,8 +574,8 @@ int sgp_bcm_nll(sgp_ctx* h, const sgp_kernel_desc* k, const sgp_hyper* hypers, i
     if (hypers[i].kind == SGP_HYPER_SCALE) {
       if (!hypers[i].coef) return fail(c, SGP_E_BADARG, "SCALE hyper-parameter without coef");
       for (int t = 0; t < k->n_terms; ++t) {
-        if (flat_of[t] >= 0) coef[static_cast<size_t>(i) * (kMaxTerms + 1) + flat_of[t]] += hypers[i].coef[t];
-        else coef[static_cast<size_t>(i) * (kMaxTerms + 1) + kMaxTerms] += hypers[i].coef[t];
+        const size_t col = (flat_of[t] >= 0) ? static_cast<size_t>(flat_of[t]) : static_cast<size_t>(kMaxTerms);
+        coef[static_cast<size_t>(i) * (kMaxTerms + 1) + col] += hypers[i].coef[t];
       }
     } else if (hypers[i].kind == SGP_HYPER_ARD_BETA || hypers[i].kind == SGP_HYPER_RBF_SIGMA) {
       if (hypers[i].term < 0 || hypers[i].term >= k->n_terms || flat_of[hypers[i].term] < 0)
@@ -593,38 +598,84 @@ int sgp_bcm_nll(sgp_ctx* h, const sgp_kernel_desc* k, const sgp_hyper* hypers, i
   std::copy(kind.begin(), kind.end(), hi.begin());
   std::copy(hterm.begin(), hterm.end(), hi.begin() + nh);
   std::copy(hdim.begin(), hdim.end(), hi.begin() + 2 * nh);
+  SGP_CUDA(c, cudaStreamSynchronize(c->stream));
   cudaFree(c->dNllScratch); c->dNllScratch = nullptr;
   SGP_CUDA(c, cudaMalloc(&c->dNllScratch, n_dbl * 8 + n_int * 4));
   double* dD = static_cast<double*>(c->dNllScratch);
   int* dI = reinterpret_cast<int*>(dD + n_dbl);
   SGP_CUDA(c, cudaMemcpyAsync(dD, hd.data(), n_dbl * 8, cudaMemcpyHostToDevice, c->stream));
   SGP_CUDA(c, cudaMemcpyAsync(dI, hi.data(), n_int * 4, cudaMemcpyHostToDevice, c->stream));
+  SGP_CUDA(c, cudaStreamSynchronize(c->stream));          // hd / hi are locals
   const size_t per_bytes = static_cast<size_t>(c->n_experts) * W * 8;
   if (per_bytes > c->nll_per_cap) {
     cudaFree(c->dNllPer); c->dNllPer = nullptr; c->nll_per_cap = 0;
     SGP_CUDA(c, cudaMalloc(&c->dNllPer, per_bytes));
     c->nll_per_cap = per_bytes;
   }
-  double* dBetaN = dD;
-  double* dCoef = dD + beta.size();
-  double* dValue = dCoef + coef.size();
-  double* dTotal = dValue + value.size();
-  SGP_CUDA(c, launch_bcm_nll(c->dEx, c->dEy, c->dEoff, c->n_experts, d, c->ex_nmax, kf, dBetaN, nh, dI, dI + nh, dI + 2 * nh,
-                             dCoef, dValue, c->dNllPer, dTotal, dI + 3 * nh, c->stream));
-  c->launches += 2;
+  o.kf = kf; o.W = W;
+  o.dBeta = dD; o.dCoef = dD + beta.size(); o.dValue = o.dCoef + coef.size(); o.dTotal = o.dValue + value.size();
+  o.dKind = dI; o.dTerm = dI + nh; o.dDim = dI + 2 * nh; o.dFlags = dI + 3 * nh;
+  return SGP_OK;
+}
+
+// all-reduce over ranks, copy the (objective, gradient) row back, map a bad pivot to SGP_E_NOT_PD
+int objective_finish(Ctx* c, const ObjectiveArgs& o, double* val_out, double* grad_out) {
   if (c->comm && c->nranks > 1) {
-    ncclResult_t r = nccl().AllReduce(dTotal, dTotal, W, ncclDouble, ncclSum, c->comm, c->stream);
+    ncclResult_t r = nccl().AllReduce(o.dTotal, o.dTotal, o.W, ncclDouble, ncclSum, c->comm, c->stream);
     if (r != ncclSuccess) return fail(c, SGP_E_NCCL, std::string("ncclAllReduce: ") + nccl().GetErrorString(r));
     c->launches += 1;
   }
-  std::vector<double> tot(W);
+  std::vector<double> tot(o.W);
   int flags = 0;
-  SGP_CUDA(c, cudaMemcpyAsync(tot.data(), dTotal, static_cast<size_t>(W) * 8, cudaMemcpyDeviceToHost, c->stream));
-  SGP_CUDA(c, cudaMemcpyAsync(&flags, dI + 3 * nh, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  SGP_CUDA(c, cudaMemcpyAsync(tot.data(), o.dTotal, static_cast<size_t>(o.W) * 8, cudaMemcpyDeviceToHost, c->stream));
+  SGP_CUDA(c, cudaMemcpyAsync(&flags, o.dFlags, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   SGP_CUDA(c, cudaStreamSynchronize(c->stream));
   if (flags & 1) return fail(c, SGP_E_NOT_PD, "an expert's kernel matrix is not positive definite (increase sigma2)");
-  *nll_out = tot[0];
-  for (int i = 0; i < nh; ++i) grad_out[i] = tot[1 + i];
+  *val_out = tot[0];
+  for (int i = 1; i < o.W; ++i) grad_out[i - 1] = tot[i];
+  return SGP_OK;
+}
+}  // namespace
+
+int sgp_bcm_nll(sgp_ctx* h, const sgp_kernel_desc* k, const sgp_hyper* hypers, int32_t nh, double* nll_out,
+                double* grad_out) {
+  Ctx* c = reinterpret_cast<Ctx*>(h);
+  if (!c) return SGP_E_BADARG;
+  if (!nll_out || (nh > 0 && !grad_out)) return fail(c, SGP_E_BADARG, "sgp_bcm_nll: null output");
+  SGP_CUDA(c, cudaSetDevice(c->device));
+  ObjectiveArgs o;
+  int rc = objective_setup(c, k, hypers, nh, o);
+  if (rc != SGP_OK) return rc;
+  SGP_CUDA(c, launch_bcm_nll(c->dEx, c->dEy, c->dEoff, c->n_experts, c->ex_d, c->ex_nmax, o.kf, o.dBeta, nh, o.dKind,
+                             o.dTerm, o.dDim, o.dCoef, o.dValue, c->dNllPer, o.dTotal, o.dFlags, c->stream));
+  c->launches += 2;
+  return objective_finish(c, o, nll_out, grad_out);
+}
+
+int sgp_laplace_nll(sgp_ctx* h, const sgp_kernel_desc* k, const sgp_hyper* hypers, int32_t nh, double tol,
+                    double* neg_log_z_out, double* grad_out) {
+  Ctx* c = reinterpret_cast<Ctx*>(h);
+  if (!c) return SGP_E_BADARG;
+  if (!neg_log_z_out || (nh > 0 && !grad_out) || !(tol > 0.0)) return fail(c, SGP_E_BADARG, "sgp_laplace_nll: bad argument");
+  SGP_CUDA(c, cudaSetDevice(c->device));
+  ObjectiveArgs o;
+  int rc = objective_setup(c, k, hypers, nh, o);
+  if (rc != SGP_OK) return rc;
+  if (laplace_smem_bytes(c->ex_nmax) > 227 * 1024)
+    return fail(c, SGP_E_BADARG, "datasetSizeForExpert too large for the on-chip Laplace kernel (max ~115 points per expert)");
+  SGP_CUDA(c, launch_laplace(c->dEx, c->dEy, c->dEf, c->dEoff, c->n_experts, c->ex_d, c->ex_nmax, o.kf, o.dBeta, nh,
+                             o.dKind, o.dTerm, o.dDim, o.dCoef, o.dValue, tol, c->dNllPer, o.dTotal, o.dFlags, c->stream));
+  c->launches += 2;
+  return objective_finish(c, o, neg_log_z_out, grad_out);
+}
+
+int sgp_experts_get_f(sgp_ctx* h, double* f_out) {
+  Ctx* c = reinterpret_cast<Ctx*>(h);
+  if (!c) return SGP_E_BADARG;
+  if (!c->dEf || !f_out) return fail(c, SGP_E_STATE, "sgp_experts_upload should have been called first");
+  SGP_CUDA(c, cudaSetDevice(c->device));
+  SGP_CUDA(c, cudaMemcpyAsync(f_out, c->dEf, static_cast<size_t>(c->ex_n) * 8, cudaMemcpyDeviceToHost, c->stream));
+  SGP_CUDA(c, cudaStreamSynchronize(c->stream));
   return SGP_OK;
 }
 

@@ -83,7 +83,8 @@ struct Ctx {
   float* dI8Ys = nullptr;    size_t i8_ys_bytes = 0;
   // BCM objective state (experts resident on the device)
   double* dEx = nullptr; double* dEy = nullptr; long long* dEoff = nullptr;
-  long long n_experts = 0; int ex_d = 0; int ex_nmax = 0;
+  double* dEf = nullptr;         // per-point latent mode of the Laplace approximation (warm start across evaluations)
+  long long n_experts = 0, ex_n = 0; int ex_d = 0; int ex_nmax = 0;
   double* dNllPer = nullptr; size_t nll_per_cap = 0;
   void* dNllScratch = nullptr;   // hyper descriptors + totals + flags
   // tail / predict state
@@ -154,6 +155,12 @@ cudaError_t launch_bcm_nll(const double* dX, const double* dy, const long long* 
                            const KernelFlat& kf, const double* dBeta, int n_hypers, const int* dKind, const int* dTerm,
                            const int* dDim, const double* dCoef, const double* dValue, double* dPerExpert,
                            double* dTotal, int* dFlags, cudaStream_t s);
+
+size_t laplace_smem_bytes(int n_max);
+cudaError_t launch_laplace(const double* dX, const double* dy, double* df, const long long* dOff, long long E, int d,
+                           int n_max, const KernelFlat& kf, const double* dBeta, int n_hypers, const int* dKind,
+                           const int* dTerm, const int* dDim, const double* dCoef, const double* dValue, double tol,
+                           double* dPerExpert, double* dTotal, int* dFlags, cudaStream_t s);
 
 int run_tail(Ctx* c, double* magic_vector, double* magic_matrix);
 int run_predict(Ctx* c, const double* X, long long n, double* mean_out, double* var_out);

@@ -151,6 +151,39 @@ class ProjectedProcessEngine:
         self._check(self._lib.sgp_experts_upload(self._h, N.ptr(X), N.ptr(y), N.ptr(off), len(off) - 1, X.shape[1]))
         self._experts_d = X.shape[1]
 
+    def _hyper_array(self, kernel: Kernel, nterms: int):
+        hd = kernel.hyper_descriptors()
+        arr = (N.Hyper * max(len(hd), 1))()
+        coefs = []
+        for i, h in enumerate(hd):
+            arr[i].kind = h["kind"]
+            arr[i].term = h.get("term", 0)
+            arr[i].dim = h.get("dim", 0)
+            arr[i].value = h.get("value", 0.0)
+            if h["kind"] == N.SGP_HYPER_SCALE:
+                cf = np.zeros(nterms)
+                for t, v in h["coef"].items():
+                    cf[t] = v
+                coefs.append(cf)
+                arr[i].coef = cf.ctypes.data_as(C.POINTER(C.c_double))
+        return arr, len(hd), coefs
+
+    def laplace_nll(self, kernel: Kernel, tol: float):
+        """Binary classification: (-log Z summed over experts, its gradient).  Updates the device-resident latent
+        modes f of the uploaded experts (warm start), as GaussianProcessClassifier.likelihoodAndGradient does."""
+        desc, keep = _make_desc(kernel, self._experts_d)
+        arr, nh, coefs = self._hyper_array(kernel, desc.n_terms)
+        val = C.c_double()
+        grad = np.zeros(max(nh, 1))
+        self._check(self._lib.sgp_laplace_nll(self._h, C.byref(desc), arr, nh, float(tol), C.byref(val), N.ptr(grad)))
+        del keep, coefs
+        return val.value, grad[:nh]
+
+    def experts_f(self, n: int):
+        f = np.empty(n)
+        self._check(self._lib.sgp_experts_get_f(self._h, N.ptr(f)))
+        return f
+
     def bcm_nll(self, kernel: Kernel):
         """(sum over experts of 1/2 y'K^-1 y + 1/2 log|K|, gradient w.r.t. kernel.getHyperparameters())."""
         desc, keep = _make_desc(kernel, self._experts_d)

@@ -462,3 +462,53 @@ def test_mnist68_classification_path_golden(eng):
     assert np.abs(var / c["var"] - 1).max() < TOL_PRED
     prob0 = 1.0 / (1.0 + np.exp(-fstar))                   # raw2probabilityInPlace: values(0) = sigmoid(f)  (GPCls:143-144)
     assert np.all((prob0 > 0.5) == (c["fstar"] > 0))
+
+
+# ---------------- classification: batched Laplace objective (GPCls:74-129) -------------------------------------------
+def test_laplace_nll_gradient_and_modes_vs_oracle(eng):
+    """Two consecutive objective evaluations at different theta (the second warm-starts from the first's modes, as the
+    reference's cached experts do): -log Z, its gradient and every expert's latent mode f vs the oracle."""
+    from oracle.classification import classification_likelihood_and_gradient
+    from spark_gp_b200.hyperopt import pack_experts, group_for_experts
+    rng = np.random.default_rng(31)
+    n, d, n_e, tol = 730, 3, 100, 1e-6
+    X = rng.standard_normal((n, d))
+    y = (np.sin(2 * X[:, 0]) + X[:, 1] * X[:, 2] + 0.3 * rng.standard_normal(n) > 0).astype(np.float64)
+    mk = lambda: 1.2 * sg.ARDRBFKernel(np.array([0.8, 0.5, 1.1])) + sg.const(1e-2) * sg.EyeKernel()
+    mo = lambda: 1.2 * oracle.ARDRBFKernel(np.array([0.8, 0.5, 1.1])) + oracle.const(1e-2) * oracle.EyeKernel()
+    groups = group_for_experts(n, n_e)
+    experts = oracle.get_expert_labels_and_kernels(X, y, mo, n_e)
+    fs = [np.zeros(len(g)) for g in groups]
+    eng.experts_upload(*pack_experts(X, y, n_e))
+    theta0 = mk().getHyperparameters()
+    for theta in (theta0, theta0 * np.array([1.4, 0.7, 1.3, 0.9])):
+        v0, g0 = 0.0, 0.0
+        for (ye, ke), f in zip(experts, fs):
+            v, g = classification_likelihood_and_gradient(ye, f, ke, theta, tol)
+            v0 += v; g0 = g0 + g
+        v, g = eng.laplace_nll(mk().setHyperparameters(theta), tol)
+        assert abs(v - v0) / abs(v0) < 1e-9
+        assert np.abs(g - g0).max() / np.abs(g0).max() < 1e-7
+        f_gpu = eng.experts_f(n)
+        assert np.abs(f_gpu - np.concatenate(fs)).max() < 1e-9 * max(1.0, np.abs(np.concatenate(fs)).max())
+
+
+def test_classifier_fit_mnist68_fixture():
+    """GaussianProcessClassifier.fit at fixed theta (MNIST.scala:28-32: RBFKernel(10), tol = 1e-3) on the mnist68
+    fixture: the GPU Laplace modes equal the oracle's (fixture `f`), the model's raw predictions equal the oracle's f*."""
+    from spark_gp_b200.regression import ExplicitActiveSetProvider
+    c = np.load(os.path.join(GOLD, "mnist68_case.npz"))
+    n = int(c["n_rows"])
+    X = (c["pixels"].astype(np.float64) - c["mean"]) / c["std"]
+    Xtr, Xte, ytr = X[:n], X[n:n + 100], c["y01"][:n]
+    gp = (sg.GaussianProcessClassifier().setDatasetSizeForExpert(100).setActiveSetSize(500)
+          .setKernel(lambda: sg.RBFKernel(float(c["sigma"]))).setTol(1e-3)
+          .setActiveSetProvider(ExplicitActiveSetProvider(Xtr[c["active_idx"]])))
+    model = gp.fit(Xtr, ytr, hyperparameters=np.array([float(c["sigma"])]))
+    assert np.abs(gp.last_latent - c["f"]).max() < 1e-8
+    raw = model.predictRaw(Xte)
+    assert rel(raw[:, 1], c["fstar"]) < TOL_PRED and np.allclose(raw[:, 0], -raw[:, 1])
+    acc = np.mean(model.predict(Xte) == (c["y01"][n:n + 100] < 0.5))     # class 0 gets sigmoid(f): the reference's quirk
+    assert acc > 0.95
+    with pytest.raises(RuntimeError):
+        gp.fit(Xtr, ytr + 1.0)
