@@ -19,12 +19,11 @@
 //
 // Pipeline of one CTA (owns G tile (I,J), I>=J, 128x128, and a slice of the shard's 64-point units):
 //   warp 0   producer : cp.async.bulk (TMA engine, UBLKCP) of pre-swizzled operand images, 3/4-stage mbarrier ring
-//   warp 1   MMA      : the whole warp runs the role (UMMA descriptors stay in uniform registers), an elect.sync lane
-//                       issues  (a) distance MMAs  T[128 active x 64 points] (kind::f16, fp32 in TMEM): -q*log2(e) as
+//   warps 1,2 MMA    : a whole warp runs each role (UMMA descriptors stay in uniform registers), an elect.sync lane
+//                       issues; warp 1: (a) distance MMAs  T[128 active x 64 points] (kind::f16, fp32 in TMEM): -q*log2(e) as
 //                       ONE contraction over the fp16 hi/lo split of the scaled, centred coordinates with the row /
-//                       column norms folded in as extra K columns;  (b) the 12 Gram MMAs (kind::i8) of the previous
-//                       unit.  FIFO order per unit: dist I(i+1) | Gram(i-1) | dist J(i+1)
-//   warp 2   TMEM allocator (512 columns: 3 x 128 int32 accumulators + 2 x 64 distance tiles)
+//                       column norms folded in as extra K columns;  warp 2 (after allocating TMEM: 512 columns = 3 x 128 int32
+//                       accumulators + 2 x 64 distance tiles): (b) the 12 Gram MMAs (kind::i8) of every unit
 //   warps 4-19 epilogue, two groups of 8 (group g consumes the distance tiles of TMEM buffer g = panel I / panel J):
 //                       tcgen05.ld T -> ex2 -> fixed point via one FFMA against 2^23 -> byte planes (PRMT) -> 16-byte
 //                       stores into the K-major SWIZZLE_128B int8 operand panels in shared memory (A/B operands of
@@ -405,11 +404,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_kernel(const I8Params
         if (++s == static_cast<uint32_t>(p.xstages)) { s = 0; e_phase ^= 1; }
       }
     }
-  } else if (warp == 1) {
-    // ================= MMA issuer ======================================================================
-    // The whole warp runs this role (warp-uniform control flow keeps the 64-bit UMMA descriptors in uniform
-    // registers); one elected lane issues the tcgen05 instructions.  Issue cost matters: a divergent
-    // single-thread version measured 155 clk per MMA (descriptor arithmetic + R2UR), i.e. issue-bound.
+  } else if (warp == 1 || warp == 2) {
+    // ================= MMA issuers: warp 1 = distance tiles, warp 2 = Gram blocks =======================================
+    // A whole warp runs each role (warp-uniform control flow keeps the 64-bit UMMA descriptors in uniform registers);
+    // one elected lane issues the tcgen05 instructions.  Measured on the way here: (1) a divergent single thread took
+    // 155 clk per MMA (descriptor arithmetic + R2UR), issue-bound; (2) ONE warp issuing both streams in program order is
+    // the serial bottleneck of the CTA: per unit it sits ~1150 clk blocked on the shallow tensor FIFO plus four barrier
+    // try_waits of 150-250 clk each ~ the whole 2340-clk period, with the tensor pipe 51 % busy.  Two issuing warps
+    // overlap those latencies and neither stream queues behind the other's barrier.
     uint32_t elected;
     asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(elected));
     constexpr uint32_t IDESC_D = idesc_f16_f32(128, UP);
@@ -418,112 +420,95 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_kernel(const I8Params
     constexpr uint32_t DESC_HI = 64u | (1u << 14) | (2u << 29);     // SBO = 1024 B, version 1, SWIZZLE_128B
     auto D = [](uint32_t lo) { return (static_cast<uint64_t>(DESC_HI) << 32) | lo; };
     auto lo_of = [](uint32_t addr) { return ((addr & 0x3FFFFu) >> 4) | (1u << 16); };
-    const uint32_t zt_lo = lo_of(s_zt), xs_lo = lo_of(s_xs), pan_lo = lo_of(s_panel);
-    const uint32_t pb_off = diag ? 0u : 3u * (PANEL_BYTES >> 4);
     constexpr uint32_t SL = PANEL_BYTES >> 4;                       // descriptor units between digit panels
-    uint32_t flush_idx = 0;
 
-    int g_until_flush = p.flush_units;   // units left before the accumulators are folded into fp64
-    bool g_fresh = true;                 // next Gram starts new accumulators
-    auto gram = [&](long long j) {
-      const uint32_t h = static_cast<uint32_t>(j & 1);
-      SGP_TL(0, j, 3);
-      mbar_wait(b_pfull + 8 * h, static_cast<uint32_t>((j >> 1) & 1));
-      SGP_TL(0, j, 4);
-      tc_fence_after();
-      const uint32_t fresh = g_fresh ? 0u : 1u;
-      g_fresh = false;
-      const uint32_t pa = pan_lo + h * 4, pb = pa + pb_off;
-      if (elected) {
-        // weight 2^32 : S2'S2
-        mma_i8(tmem + TM_ACC4, D(pa + 2 * SL), D(pb + 2 * SL), ID_UU, fresh);
-        mma_i8(tmem + TM_ACC4, D(pa + 2 * SL + 2), D(pb + 2 * SL + 2), ID_UU, 1u);
-        // weight 2^24 : S2'S1 + S1'S2
-        mma_i8(tmem + TM_ACC3, D(pa + 2 * SL), D(pb + 1 * SL), ID_US, fresh);
-        mma_i8(tmem + TM_ACC3, D(pa + 2 * SL + 2), D(pb + 1 * SL + 2), ID_US, 1u);
-        mma_i8(tmem + TM_ACC3, D(pa + 1 * SL), D(pb + 2 * SL), ID_SU, 1u);
-        mma_i8(tmem + TM_ACC3, D(pa + 1 * SL + 2), D(pb + 2 * SL + 2), ID_SU, 1u);
-        // weight 2^16 : S2'S0 + S0'S2 + S1'S1
-        mma_i8(tmem + TM_ACC2, D(pa + 2 * SL), D(pb), ID_US, fresh);
-        mma_i8(tmem + TM_ACC2, D(pa + 2 * SL + 2), D(pb + 2), ID_US, 1u);
-        mma_i8(tmem + TM_ACC2, D(pa), D(pb + 2 * SL), ID_SU, 1u);
-        mma_i8(tmem + TM_ACC2, D(pa + 2), D(pb + 2 * SL + 2), ID_SU, 1u);
-        mma_i8(tmem + TM_ACC2, D(pa + 1 * SL), D(pb + 1 * SL), ID_SS, 1u);
-        mma_i8(tmem + TM_ACC2, D(pa + 1 * SL + 2), D(pb + 1 * SL + 2), ID_SS, 1u);
-        tc_commit(b_pempty + 8 * h);
-      }
-      SGP_TL(0, j, 5);
-      if (--g_until_flush == 0 || j == nu - 1) {
-        g_until_flush = p.flush_units;
-        g_fresh = true;
-        if (elected) tc_commit(b_accfull);
-        if (j != nu - 1) {
-          mbar_wait(b_accempty, flush_idx & 1);
-          tc_fence_after();
-        }
-        ++flush_idx;
-      }
-    };
-
-    mbar_wait(b_zfull, 0);
-    const uint32_t xstride = static_cast<uint32_t>(p.nchunks) * (XIMG_BYTES >> 4);
-    uint32_t s = 0, x_phase = 0;
-    long long t_next = 0;                // index of the next distance tile
-    // One distance tile = panel P of unit iu (4..7 kind::f16 MMAs, N = 64 points).
-    auto dist_tile = [&](long long iu, int P) {
-      if (P == 0) {
-        SGP_TL(0, iu, 0);
+    if (warp == 1) {
+      // ---------------- distance tiles: T[128 active x 64 points] per (unit, panel) ------------------------------------
+      const uint32_t zt_lo = lo_of(s_zt), xs_lo = lo_of(s_xs);
+      const uint32_t xstride = static_cast<uint32_t>(p.nchunks) * (XIMG_BYTES >> 4);
+      mbar_wait(b_zfull, 0);
+      uint32_t s = 0, x_phase = 0;
+      long long t = 0;
+      for (long long i = 0; i < nu; ++i) {
+        SGP_TL(0, i, 0);
         mbar_wait(b_xfull + 8 * s, x_phase);
-        SGP_TL(0, iu, 1);
         tc_fence_after();
-      }
-      const long long t = t_next++;
-      const uint32_t qb = static_cast<uint32_t>(t & 1);
-      if (t >= 2) {
-        mbar_wait(b_qempty + 8 * qb, static_cast<uint32_t>(((t >> 1) - 1) & 1));
-        tc_fence_after();
-      }
-      const uint32_t d_tmem = tmem + TM_Q0 + qb * UP;
-      const uint32_t a0 = zt_lo + static_cast<uint32_t>(P * p.nchunks) * SL, b0 = xs_lo + s * xstride;
-      if (elected) {
-        const int nks0 = (p.nchunks == 1) ? p.ksteps_last : 4;
-        mma_f16(d_tmem, D(a0), D(b0), IDESC_D, 0u);
-        if (nks0 > 1) mma_f16(d_tmem, D(a0 + 2), D(b0 + 2), IDESC_D, 1u);
-        if (nks0 > 2) mma_f16(d_tmem, D(a0 + 4), D(b0 + 4), IDESC_D, 1u);
-        if (nks0 > 3) mma_f16(d_tmem, D(a0 + 6), D(b0 + 6), IDESC_D, 1u);
-        if (p.nchunks == 2) {
-          const uint32_t a1 = a0 + SL, b1 = b0 + (XIMG_BYTES >> 4);
-          mma_f16(d_tmem, D(a1), D(b1), IDESC_D, 1u);
-          if (p.ksteps_last > 1) mma_f16(d_tmem, D(a1 + 2), D(b1 + 2), IDESC_D, 1u);
-          if (p.ksteps_last > 2) mma_f16(d_tmem, D(a1 + 4), D(b1 + 4), IDESC_D, 1u);
-          if (p.ksteps_last > 3) mma_f16(d_tmem, D(a1 + 6), D(b1 + 6), IDESC_D, 1u);
+        SGP_TL(0, i, 1);
+        for (int P = 0; P < np; ++P, ++t) {
+          const uint32_t qb = static_cast<uint32_t>(t & 1);
+          if (t >= 2) {
+            mbar_wait(b_qempty + 8 * qb, static_cast<uint32_t>(((t >> 1) - 1) & 1));
+            tc_fence_after();
+          }
+          const uint32_t d_tmem = tmem + TM_Q0 + qb * UP;
+          const uint32_t a0 = zt_lo + static_cast<uint32_t>(P * p.nchunks) * SL, b0 = xs_lo + s * xstride;
+          if (elected) {
+            const int nks0 = (p.nchunks == 1) ? p.ksteps_last : 4;
+            mma_f16(d_tmem, D(a0), D(b0), IDESC_D, 0u);
+            if (nks0 > 1) mma_f16(d_tmem, D(a0 + 2), D(b0 + 2), IDESC_D, 1u);
+            if (nks0 > 2) mma_f16(d_tmem, D(a0 + 4), D(b0 + 4), IDESC_D, 1u);
+            if (nks0 > 3) mma_f16(d_tmem, D(a0 + 6), D(b0 + 6), IDESC_D, 1u);
+            if (p.nchunks == 2) {
+              const uint32_t a1 = a0 + SL, b1 = b0 + (XIMG_BYTES >> 4);
+              mma_f16(d_tmem, D(a1), D(b1), IDESC_D, 1u);
+              if (p.ksteps_last > 1) mma_f16(d_tmem, D(a1 + 2), D(b1 + 2), IDESC_D, 1u);
+              if (p.ksteps_last > 2) mma_f16(d_tmem, D(a1 + 4), D(b1 + 4), IDESC_D, 1u);
+              if (p.ksteps_last > 3) mma_f16(d_tmem, D(a1 + 6), D(b1 + 6), IDESC_D, 1u);
+            }
+            tc_commit(b_qfull + 8 * qb);
+          }
         }
-        tc_commit(b_qfull + 8 * qb);
-      }
-      if (P == np - 1) {
-        if (elected) tc_commit(b_xempty + 8 * s);
+        if (elected) tc_commit(b_xempty + 8 * s);     // arrives when every MMA issued so far by this thread has drained
         if (++s == static_cast<uint32_t>(p.xstages)) { s = 0; x_phase ^= 1; }
-        SGP_TL(0, iu, 2);
+        SGP_TL(0, i, 2);
       }
-    };
-    // Issue order per unit:  dist I(i+1) | gram(i-1) | dist J(i+1).
-    // The two epilogue groups (I tiles / J tiles) are self-clocked by the arrival of their tiles; putting the 768-clk
-    // Gram block BETWEEN the two distance tiles in the tensor FIFO runs the groups about half a period out of phase,
-    // so the MUFU phase of one overlaps the PRMT phase (and barrier latencies) of the other.  (Issued back to back,
-    // both groups do their exps, then their byte shuffles, in lockstep: XU and ALU each idle half the time.)
-    // At an accumulator-fold boundary the Gram goes first (the epilogue cannot free a distance buffer while it waits
-    // for the fold).
-    dist_tile(0, 0);
-    if (np == 2) dist_tile(0, 1);
-    for (long long i = 0; i < nu; ++i) {
-      const bool has_next = (i + 1 < nu);
-      const bool fold_prev = (i >= 1) && (g_until_flush == 1);
-      if (i >= 1 && fold_prev) gram(i - 1);
-      if (has_next) dist_tile(i + 1, 0);
-      if (i >= 1 && !fold_prev) gram(i - 1);
-      if (has_next && np == 2) dist_tile(i + 1, 1);
+    } else {
+      // ---------------- Gram blocks: 12 kind::i8 MMAs per unit into the three int32 accumulators ----------------------
+      const uint32_t pan_lo = lo_of(s_panel);
+      const uint32_t pb_off = diag ? 0u : 3u * (PANEL_BYTES >> 4);
+      uint32_t flush_idx = 0;
+      int until_flush = p.flush_units;
+      bool fresh_acc = true;
+      for (long long j = 0; j < nu; ++j) {
+        const uint32_t h = static_cast<uint32_t>(j & 1);
+        SGP_TL(0, j, 3);
+        mbar_wait(b_pfull + 8 * h, static_cast<uint32_t>((j >> 1) & 1));
+        SGP_TL(0, j, 4);
+        tc_fence_after();
+        const uint32_t fresh = fresh_acc ? 0u : 1u;
+        fresh_acc = false;
+        const uint32_t pa = pan_lo + h * 4, pb = pa + pb_off;
+        if (elected) {
+          // weight 2^32 : S2'S2
+          mma_i8(tmem + TM_ACC4, D(pa + 2 * SL), D(pb + 2 * SL), ID_UU, fresh);
+          mma_i8(tmem + TM_ACC4, D(pa + 2 * SL + 2), D(pb + 2 * SL + 2), ID_UU, 1u);
+          // weight 2^24 : S2'S1 + S1'S2
+          mma_i8(tmem + TM_ACC3, D(pa + 2 * SL), D(pb + 1 * SL), ID_US, fresh);
+          mma_i8(tmem + TM_ACC3, D(pa + 2 * SL + 2), D(pb + 1 * SL + 2), ID_US, 1u);
+          mma_i8(tmem + TM_ACC3, D(pa + 1 * SL), D(pb + 2 * SL), ID_SU, 1u);
+          mma_i8(tmem + TM_ACC3, D(pa + 1 * SL + 2), D(pb + 2 * SL + 2), ID_SU, 1u);
+          // weight 2^16 : S2'S0 + S0'S2 + S1'S1
+          mma_i8(tmem + TM_ACC2, D(pa + 2 * SL), D(pb), ID_US, fresh);
+          mma_i8(tmem + TM_ACC2, D(pa + 2 * SL + 2), D(pb + 2), ID_US, 1u);
+          mma_i8(tmem + TM_ACC2, D(pa), D(pb + 2 * SL), ID_SU, 1u);
+          mma_i8(tmem + TM_ACC2, D(pa + 2), D(pb + 2 * SL + 2), ID_SU, 1u);
+          mma_i8(tmem + TM_ACC2, D(pa + 1 * SL), D(pb + 1 * SL), ID_SS, 1u);
+          mma_i8(tmem + TM_ACC2, D(pa + 1 * SL + 2), D(pb + 1 * SL + 2), ID_SS, 1u);
+          tc_commit(b_pempty + 8 * h);
+        }
+        SGP_TL(0, j, 5);
+        if (--until_flush == 0 || j == nu - 1) {
+          until_flush = p.flush_units;
+          fresh_acc = true;
+          if (elected) tc_commit(b_accfull);
+          if (j != nu - 1) {
+            mbar_wait(b_accempty, flush_idx & 1);
+            tc_fence_after();
+          }
+          ++flush_idx;
+        }
+      }
     }
-    gram(nu - 1);
   } else if (warp >= 4) {
     // ================= epilogue warps ===================================================================
     const int ew = warp - 4;
