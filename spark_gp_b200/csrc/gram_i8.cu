@@ -75,6 +75,18 @@ __device__ __forceinline__ uint32_t mbar_try(uint32_t bar, uint32_t parity) {
       : "memory");
   return done;
 }
+// Non-blocking poll (try_wait may suspend the thread for a while when the phase is still open).
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done != 0;
+}
 // Bounded spin: a protocol bug must not hang the GPU box -- trap after ~4 s instead.
 __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
   const long long t0 = clock64();
@@ -525,6 +537,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_kernel(const I8Params
     uint32_t flush_idx = 0, q_phase = 0;
     int until_flush = p.flush_units;
     bool first_flush = true;
+    // barrier polls are software-pipelined: a try_wait on an already-complete phase still costs 150-250 clk of latency,
+    // so q_full of the NEXT tile is tested during this tile's store phase and p_empty in the middle of the exp block
+    bool q_ready = false;
     const bool dbg = DBG && (p.dbg_T != nullptr) && blockIdx.x == 0 && blockIdx.y == 0;
     for (long long i = 0; i < nu; ++i) {
       const uint32_t h = static_cast<uint32_t>(i & 1);
@@ -532,7 +547,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_kernel(const I8Params
         // ---- one distance tile (128 active rows x 64 points) -> three int8 digit panels -------------------
         const bool tle = tl && (ew & 7) == 0;
         if (tle) SGP_TL(1 + grp, i, 0);
-        mbar_wait(b_qfull + 8 * grp, q_phase);
+        if (!q_ready) mbar_wait(b_qfull + 8 * grp, q_phase);
         if (tle) SGP_TL(1 + grp, i, 1);
         q_phase ^= 1;
         tc_fence_after();
@@ -547,11 +562,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_kernel(const I8Params
           for (int k = 0; k < 32; ++k) p.dbg_T[L * UP + ch * 32 + k] = __uint_as_float(T[k]);
         }
         // kappa = 2^T ; fixed point: mantissa(kappa*C0 + MAGIC) = u + 0x8080
+        // (the Gram MMAs that read this half of the panels two units ago must have drained before we overwrite it:
+        //  p_empty is polled between the two halves of the exp block)
+        const uint32_t pe_bar = b_pempty + 8 * h, pe_par = static_cast<uint32_t>(((i >> 1) - 1) & 1);
+        bool pe_ready = (i < 2);
         if (diag) {
           const float4* yv = reinterpret_cast<const float4*>(sm_ys + static_cast<int>(i & (YSTAGES - 1)) * UP + ch * 32);
           float bacc = 0.f;
 #pragma unroll
           for (int g = 0; g < 8; ++g) {
+            if (g == 4 && !pe_ready) pe_ready = mbar_test(pe_bar, pe_par);
             const float4 y4 = yv[g];
             const float e0 = ex2f(__uint_as_float(T[4 * g + 0])), e1 = ex2f(__uint_as_float(T[4 * g + 1])),
                         e2 = ex2f(__uint_as_float(T[4 * g + 2])), e3 = ex2f(__uint_as_float(T[4 * g + 3]));
@@ -563,14 +583,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_kernel(const I8Params
           bsum += static_cast<double>(bacc);
         } else {
 #pragma unroll
-          for (int k = 0; k < 32; ++k) T[k] = __float_as_uint(fmaf(ex2f(__uint_as_float(T[k])), C0, MAGIC));
+          for (int k = 0; k < 16; ++k) T[k] = __float_as_uint(fmaf(ex2f(__uint_as_float(T[k])), C0, MAGIC));
+          if (!pe_ready) pe_ready = mbar_test(pe_bar, pe_par);
+#pragma unroll
+          for (int k = 16; k < 32; ++k) T[k] = __float_as_uint(fmaf(ex2f(__uint_as_float(T[k])), C0, MAGIC));
         }
         if (DBG && dbg && i == 0 && P == 0) {
           for (int k = 0; k < 32; ++k) p.dbg_w[L * UP + ch * 32 + k] = T[k];
         }
-        // the Gram MMAs that read this half of the panels two units ago must have drained before we overwrite it
         if (tle) SGP_TL(1 + grp, i, 3);
-        if (i >= 2) mbar_wait(b_pempty + 8 * h, static_cast<uint32_t>(((i >> 1) - 1) & 1));
+        if (!pe_ready) mbar_wait(pe_bar, pe_par);
         if (tle) SGP_TL(1 + grp, i, 4);
         // byte planes: 4 consecutive points -> one word per digit; 16 points -> one 16-byte store per digit
 #pragma unroll
@@ -586,6 +608,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_kernel(const I8Params
             const uint32_t u01 = prmt(w0, w1, 0x0062), u23 = prmt(w2, w3, 0x0062);
             d2[g] = prmt(u01, u23, 0x5410);                   // s2 = byte2 (0..127)
           }
+          if (g16 == 1) q_ready = mbar_test(b_qfull + 8 * grp, q_phase);     // next tile of this group
           uint8_t* dst = pan_base + sw128_off(L, static_cast<int>(h * 4 + ch * 2 + g16));
           *reinterpret_cast<uint4*>(dst + 0 * PANEL_BYTES) = make_uint4(d0[0], d0[1], d0[2], d0[3]);
           *reinterpret_cast<uint4*>(dst + 1 * PANEL_BYTES) = make_uint4(d1[0], d1[1], d1[2], d1[3]);
