@@ -534,6 +534,7 @@ namespace {
 struct ObjectiveArgs {          // device-side view of (kernel, hyper-parameter descriptors) for the per-expert objectives
   KernelFlat kf;
   int W = 0;                    // 1 + n_hypers
+  int any_ard = 0;              // some hyper-parameter is an ARD beta (per-dimension sums needed)
   double *dBeta = nullptr, *dCoef = nullptr, *dValue = nullptr, *dTotal = nullptr;
   int *dKind = nullptr, *dTerm = nullptr, *dDim = nullptr, *dFlags = nullptr;
 };
@@ -583,6 +584,7 @@ int objective_setup(Ctx* c, const sgp_kernel_desc* k, const sgp_hyper* hypers, i
         return fail(c, SGP_E_BADARG, "hyper-parameter refers to a bad term");
       hterm[i] = flat_of[hypers[i].term];
       hdim[i] = hypers[i].dim;
+      if (hypers[i].kind == SGP_HYPER_ARD_BETA) o.any_ard = 1;
       if (hypers[i].kind == SGP_HYPER_ARD_BETA && (hdim[i] < 0 || hdim[i] >= d)) return fail(c, SGP_E_BADARG, "bad ARD dim");
     } else {
       return fail(c, SGP_E_BADARG, "unknown hyper-parameter kind");
@@ -648,7 +650,7 @@ int sgp_bcm_nll(sgp_ctx* h, const sgp_kernel_desc* k, const sgp_hyper* hypers, i
   int rc = objective_setup(c, k, hypers, nh, o);
   if (rc != SGP_OK) return rc;
   SGP_CUDA(c, launch_bcm_nll(c->dEx, c->dEy, c->dEoff, c->n_experts, c->ex_d, c->ex_nmax, o.kf, o.dBeta, nh, o.dKind,
-                             o.dTerm, o.dDim, o.dCoef, o.dValue, c->dNllPer, o.dTotal, o.dFlags, c->stream));
+                             o.dTerm, o.dDim, o.dCoef, o.dValue, o.any_ard, c->dNllPer, o.dTotal, o.dFlags, c->stream));
   c->launches += 2;
   return objective_finish(c, o, nll_out, grad_out);
 }

@@ -153,8 +153,8 @@ size_t bcm_nll_smem_bytes(int n_max);
 int bcm_nll_max_hypers();
 cudaError_t launch_bcm_nll(const double* dX, const double* dy, const long long* dOff, long long E, int d, int n_max,
                            const KernelFlat& kf, const double* dBeta, int n_hypers, const int* dKind, const int* dTerm,
-                           const int* dDim, const double* dCoef, const double* dValue, double* dPerExpert,
-                           double* dTotal, int* dFlags, cudaStream_t s);
+                           const int* dDim, const double* dCoef, const double* dValue, int any_ard,
+                           double* dPerExpert, double* dTotal, int* dFlags, cudaStream_t s);
 
 size_t laplace_smem_bytes(int n_max);
 cudaError_t launch_laplace(const double* dX, const double* dy, double* df, const long long* dOff, long long E, int d,
