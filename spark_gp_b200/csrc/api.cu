@@ -667,7 +667,7 @@ int sgp_laplace_nll(sgp_ctx* h, const sgp_kernel_desc* k, const sgp_hyper* hyper
   if (laplace_smem_bytes(c->ex_nmax) > 227 * 1024)
     return fail(c, SGP_E_BADARG, "datasetSizeForExpert too large for the on-chip Laplace kernel (max ~115 points per expert)");
   SGP_CUDA(c, launch_laplace(c->dEx, c->dEy, c->dEf, c->dEoff, c->n_experts, c->ex_d, c->ex_nmax, o.kf, o.dBeta, nh,
-                             o.dKind, o.dTerm, o.dDim, o.dCoef, o.dValue, tol, c->dNllPer, o.dTotal, o.dFlags, c->stream));
+                             o.dKind, o.dTerm, o.dDim, o.dCoef, o.dValue, o.any_ard, tol, c->dNllPer, o.dTotal, o.dFlags, c->stream));
   c->launches += 2;
   return objective_finish(c, o, neg_log_z_out, grad_out);
 }

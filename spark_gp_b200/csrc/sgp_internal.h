@@ -159,7 +159,8 @@ cudaError_t launch_bcm_nll(const double* dX, const double* dy, const long long* 
 size_t laplace_smem_bytes(int n_max);
 cudaError_t launch_laplace(const double* dX, const double* dy, double* df, const long long* dOff, long long E, int d,
                            int n_max, const KernelFlat& kf, const double* dBeta, int n_hypers, const int* dKind,
-                           const int* dTerm, const int* dDim, const double* dCoef, const double* dValue, double tol,
+                           const int* dTerm, const int* dDim, const double* dCoef, const double* dValue, int any_ard,
+                           double tol,
                            double* dPerExpert, double* dTotal, int* dFlags, cudaStream_t s);
 
 int run_tail(Ctx* c, double* magic_vector, double* magic_matrix);

@@ -13,6 +13,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 import oracle
+from oracle.regression import bcm_objective
 
 
 def _free_port():
@@ -47,6 +48,18 @@ def _worker(rank, world, port, ret):
         out = packed.numpy()
         ret["dG"] = float(np.abs(out[:m * m].reshape(m, m) - G0).max() / np.abs(G0).max())
         ret["db"] = float(np.abs(out[m * m:] - b0).max() / np.abs(b0).max())
+    # the hyper-parameter objective (GPC:73-78) is a sum over EXPERTS: rank r owns experts r, r+world, ... of the
+    # reference's grouping (point i -> expert i % E) and one all-reduce of the packed [nll; grad] row gives the total --
+    # the contract of sgp_experts_upload + sgp_bcm_nll / sgp_laplace_nll (tools/multi_gpu_check.py runs it on GPUs)
+    full = oracle.get_expert_labels_and_kernels(X, y, fac, 100)
+    mine = full[rank::world]
+    v, g = bcm_objective(mine, theta)
+    row = torch.from_numpy(np.concatenate([[v], g]))
+    dist.all_reduce(row, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        v0, g0 = bcm_objective(full, theta)
+        ret["dnll"] = float(abs(row[0].item() - v0) / abs(v0))
+        ret["dgrad"] = float(np.abs(row[1:].numpy() - g0).max() / np.abs(g0).max())
     dist.destroy_process_group()
 
 
@@ -63,3 +76,4 @@ def test_two_rank_allreduce_of_shard_statistics():
             assert p.exitcode == 0
         # expert boundaries differ between the sharded and the unsharded run, which is irrelevant to G and b
         assert ret["dG"] < 1e-13 and ret["db"] < 1e-13
+        assert ret["dnll"] < 1e-13 and ret["dgrad"] < 1e-12
