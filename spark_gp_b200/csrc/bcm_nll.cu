@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(EX_THREADS, 2) bcm_nll_kernel(const NllParams 
   ex_build_kernel<false>(p.hv, Xe, xld, n, K, ld);
   __syncthreads();
   bool bad = false;
-  const double logdet = 2.0 * ex_cholesky(K, n, ld, rowbuf, bad);
+  const double logdet = 2.0 * ex_cholesky(K, n, ld, rowbuf, red, bad);
   if (bad && tid == 0) atomicOr(p.flags, 1);
   ex_invert_lower(K, n, ld, rowbuf);
   ex_ltl_inplace(K, n, ld, rowbuf);           // K now holds K^-1 (lower)
@@ -74,13 +74,22 @@ __global__ void __launch_bounds__(EX_THREADS, 2) bcm_nll_kernel(const NllParams 
                          out + 1, sums, red);
 }
 
-// sum the per-expert rows in a fixed order: deterministic
-__global__ void nll_reduce_kernel(double* __restrict__ total, const double* __restrict__ per_expert, long long E, int width) {
-  const int c = threadIdx.x;
-  if (c >= width) return;
+// Sum the per-expert rows: one CTA per column, thread t adds experts t, t+256, ... and the 256 partials are combined by
+// a fixed tree -- the order never depends on timing, so the result is deterministic.
+__global__ void __launch_bounds__(EX_THREADS) rows_reduce_kernel(double* __restrict__ total,
+                                                                   const double* __restrict__ per_expert, long long E,
+                                                                   int width) {
+  __shared__ double part[EX_THREADS];
+  const int c = blockIdx.x;
   double s = 0.0;
-  for (long long e = 0; e < E; ++e) s += per_expert[e * width + c];
-  total[c] = s;
+  for (long long e = threadIdx.x; e < E; e += EX_THREADS) s += per_expert[e * width + c];
+  part[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = EX_THREADS / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) part[threadIdx.x] += part[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) total[c] = part[0];
 }
 
 }  // namespace
@@ -89,6 +98,11 @@ size_t bcm_nll_smem_bytes(int n_max) {
   return sizeof(double) * (static_cast<size_t>(n_max) * (n_max + 1) + 3 * static_cast<size_t>(n_max) + 8 + EX_SUMS);
 }
 int bcm_nll_max_hypers() { return MAX_HYPERS; }
+
+cudaError_t launch_rows_reduce(double* dTotal, const double* dPerExpert, long long E, int width, cudaStream_t s) {
+  rows_reduce_kernel<<<width, EX_THREADS, 0, s>>>(dTotal, dPerExpert, E, width);
+  return cudaGetLastError();
+}
 
 HyperView make_hyper_view(int d, const KernelFlat& kf, const double* dBeta, int n_hypers, const int* dKind, const int* dTerm,
                           const int* dDim, const double* dCoef, const double* dValue, int any_ard) {
@@ -119,8 +133,7 @@ cudaError_t launch_bcm_nll(const double* dX, const double* dy, const long long* 
   bcm_nll_kernel<<<static_cast<unsigned>(E), EX_THREADS, smem, s>>>(p);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  nll_reduce_kernel<<<1, 128, 0, s>>>(dTotal, dPerExpert, E, 1 + n_hypers);
-  return cudaGetLastError();
+  return launch_rows_reduce(dTotal, dPerExpert, E, 1 + n_hypers, s);
 }
 
 }  // namespace sgp

@@ -38,6 +38,8 @@ struct HyperView {
 // host side (bcm_nll.cu)
 HyperView make_hyper_view(int d, const KernelFlat& kf, const double* dBeta, int n_hypers, const int* dKind, const int* dTerm,
                           const int* dDim, const double* dCoef, const double* dValue, int any_ard);
+// total[c] = sum_e per_expert[e][c], deterministic
+cudaError_t launch_rows_reduce(double* dTotal, const double* dPerExpert, long long E, int width, cudaStream_t s);
 
 __device__ __forceinline__ double ex_block_sum(double v, double* red) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -82,18 +84,16 @@ __device__ __forceinline__ void ex_build_kernel(const HyperView& hv, const doubl
 }
 
 // In-place lower Cholesky (right-looking; the scaled column goes through `col`, the trailing update is row-per-warp).
-// Returns sum(log diag L); `bad` is set when a pivot is not positive.
-__device__ __forceinline__ double ex_cholesky(double* M, int n, int ld, double* col, bool& bad) {
+// Returns sum(log diag L) (computed in parallel after the factorisation: the per-column critical path is one rsqrt);
+// `bad` is set when a pivot is not positive.  `red`: 8 doubles.
+__device__ __forceinline__ double ex_cholesky(double* M, int n, int ld, double* col, double* red, bool& bad) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  double sumlog = 0.0;
   for (int j = 0; j < n; ++j) {
     const double djj = M[j * ld + j];
     if (!(djj > 0.0)) bad = true;
-    const double ljj = sqrt(djj > 0.0 ? djj : 1.0);
-    sumlog += log(ljj);
+    const double inv = rsqrt(djj > 0.0 ? djj : 1.0);
     __syncthreads();
-    if (tid == 0) M[j * ld + j] = ljj;
-    const double inv = 1.0 / ljj;
+    if (tid == 0) M[j * ld + j] = (djj > 0.0 ? djj : 1.0) * inv;
     for (int i = j + 1 + tid; i < n; i += EX_THREADS) col[i] = M[i * ld + j] * inv;
     __syncthreads();
     for (int i = j + 1 + warp; i < n; i += EX_WARPS) {
@@ -103,7 +103,9 @@ __device__ __forceinline__ double ex_cholesky(double* M, int n, int ld, double* 
     }
     __syncthreads();
   }
-  return sumlog;
+  double part = 0.0;
+  for (int j = tid; j < n; j += EX_THREADS) part += log(M[j * ld + j]);
+  return ex_block_sum(part, red);
 }
 
 // L -> L^-1 in place (row by row: row i of L^-1 needs rows < i of L^-1 and row i of L)

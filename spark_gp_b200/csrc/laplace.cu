@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(LT, 1) laplace_kernel(const LapParams p) {
     for (int a = warp; a < n; a += EX_WARPS)             // B = I + sqrtW K sqrtW   (GPCls:95-97), lower
       for (int b = lane; b <= a; b += 32) M[a * ld + b] = sw[a] * sw[b] * K[a * ld + b] + (a == b ? 1.0 : 0.0);
     __syncthreads();
-    sumlogL = ex_cholesky(M, n, ld, t2, bad);            // GPCls:98
+    sumlogL = ex_cholesky(M, n, ld, t2, red, bad);            // GPCls:98
     for (int i = tid; i < n; i += LT) bv[i] = wv[i] * f[i] + glp[i];           // b = W f + grad log p   (:100)
     __syncthreads();
     for (int i = tid; i < n; i += LT) {                  // rhs = sqrtW (K b)
@@ -168,14 +168,6 @@ __global__ void __launch_bounds__(LT, 1) laplace_kernel(const LapParams p) {
       -1.0, out + 1, sums, red);                         // -gradLogZ
 }
 
-__global__ void lap_reduce_kernel(double* __restrict__ total, const double* __restrict__ per_expert, long long E, int width) {
-  const int c = threadIdx.x;
-  if (c >= width) return;
-  double s = 0.0;
-  for (long long e = 0; e < E; ++e) s += per_expert[e * width + c];
-  total[c] = s;
-}
-
 }  // namespace
 
 size_t laplace_smem_bytes(int n_max) {
@@ -199,8 +191,7 @@ cudaError_t launch_laplace(const double* dX, const double* dy, double* df, const
   laplace_kernel<<<static_cast<unsigned>(E), LT, smem, s>>>(p);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  lap_reduce_kernel<<<1, 128, 0, s>>>(dTotal, dPerExpert, E, 1 + n_hypers);
-  return cudaGetLastError();
+  return launch_rows_reduce(dTotal, dPerExpert, E, 1 + n_hypers, s);
 }
 
 }  // namespace sgp

@@ -102,6 +102,48 @@ def test_hyper_descriptors_match_oracle_derivatives(idx):
         assert np.allclose(a, b, rtol=1e-12, atol=1e-14)
 
 
+@pytest.mark.parametrize("idx", range(5))
+def test_descriptor_gradient_from_pair_sums(idx):
+    """csrc/expert_common.cuh: sum_ab dK_i[a,b] W_ab for a symmetric W from ONE lower-triangle sweep of pair sums
+    (S_t, Q_t, D_tk per non-Eye term, trW) -- the algebra both objective kernels use -- vs the oracle's dense dK_i."""
+    pairs = _pairs() + [
+        (lambda: 0.7 * (1.5 * sg.ARDRBFKernel(np.full(5, 0.9)) + 0.5 * sg.RBFKernel(2.0)) + sg.WhiteNoiseKernel(0.4, 0, 1) + sg.const(0.2) * sg.EyeKernel(),
+         lambda: 0.7 * (1.5 * oracle.ARDRBFKernel(np.full(5, 0.9)) + 0.5 * oracle.RBFKernel(2.0)) + oracle.WhiteNoiseKernel(0.4, 0, 1) + oracle.const(0.2) * oracle.EyeKernel())]
+    mk, mo = pairs[idx]
+    k, o = mk(), mo()
+    d = 2 if idx == 3 else 5
+    rng = np.random.default_rng(10 + idx)
+    n = 11
+    X = rng.random((n, d))
+    A = rng.standard_normal((n, n)); W = A + A.T
+    _, dK0 = o.set_training_vectors(X).training_kernel_and_derivative()
+    terms = k.flatten()
+    tri = [(a, b) for a in range(n) for b in range(a + 1)]
+    w2 = {(a, b): (1.0 if a == b else 2.0) * W[a, b] for a, b in tri}
+    S, Q, D = {}, {}, {}
+    for t, term in enumerate(terms):
+        if term["type"] == N.SGP_TERM_EYE:
+            continue
+        beta = term["beta"] if term["type"] == N.SGP_TERM_ARD else np.full(d, 1.0 / (np.sqrt(2.0) * term["sigma"]))
+        S[t], Q[t], D[t] = 0.0, 0.0, np.zeros(d)
+        for a, b in tri:
+            dx = X[a] - X[b]
+            kw = np.exp(-((dx * beta) ** 2).sum()) * w2[(a, b)]
+            S[t] += kw; Q[t] += (dx ** 2).sum() * kw; D[t] += dx ** 2 * kw
+    trW = np.trace(W)
+    hd = k.hyper_descriptors()
+    assert len(hd) == len(dK0)
+    for h, dk in zip(hd, dK0):
+        if h["kind"] == N.SGP_HYPER_SCALE:
+            g = sum(c * (trW if terms[t]["type"] == N.SGP_TERM_EYE else S[t]) for t, c in h["coef"].items())
+        elif h["kind"] == N.SGP_HYPER_ARD_BETA:
+            g = terms[h["term"]]["scale"] * (-2.0 * h["value"]) * D[h["term"]][h["dim"]]
+        else:
+            g = terms[h["term"]]["scale"] * Q[h["term"]] / h["value"] ** 3
+        g0 = float((dk * W).sum())
+        assert abs(g - g0) <= 1e-12 * max(1.0, abs(g0))
+
+
 def test_expert_packing_matches_reference_grouping():
     from spark_gp_b200.hyperopt import group_for_experts, pack_experts
     for n, ne in ((1503, 100), (150, 100), (1000, 100), (999, 37)):
