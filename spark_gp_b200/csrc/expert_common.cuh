@@ -108,34 +108,57 @@ __device__ __forceinline__ double ex_cholesky(double* M, int n, int ld, double* 
   return ex_block_sum(part, red);
 }
 
-// L -> L^-1 in place (row by row: row i of L^-1 needs rows < i of L^-1 and row i of L)
+// L -> L^-1 in place, right-looking (Gauss-Jordan on the triangle): step k finalises row k and applies its rank-1
+// update to the rows below -- (n-k-1) x (k+1) independent FMAs per step instead of one serial dot product per element.
 __device__ __forceinline__ void ex_invert_lower(double* M, int n, int ld, double* rowbuf) {
-  const int tid = threadIdx.x;
-  for (int i = 0; i < n; ++i) {
-    const double lii = M[i * ld + i];
-    for (int j = tid; j < i; j += EX_THREADS) {
-      double s = 0.0;
-      for (int k = j; k < i; ++k) s = fma(M[i * ld + k], M[k * ld + j], s);
-      rowbuf[j] = -s / lii;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int k = 0; k < n; ++k) {
+    const double pinv = 1.0 / M[k * ld + k];
+    __syncthreads();
+    for (int j = tid; j <= k; j += EX_THREADS) {            // row k of the inverse: scale; keep a copy for the update
+      const double v = (j == k) ? pinv : M[k * ld + j] * pinv;
+      M[k * ld + j] = v;
+      rowbuf[j] = v;
     }
     __syncthreads();
-    for (int j = tid; j < i; j += EX_THREADS) M[i * ld + j] = rowbuf[j];
-    if (tid == 0) M[i * ld + i] = 1.0 / lii;
-    __syncthreads();
+    for (int i = k + 1 + warp; i < n; i += EX_WARPS) {
+      const double f = M[i * ld + k];
+      for (int j = lane; j < k; j += 32) M[i * ld + j] = fma(-f, rowbuf[j], M[i * ld + j]);
+      if (lane == 0) M[i * ld + k] = -f * rowbuf[k];
+    }
   }
+  __syncthreads();
 }
 
-// L^-1 -> (L L^T)^-1 = L^-T L^-1 in place, lower triangle (row i needs rows >= i of L^-1; finalised top-down)
-__device__ __forceinline__ void ex_ltl_inplace(double* M, int n, int ld, double* rowbuf) {
-  const int tid = threadIdx.x;
-  for (int i = 0; i < n; ++i) {
-    for (int j = tid; j <= i; j += EX_THREADS) {
-      double s = 0.0;
-      for (int k = i; k < n; ++k) s = fma(M[k * ld + i], M[k * ld + j], s);
-      rowbuf[j] = s;
+// L^-1 -> (L L^T)^-1 = L^-T L^-1 in place, lower triangle.  out[i][j] = sum_{k>=i} X[k][i] X[k][j] needs rows >= i of X
+// only, so bands of EX_WARPS rows are processed top-down: every thread first accumulates its entries of the band in
+// registers (independent chains), then the band is overwritten.  Two barriers per band instead of two per row.
+constexpr int EX_LTL_MAXC = 6;      // columns per lane: n <= 192
+__device__ __forceinline__ void ex_ltl_inplace(double* M, int n, int ld, double* /*rowbuf*/) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i0 = 0; i0 < n; i0 += EX_WARPS) {
+    const int i = i0 + warp;
+    double acc[EX_LTL_MAXC];
+#pragma unroll
+    for (int c = 0; c < EX_LTL_MAXC; ++c) acc[c] = 0.0;
+    if (i < n) {
+      for (int k = i; k < n; ++k) {
+        const double xki = M[k * ld + i];
+#pragma unroll
+        for (int c = 0; c < EX_LTL_MAXC; ++c) {
+          const int j = lane + 32 * c;
+          if (j <= i) acc[c] = fma(xki, M[k * ld + j], acc[c]);
+        }
+      }
     }
     __syncthreads();
-    for (int j = tid; j <= i; j += EX_THREADS) M[i * ld + j] = rowbuf[j];
+    if (i < n) {
+#pragma unroll
+      for (int c = 0; c < EX_LTL_MAXC; ++c) {
+        const int j = lane + 32 * c;
+        if (j <= i) M[i * ld + j] = acc[c];
+      }
+    }
     __syncthreads();
   }
 }
