@@ -18,6 +18,12 @@
 // the slices in a fixed order, mirrors the lower triangle and adds into the persistent fp64 [G;b]
 // (deterministic: no atomics anywhere).
 //
+// Tile shapes.  Strict mode keeps the 128x128 tile (128 accumulator registers per thread, one CTA per SM).  The default
+// mode uses 128x64 tiles (TN = 64): 64 accumulator registers per thread, so TWO CTAs fit on an SM and the panel phase
+// (FMA / XU pipes) of one overlaps the DMMA phase of the other -- with one CTA per SM the two phases alternate and
+// the DMMA pipe sat at 43.5 % (profiles/r01_t1_gram_f64_ncu_summary.txt).  Column tiles of 64 inside the 128-row
+// diagonal block reuse the I panel (no second panel); the tile map is the staircase tj <= 2 ti + 1.
+//
 // Why fp64 accumulation: tools/precision_study.py -- the posterior mean needs the Gram accumulated to
 // better than fp32 (fp16 hi/lo operands + fp32 accumulators already sit AT the 1e-5 parity bound for
 // N=1e5 and degrade with N), while fp32-accurate *elements* with exact accumulation are 50x inside it.
@@ -59,8 +65,9 @@ constexpr size_t gram_smem_bytes() {
   return sizeof(double) * (2 * PB * PS + 2 * PB) + sizeof(ET) * (DC * 256 + PB * DC);
 }
 
-template <typename ET>
-__global__ void __launch_bounds__(NT, 1) kmn_gram_f64_kernel(const GramParams p) {
+template <typename ET, int TN>
+__global__ void __launch_bounds__(NT, (TN == 64) ? 2 : 1) kmn_gram_f64_kernel(const GramParams p) {
+  constexpr int NJ = TN / 16;                                // 8-column B fragments per warp (warp tile 32 x TN/2)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* panel = reinterpret_cast<double*>(smem_raw);      // [2][PB][PS]
   double* ys2 = panel + 2 * PB * PS;                         // [2][PB] (double buffered by block parity)
@@ -71,20 +78,31 @@ __global__ void __launch_bounds__(NT, 1) kmn_gram_f64_kernel(const GramParams p)
   const int lane = tid & 31, warp = tid >> 5;
   const int wr = warp >> 1, wc = warp & 1;
 
-  // tile decode: t -> (ti, tj), ti >= tj
+  // tile decode.  TN = 128: t -> (ti, tj), ti >= tj (triangular).  TN = 64: staircase, row tile ti owns column tiles
+  // tj = 0 .. 2 ti + 1 (ti (ti + 1) tiles precede row ti).
   int ti, tj;
   {
     const int t = blockIdx.x;
-    ti = static_cast<int>((sqrtf(8.0f * t + 1.0f) - 1.0f) * 0.5f);
-    while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
-    while (ti * (ti + 1) / 2 > t) --ti;
-    tj = t - ti * (ti + 1) / 2;
+    if (TN == 128) {
+      ti = static_cast<int>((sqrtf(8.0f * t + 1.0f) - 1.0f) * 0.5f);
+      while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+      while (ti * (ti + 1) / 2 > t) --ti;
+      tj = t - ti * (ti + 1) / 2;
+    } else {
+      ti = static_cast<int>((sqrtf(4.0f * t + 1.0f) - 1.0f) * 0.5f);
+      while ((ti + 1) * (ti + 2) <= t) ++ti;
+      while (ti * (ti + 1) > t) --ti;
+      tj = t - ti * (ti + 1);
+    }
   }
-  const bool diag = (ti == tj);
+  // column tiles inside the diagonal block read their B operand from the I panel
+  const bool diag = (TN == 128) ? (ti == tj) : (tj >= 2 * ti);
+  const int joff = (TN == 128) ? 0 : (tj - 2 * ti) * TN;      // offset of the J columns inside the I panel (diag only)
+  const bool owns_b = (TN == 128) ? diag : (tj == 2 * ti);   // one tile per row tile accumulates b_I
   const int col = tid & 127, pan = tid >> 7;
-  const int zrow = (pan ? tj : ti) * kTile + col;            // active-set index of this thread's column
+  const int zrow = pan ? (tj * TN + col) : (ti * kTile + col);   // active-set index of this thread's column
   const bool zvalid = zrow < p.m;
-  const bool elem_active = !(diag && pan == 1);
+  const bool elem_active = (pan == 0) || (!diag && col < TN);
 
   // slice of points
   const long long total_blocks = (p.n + PB - 1) / PB;
@@ -96,8 +114,10 @@ __global__ void __launch_bounds__(NT, 1) kmn_gram_f64_kernel(const GramParams p)
   const bool z_resident = (p.n_terms == 1 && p.dpad <= DC);
 
   auto load_z_chunk = [&](int term, int c0, int clen) {
-    const double* src = p.Zs + (static_cast<size_t>(term) * p.m_pad + zrow) * p.dpad + c0;
-    for (int k = 0; k < clen; ++k) zs[((k >> 2) * 256 + tid) * 4 + (k & 3)] = static_cast<ET>(src[k]);
+    // (threads 192..255 of a 128x64 tile have no column: their zrow may point past the padded active set)
+    const bool in_range = zrow < p.m_pad;
+    const double* src = p.Zs + (static_cast<size_t>(term) * p.m_pad + (in_range ? zrow : 0)) * p.dpad + c0;
+    for (int k = 0; k < clen; ++k) zs[((k >> 2) * 256 + tid) * 4 + (k & 3)] = in_range ? static_cast<ET>(src[k]) : ET(0);
   };
   auto load_x_chunk = [&](long long pt0, int term, int c0, int clen) {
     const double* bt = p.beta + term * p.dpad + c0;
@@ -117,11 +137,11 @@ __global__ void __launch_bounds__(NT, 1) kmn_gram_f64_kernel(const GramParams p)
 
   if (z_resident) load_z_chunk(0, 0, p.dpad);   // visible after the first __syncthreads below
 
-  double acc[4][8][2];
+  double acc[4][NJ][2];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int j = 0; j < NJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
   double bacc = 0.0;
 
   for (long long blk = blk_lo; blk < blk_hi; ++blk) {
@@ -173,26 +193,26 @@ __global__ void __launch_bounds__(NT, 1) kmn_gram_f64_kernel(const GramParams p)
     }
     __syncthreads();
     // ---------------- b_I += P_I^T y (diagonal tiles) ----------------------------------------------
-    if (diag && tid < kTile) {
+    if (owns_b && tid < kTile) {
 #pragma unroll
       for (int pp = 0; pp < PB; ++pp) bacc = fma(panel[pp * PS + tid], ys[pp], bacc);
     }
     // ---------------- phase 2: acc += P_I^T P_J  (fp64 tensor cores) --------------------------------
     const double* PA = panel;
-    const double* PBm = diag ? panel : panel + PB * PS;
+    const double* PBm = diag ? panel + joff : panel + PB * PS;
 #pragma unroll
     for (int k0 = 0; k0 < PB; k0 += 4) {
-      double a[4], b[8];
+      double a[4], b[NJ];
       const double* pa = PA + (k0 + (lane & 3)) * PS + wr * 32 + (lane >> 2);
-      const double* pb = PBm + (k0 + (lane & 3)) * PS + wc * 64 + (lane >> 2);
+      const double* pb = PBm + (k0 + (lane & 3)) * PS + wc * (TN / 2) + (lane >> 2);
 #pragma unroll
       for (int i = 0; i < 4; ++i) a[i] = pa[i * 8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) b[j] = pb[j * 8];
+      for (int j = 0; j < NJ; ++j) b[j] = pb[j * 8];
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) dmma_m8n8k4(acc[i][j], a[i], b[j]);
+        for (int j = 0; j < NJ; ++j) dmma_m8n8k4(acc[i][j], a[i], b[j]);
     }
     // the __syncthreads at the top of the next block's chunk loop protects the panels
   }
@@ -202,13 +222,13 @@ __global__ void __launch_bounds__(NT, 1) kmn_gram_f64_kernel(const GramParams p)
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < NJ; ++j) {
       const int row = ti * kTile + wr * 32 + i * 8 + (lane >> 2);
-      const int cc = tj * kTile + wc * 64 + j * 8 + 2 * (lane & 3);
+      const int cc = tj * TN + wc * (TN / 2) + j * 8 + 2 * (lane & 3);
       *reinterpret_cast<double2*>(Gp + static_cast<size_t>(row) * p.m_pad + cc) =
           make_double2(acc[i][j][0], acc[i][j][1]);
     }
-  if (diag && tid < kTile) p.bpart[static_cast<size_t>(blockIdx.y) * p.m_pad + ti * kTile + tid] = bacc;
+  if (owns_b && tid < kTile) p.bpart[static_cast<size_t>(blockIdx.y) * p.m_pad + ti * kTile + tid] = bacc;
 }
 
 // G[i][j] (+ mirror) += sum_s Gpart[s][i][j] for i >= j ;  b[i] += sum_s bpart[s][i]
@@ -234,28 +254,30 @@ __global__ void gram_reduce_kernel(double* __restrict__ G, double* __restrict__ 
 }  // namespace
 
 cudaError_t launch_gram_f64(const GramParams& p, bool strict_elements, cudaStream_t s) {
-  const int nt = p.n_tiles_1d * (p.n_tiles_1d + 1) / 2;
-  dim3 grid(nt, p.n_slices);
   if (strict_elements) {
+    const int nt = p.n_tiles_1d * (p.n_tiles_1d + 1) / 2;
+    dim3 grid(nt, p.n_slices);
     constexpr size_t smem = gram_smem_bytes<double>();
     static bool attr_set = false;
     if (!attr_set) {
-      cudaError_t e = cudaFuncSetAttribute(kmn_gram_f64_kernel<double>,
+      cudaError_t e = cudaFuncSetAttribute(kmn_gram_f64_kernel<double, 128>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return e;
       attr_set = true;
     }
-    kmn_gram_f64_kernel<double><<<grid, NT, smem, s>>>(p);
+    kmn_gram_f64_kernel<double, 128><<<grid, NT, smem, s>>>(p);
   } else {
+    const int nt = p.n_tiles_1d * (p.n_tiles_1d + 1);       // 128 x 64 staircase; two CTAs per SM
+    dim3 grid(nt, p.n_slices);
     constexpr size_t smem = gram_smem_bytes<float>();
     static bool attr_set = false;
     if (!attr_set) {
-      cudaError_t e = cudaFuncSetAttribute(kmn_gram_f64_kernel<float>,
+      cudaError_t e = cudaFuncSetAttribute(kmn_gram_f64_kernel<float, 64>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return e;
       attr_set = true;
     }
-    kmn_gram_f64_kernel<float><<<grid, NT, smem, s>>>(p);
+    kmn_gram_f64_kernel<float, 64><<<grid, NT, smem, s>>>(p);
   }
   return cudaGetLastError();
 }
