@@ -16,6 +16,13 @@ private[ml] object NativeProjectedProcess {
   @native def finish(ctx: Long, g: Array[Double], b: Array[Double]): Unit
   @native def magic(ctx: Long, g: Array[Double], b: Array[Double], magicVector: Array[Double],
                     magicMatrix: Array[Double]): Unit
+  // hyper-parameter objective: experts resident on the GPU, one native call per objective evaluation
+  @native def expertsUpload(ctx: Long, x: Array[Double], y: Array[Double], offsets: Array[Long], d: Int): Unit
+  /** [value, gradient...]; tol <= 0: regression NLL (GPR:55-68), tol > 0: the classifier's Laplace objective. */
+  @native def objective(ctx: Long, types: Array[Int], scales: Array[Double], sigmas: Array[Double], betas: Array[Double],
+                        d: Int, hKind: Array[Int], hTerm: Array[Int], hDim: Array[Int], hValue: Array[Double],
+                        hCoef: Array[Double], tol: Double): Array[Double]
+  @native def expertsGetF(ctx: Long, f: Array[Double]): Unit
 
   /** Flattens the kernel DSL tree into (type, scale, sigma, beta) terms; `scale` multiplies down the tree
     * (ScalarTimesKernel.scala:20-28), Eye terms are kept (they carry whiteNoiseVar / the K_mm diagonal). */
@@ -25,6 +32,38 @@ private[ml] object NativeProjectedProcess {
     case a: ARDRBFKernel       => Seq((0, scale, 0d, a.getHyperparameters.toArray))
     case r: RBFKernel          => Seq((1, scale, r.getHyperparameters(0), Array.empty[Double]))
     case _: EyeKernel          => Seq((2, scale, 0d, Array.empty[Double]))
+  }
+
+  /** One descriptor per hyper-parameter, in `getHyperparameters` order (depth first, a trainable scalar PREPENDED to
+    * its inner kernel's vector, ScalarTimesKernel.scala:76-82), saying how the kernel matrix depends on it:
+    * (kind, term, dim, value, coef) with kind 0 = trainable scalar (coef(t) = d scale_t / d theta for every flattened
+    * term t, i.e. the scale of the inner term WITHOUT this C, ScalarTimesKernel.scala:93-97), 1 = ARD beta_k of term t
+    * (ARDRBFKernel.scala:61-79), 2 = RBF sigma of term t (RBFKernel.scala:56-64).  `offset` = index of the first
+    * flattened term of this sub-tree. */
+  case class Hyper(kind: Int, term: Int, dim: Int, value: Double, coef: Map[Int, Double])
+  def describe(k: Kernel, scale: Double = 1d, offset: Int = 0): Seq[Hyper] = k match {
+    case s: SumOfKernels =>
+      describe(s.kernel1, scale, offset) ++ describe(s.kernel2, scale, offset + flatten(s.kernel1).length)
+    case t: TrainableScalarTimesKernel =>
+      val inner = flatten(t.innerKernel, scale)
+      Hyper(0, 0, 0, t.scalar, inner.zipWithIndex.map { case (term, i) => (offset + i) -> term._2 }.toMap) +:
+        describe(t.innerKernel, scale * t.scalar, offset)
+    case c: ScalarTimesKernel => describe(c.innerKernel, scale * c.scalar, offset)
+    case a: ARDRBFKernel      => a.getHyperparameters.toArray.zipWithIndex.map { case (b, j) => Hyper(1, offset, j, b, Map.empty) }
+    case r: RBFKernel         => Seq(Hyper(2, offset, 0, r.getHyperparameters(0), Map.empty))
+    case _: EyeKernel         => Seq.empty
+  }
+
+  /** One objective evaluation on an executor's resident experts (the body of the treeAggregate in
+    * GaussianProcessCommons.scala:73-78): returns (value, gradient). */
+  def evaluate(ctx: Long, kernel: Kernel, d: Int, tol: Double): (Double, BDV[Double]) = {
+    val terms = flatten(kernel)
+    val hs = describe(kernel)
+    val coef = hs.flatMap(h => terms.indices.map(t => h.coef.getOrElse(t, 0d))).toArray      // [h][n_terms]
+    val out = objective(ctx, terms.map(_._1).toArray, terms.map(_._2).toArray, terms.map(_._3).toArray,
+      terms.flatMap(_._4).toArray, d, hs.map(_.kind).toArray, hs.map(_.term).toArray, hs.map(_.dim).toArray,
+      hs.map(_.value).toArray, coef, tol)
+    (out(0), new BDV(out.drop(1)))
   }
 }
 
