@@ -43,7 +43,7 @@ import oracle
 from oracle.regression import bcm_objective
 from oracle import cpu_baseline
 ns = 20000
-fac = lambda: oracle.get_kernel(lambda: 1 * oracle.ARDRBFKernel(np.full(d, np.sqrt(18.0 / d))) + oracle.const(1) * oracle.EyeKernel(), 1e-4)
+fac = oracle.get_kernel(lambda: 1 * oracle.ARDRBFKernel(np.full(d, np.sqrt(18.0 / d))) + oracle.const(1) * oracle.EyeKernel(), 1e-4)
 ex = oracle.get_expert_labels_and_kernels(X[:ns].astype(np.float64), y[:ns], fac, n_e)
 th0 = fac().get_hyperparameters()
 t0 = time.perf_counter(); bcm_objective(ex, th0); dt = time.perf_counter() - t0
