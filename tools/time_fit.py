@@ -23,12 +23,14 @@ gp = (sg.GaussianProcessRegression().setKernel(lambda: 1 * sg.ARDRBFKernel(np.fu
 # warm-up: CUDA context, cuSOLVER handles, kernels' first-launch costs
 sg.GaussianProcessRegression().setKernel(lambda: 1 * sg.ARDRBFKernel(d) + sg.const(1) * sg.EyeKernel()).setActiveSetSize(64).setMaxIter(2).fit(X[:20000], y[:20000])
 
-t0 = time.perf_counter()
 from spark_gp_b200.hyperopt import optimize_hypers
-theta = optimize_hypers(gp, X, y)
-t1 = time.perf_counter()
-model = gp._produce_model(X, y, theta)
-t2 = time.perf_counter()
+for rep in range(2):          # the first pass also pays one-off costs (cuSOLVER/cuBLAS kernels for m x m, allocations)
+    t0 = time.perf_counter()
+    theta = optimize_hypers(gp, X, y)
+    t1 = time.perf_counter()
+    model = gp._produce_model(X, y, theta)
+    t2 = time.perf_counter()
+    print("pass %d: hyperopt %.3f s, stats+tail %.3f s" % (rep, t1 - t0, t2 - t1), flush=True)
 info = gp.last_objective
 print("fit N=%d d=%d m=%d n_e=%d maxIter=%d: total %.3f s = hyperopt %.3f s (%d objective evaluations, %d L-BFGS-B iterations, %.1f ms each incl. host) + stats+tail %.3f s"
       % (N_, d, m, n_e, max_iter, t2 - t0, t1 - t0, info["evaluations"], info["iterations"], 1e3 * (t1 - t0) / max(info["evaluations"], 1), t2 - t1), flush=True)
