@@ -27,6 +27,8 @@
 // Why fp64 accumulation: tools/precision_study.py -- the posterior mean needs the Gram accumulated to
 // better than fp32 (fp16 hi/lo operands + fp32 accumulators already sit AT the 1e-5 parity bound for
 // N=1e5 and degrade with N), while fp32-accurate *elements* with exact accumulation are 50x inside it.
+#include <type_traits>
+
 #include "sgp_internal.h"
 
 namespace sgp {
@@ -39,13 +41,20 @@ constexpr int NT = 256;           // threads per CTA (8 warps: 4 x 2 grid of 32x
 
 template <typename ET> struct ElemOps;
 template <> struct ElemOps<float> {
-  static __device__ __forceinline__ float ex(float q) { return expf(-q); }
+  // coordinates are pre-scaled by sqrt(log2 e) at staging time, so exp(-q) = 2^(-q'): one MUFU.EX2 (2 ulp)
+  static constexpr double kPrescale = 1.2011224087864498;     // sqrt(log2(e))
+  static __device__ __forceinline__ float ex(float q) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(-q));
+    return y;
+  }
   static __device__ __forceinline__ void ld4(const float* p, float (&v)[4]) {
     float4 t = *reinterpret_cast<const float4*>(p);
     v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
   }
 };
 template <> struct ElemOps<double> {
+  static constexpr double kPrescale = 1.0;
   static __device__ __forceinline__ double ex(double q) { return exp(-q); }
   static __device__ __forceinline__ void ld4(const double* p, double (&v)[4]) {
     double2 a = *reinterpret_cast<const double2*>(p);
@@ -62,17 +71,19 @@ __device__ __forceinline__ void dmma_m8n8k4(double (&c)[2], double a, double b) 
 
 template <typename ET>
 constexpr size_t gram_smem_bytes() {
-  return sizeof(double) * (2 * PB * PS + 2 * PB) + sizeof(ET) * (DC * 256 + PB * DC);
+  constexpr int NBUF = (sizeof(ET) == 4) ? 2 : 1;     // fp32 elements: panels and x staging are double buffered (pipelined loop)
+  return sizeof(double) * (NBUF * 2 * PB * PS + 2 * PB) + sizeof(ET) * (DC * 256 + NBUF * PB * DC);
 }
 
 template <typename ET, int TN>
 __global__ void __launch_bounds__(NT, (TN == 64) ? 2 : 1) kmn_gram_f64_kernel(const GramParams p) {
   constexpr int NJ = TN / 16;                                // 8-column B fragments per warp (warp tile 32 x TN/2)
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  double* panel = reinterpret_cast<double*>(smem_raw);      // [2][PB][PS]
-  double* ys2 = panel + 2 * PB * PS;                         // [2][PB] (double buffered by block parity)
+  constexpr int NBUF = (sizeof(ET) == 4) ? 2 : 1;
+  double* panel = reinterpret_cast<double*>(smem_raw);      // [NBUF][2][PB][PS]
+  double* ys2 = panel + NBUF * 2 * PB * PS;                  // [2][PB] (double buffered by block parity)
   ET* zs = reinterpret_cast<ET*>(ys2 + 2 * PB);              // [DC/4][256][4]
-  ET* xs = zs + DC * 256;                                    // [PB][DC]
+  ET* xs = zs + DC * 256;                                    // [NBUF][PB][DC]
 
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
@@ -111,13 +122,15 @@ __global__ void __launch_bounds__(NT, (TN == 64) ? 2 : 1) kmn_gram_f64_kernel(co
   long long blk_hi = blk_lo + bps;
   if (blk_hi > total_blocks) blk_hi = total_blocks;
 
+  constexpr bool kPacked = sizeof(ET) == 4;                  // fp32 elements: packed f32x2 arithmetic, z staged negated
+  constexpr double kZSign = kPacked ? -1.0 : 1.0;
   const bool z_resident = (p.n_terms == 1 && p.dpad <= DC);
 
   auto load_z_chunk = [&](int term, int c0, int clen) {
     // (threads 192..255 of a 128x64 tile have no column: their zrow may point past the padded active set)
     const bool in_range = zrow < p.m_pad;
     const double* src = p.Zs + (static_cast<size_t>(term) * p.m_pad + (in_range ? zrow : 0)) * p.dpad + c0;
-    for (int k = 0; k < clen; ++k) zs[((k >> 2) * 256 + tid) * 4 + (k & 3)] = in_range ? static_cast<ET>(src[k]) : ET(0);
+    for (int k = 0; k < clen; ++k) zs[((k >> 2) * 256 + tid) * 4 + (k & 3)] = in_range ? static_cast<ET>(kZSign * ElemOps<ET>::kPrescale * src[k]) : ET(0);
   };
   auto load_x_chunk = [&](long long pt0, int term, int c0, int clen) {
     const double* bt = p.beta + term * p.dpad + c0;
@@ -129,7 +142,7 @@ __global__ void __launch_bounds__(NT, (TN == 64) ? 2 : 1) kmn_gram_f64_kernel(co
         const size_t off = static_cast<size_t>(pt) * p.d + c0 + k;
         v = p.x_is_f32 ? static_cast<double>(reinterpret_cast<const float*>(p.X)[off])
                        : reinterpret_cast<const double*>(p.X)[off];
-        v *= bt[k];
+        v *= bt[k] * ElemOps<ET>::kPrescale;
       }
       xs[pp * DC + k] = static_cast<ET>(v);
     }
@@ -144,18 +157,127 @@ __global__ void __launch_bounds__(NT, (TN == 64) ? 2 : 1) kmn_gram_f64_kernel(co
     for (int j = 0; j < NJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
   double bacc = 0.0;
 
+
+  // ================= pipelined loop (fp32 elements, one kernel term, d <= 32: the common case) =========================
+  // With the panel phase and the DMMA phase separated by barriers the tensor pipe idles while panels are built -- and
+  // two co-resident CTAs do not fix that: they phase-lock (both share the pipe in the DMMA phase, finish together, then
+  // both build panels): measured 45 % DMMA utilisation either way.  Here the DMMAs of block i and the panel build of
+  // block i+1 sit in the same barrier-free region (double-buffered panels / x staging, ONE __syncthreads per block),
+  // so warps drift apart and FFMA2 / MUFU work of some warps fills the issue slots of warps blocked on the tensor pipe.
+  if constexpr (kPacked) {
+    if (z_resident) {
+      const int nk4 = p.dpad >> 2;                               // <= 8
+      const double* bt = p.beta;
+      // this thread's two elements of a 16-point x 32-dim staging tile
+      const int e0 = tid, e1 = tid + NT;
+      auto fetch_x = [&](long long blk, int e) -> float {
+        const int pp = e / DC, k = e % DC;
+        const long long pt = blk * PB + pp;
+        if (blk < blk_hi && k < p.d && pt < p.n) {
+          const size_t off = static_cast<size_t>(pt) * p.d + k;
+          const double v = p.x_is_f32 ? static_cast<double>(reinterpret_cast<const float*>(p.X)[off])
+                                      : reinterpret_cast<const double*>(p.X)[off];
+          return static_cast<float>(v * bt[k] * ElemOps<ET>::kPrescale);
+        }
+        return 0.f;
+      };
+      auto panel_block = [&](long long blk, const float* xb, double* pbuf, int k4_lo, int k4_hi, float2 (&q)[PB]) {
+        for (int k4 = k4_lo; k4 < k4_hi; ++k4) {
+          const float4 z = *reinterpret_cast<const float4*>(zs + (k4 * 256 + tid) * 4);      // negated at staging
+          const float2 z01 = make_float2(z.x, z.y), z23 = make_float2(z.z, z.w);
+#pragma unroll
+          for (int pp = 0; pp < PB; ++pp) {
+            const float4 x = *reinterpret_cast<const float4*>(xb + pp * DC + k4 * 4);         // warp-wide broadcast
+            const float2 d01 = __fadd2_rn(make_float2(x.x, x.y), z01), d23 = __fadd2_rn(make_float2(x.z, x.w), z23);
+            q[pp] = __ffma2_rn(d01, d01, q[pp]);
+            q[pp] = __ffma2_rn(d23, d23, q[pp]);
+          }
+        }
+        (void)blk; (void)pbuf;
+      };
+      auto panel_store = [&](long long blk, double* pbuf, const float2 (&q)[PB]) {
+        const float sc = static_cast<float>(p.scale[0]);
+        double* dst = pbuf + pan * PB * PS + col;
+        const long long pt0 = blk * PB;
+#pragma unroll
+        for (int pp = 0; pp < PB; ++pp)
+          dst[pp * PS] = (zvalid && pt0 + pp < p.n) ? static_cast<double>(sc * ElemOps<ET>::ex(q[pp].x + q[pp].y)) : 0.0;
+      };
+      // ---- prologue: x(blk_lo) -> xs[0]; panel(blk_lo) -> panel[0]; x(blk_lo+1) -> xs[1]
+      xs[e0] = fetch_x(blk_lo, e0); xs[e1] = fetch_x(blk_lo, e1);
+      if (tid < PB) ys2[tid] = (blk_lo * PB + tid < p.n) ? p.y[blk_lo * PB + tid] : 0.0;
+      __syncthreads();
+      if (blk_lo < blk_hi && elem_active) {
+        float2 q[PB];
+#pragma unroll
+        for (int i = 0; i < PB; ++i) q[i] = make_float2(0.f, 0.f);
+        panel_block(blk_lo, xs, panel, 0, nk4, q);
+        panel_store(blk_lo, panel, q);
+      }
+      xs[PB * DC + e0] = fetch_x(blk_lo + 1, e0); xs[PB * DC + e1] = fetch_x(blk_lo + 1, e1);
+      __syncthreads();
+      for (long long blk = blk_lo; blk < blk_hi; ++blk) {
+        const int cur = static_cast<int>((blk - blk_lo) & 1), nxt = cur ^ 1;
+        const double* pcur = panel + cur * 2 * PB * PS;
+        double* pnxt = panel + nxt * 2 * PB * PS;
+        const float* xnxt = xs + nxt * PB * DC;
+        const bool has_next = blk + 1 < blk_hi;
+        // global loads for block blk+2 are issued first and stored at the end of the region
+        const float xa = fetch_x(blk + 2, e0), xb2 = fetch_x(blk + 2, e1);
+        double ynext = 0.0;
+        if (tid < PB && has_next) ynext = ((blk + 1) * PB + tid < p.n) ? p.y[(blk + 1) * PB + tid] : 0.0;
+        if (owns_b && tid < kTile) {
+          const double* ys = ys2 + cur * PB;
+#pragma unroll
+          for (int pp = 0; pp < PB; ++pp) bacc = fma(pcur[pp * PS + tid], ys[pp], bacc);
+        }
+        float2 q[PB];
+#pragma unroll
+        for (int i = 0; i < PB; ++i) q[i] = make_float2(0.f, 0.f);
+        const bool build = has_next && elem_active;
+        const double* PA = pcur;
+        const double* PBm = diag ? pcur + joff : pcur + PB * PS;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          // panel work of block blk+1 spread over the four DMMA k-steps of block blk
+          if (build) panel_block(blk + 1, xnxt, pnxt, (ks * nk4) >> 2, ((ks + 1) * nk4) >> 2, q);
+          const int k0 = ks * 4;
+          double a[4], b[NJ];
+          const double* pa = PA + (k0 + (lane & 3)) * PS + wr * 32 + (lane >> 2);
+          const double* pb = PBm + (k0 + (lane & 3)) * PS + wc * (TN / 2) + (lane >> 2);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) a[i] = pa[i * 8];
+#pragma unroll
+          for (int j = 0; j < NJ; ++j) b[j] = pb[j * 8];
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) dmma_m8n8k4(acc[i][j], a[i], b[j]);
+        }
+        if (build) panel_store(blk + 1, pnxt, q);
+        float* xdst = xs + cur * PB * DC;                        // consumed in the previous region
+        xdst[e0] = xa; xdst[e1] = xb2;
+        if (tid < PB && has_next) ys2[nxt * PB + tid] = ynext;
+        __syncthreads();
+      }
+      blk_hi = blk_lo;                                           // the generic loop below has nothing left to do
+    }
+  }
+
   for (long long blk = blk_lo; blk < blk_hi; ++blk) {
     const long long pt0 = blk * PB;
     // ---------------- phase 1: panels -----------------------------------------------------------
-    ET val[PB];
-#pragma unroll
-    for (int i = 0; i < PB; ++i) val[i] = ET(0);
+    // fp32 elements: q is accumulated as float2 (even / odd feature dims) with packed f32x2 FADD/FFMA -- half the
+    // instructions of the scalar form; per-term results go straight into the panel (the thread owns its column).
     double* ys = ys2 + ((blk - blk_lo) & 1) * PB;   // stragglers of block k-1 may still read the other half
     if (tid < PB) ys[tid] = (pt0 + tid < p.n) ? p.y[pt0 + tid] : 0.0;
+    double* dst = panel + pan * PB * PS + col;
     for (int term = 0; term < p.n_terms; ++term) {
-      ET q[PB];
+      typename std::conditional<kPacked, float2, ET>::type q[PB];
 #pragma unroll
-      for (int i = 0; i < PB; ++i) q[i] = ET(0);
+      for (int i = 0; i < PB; ++i) {
+        if constexpr (kPacked) q[i] = make_float2(0.f, 0.f); else q[i] = ET(0);
+      }
       for (int c0 = 0; c0 < p.dpad; c0 += DC) {
         const int clen = (p.dpad - c0 < DC) ? (p.dpad - c0) : DC;
         __syncthreads();                       // previous users of xs/zs (and of the panels) are done
@@ -164,16 +286,28 @@ __global__ void __launch_bounds__(NT, (TN == 64) ? 2 : 1) kmn_gram_f64_kernel(co
         __syncthreads();
         if (elem_active) {
           for (int k4 = 0; k4 < (clen >> 2); ++k4) {
-            ET z4[4];
-            ElemOps<ET>::ld4(zs + (k4 * 256 + tid) * 4, z4);
+            if constexpr (kPacked) {
+              const float4 z = *reinterpret_cast<const float4*>(zs + (k4 * 256 + tid) * 4);      // already negated
+              const float2 z01 = make_float2(z.x, z.y), z23 = make_float2(z.z, z.w);
 #pragma unroll
-            for (int pp = 0; pp < PB; ++pp) {
-              ET x4[4];
-              ElemOps<ET>::ld4(xs + pp * DC + k4 * 4, x4);   // warp-wide broadcast
+              for (int pp = 0; pp < PB; ++pp) {
+                const float4 x = *reinterpret_cast<const float4*>(xs + pp * DC + k4 * 4);          // warp-wide broadcast
+                const float2 d01 = __fadd2_rn(make_float2(x.x, x.y), z01), d23 = __fadd2_rn(make_float2(x.z, x.w), z23);
+                q[pp] = __ffma2_rn(d01, d01, q[pp]);
+                q[pp] = __ffma2_rn(d23, d23, q[pp]);
+              }
+            } else {
+              ET z4[4];
+              ElemOps<ET>::ld4(zs + (k4 * 256 + tid) * 4, z4);
 #pragma unroll
-              for (int c = 0; c < 4; ++c) {
-                const ET df = x4[c] - z4[c];
-                q[pp] = fma(df, df, q[pp]);
+              for (int pp = 0; pp < PB; ++pp) {
+                ET x4[4];
+                ElemOps<ET>::ld4(xs + pp * DC + k4 * 4, x4);   // warp-wide broadcast
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                  const ET df = x4[c] - z4[c];
+                  q[pp] = fma(df, df, q[pp]);
+                }
               }
             }
           }
@@ -182,14 +316,13 @@ __global__ void __launch_bounds__(NT, (TN == 64) ? 2 : 1) kmn_gram_f64_kernel(co
       if (elem_active) {
         const ET sc = static_cast<ET>(p.scale[term]);
 #pragma unroll
-        for (int pp = 0; pp < PB; ++pp) val[pp] = fma(sc, ElemOps<ET>::ex(q[pp]), val[pp]);
+        for (int pp = 0; pp < PB; ++pp) {
+          ET qq;
+          if constexpr (kPacked) qq = q[pp].x + q[pp].y; else qq = q[pp];
+          const double v = (zvalid && pt0 + pp < p.n) ? static_cast<double>(sc * ElemOps<ET>::ex(qq)) : 0.0;
+          dst[pp * PS] = (term == 0) ? v : dst[pp * PS] + v;
+        }
       }
-    }
-    if (elem_active) {
-      double* dst = panel + pan * PB * PS + col;
-#pragma unroll
-      for (int pp = 0; pp < PB; ++pp)
-        dst[pp * PS] = (zvalid && pt0 + pp < p.n) ? static_cast<double>(val[pp]) : 0.0;
     }
     __syncthreads();
     // ---------------- b_I += P_I^T y (diagonal tiles) ----------------------------------------------
