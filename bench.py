@@ -244,7 +244,9 @@ def run_ours(args):
         kms, kn = eng.gram_kernel_time()
         kern_ms += kms; kern_n += kn
         l2_flush()
-    barrier()
+        # every step ends in an all-reduce, so a rank that starts its step early spends the skew waiting INSIDE its
+        # event-timed region: line the ranks up again (outside the timed region) before the next step
+        barrier()
     t_wall1 = time.perf_counter()
     wall_ms = 1e3 * (t_wall1 - t_wall0)
     launches = eng.launch_count() - launches0
