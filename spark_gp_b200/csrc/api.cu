@@ -70,9 +70,11 @@ static int ensure_partials(Ctx* c, int n_slices) {
 }
 
 // One fused-kernel launch over n device-resident points + the deterministic slice reduction.
-static int launch_stats(Ctx* c, const void* dX, int x_is_f32, const double* dy, long long n, long long n_call) {
-  // n: points of this launch; n_call: points of the whole accumulate call (AUTO's size gate looks at the call, so the
-  // chunks of one shard never mix kernels)
+static int launch_stats(Ctx* c, const void* dX, int x_is_f32, const double* dy, long long n, long long n_call,
+                        bool first_of_call) {
+  // n: points of this launch; n_call: points of the whole accumulate call.  AUTO decides per CALL -- the size gate
+  // looks at n_call and the magnitude gate at the first chunk -- so the chunks of one shard never mix kernels (and
+  // only the first chunk pays the device->host round trip of the gate)
   if (n <= 0) return SGP_OK;
   const int nt1 = c->m_pad / kTile;
   const int ntiles = nt1 * (nt1 + 1) / 2;
@@ -97,6 +99,7 @@ static int launch_stats(Ctx* c, const void* dX, int x_is_f32, const double* dy, 
   // is the two dropped low-order digit products, tools/i8_error_model.py) and small scaled norms (gate below).
   // Smaller shards stay on the fp64 DMMA kernel (2e-7), which is fast enough at that size.
   bool use_i8 = c->i8_ok && (c->precision == SGP_PREC_I8 || (c->precision == SGP_PREC_AUTO && n_call >= 262144));
+  if (c->precision == SGP_PREC_AUTO && !first_of_call) use_i8 = use_i8 && c->call_i8;
   if (c->precision == SGP_PREC_I8 && !c->i8_ok)
     return fail(c, SGP_E_BADARG, "SGP_PREC_I8 needs a kernel with exactly one non-Eye term and d <= 32");
   if (use_i8) {
@@ -113,7 +116,7 @@ static int launch_stats(Ctx* c, const void* dX, int x_is_f32, const double* dy, 
       SGP_CUDA(c, cudaMalloc(&c->dI8Ys, yb));
       c->i8_ys_bytes = yb;
     }
-    const bool gate = (c->precision == SGP_PREC_AUTO);
+    const bool gate = (c->precision == SGP_PREC_AUTO) && first_of_call;
     if (gate) SGP_CUDA(c, cudaMemsetAsync(c->dI8NormSum, 0, sizeof(double), c->stream));
     SGP_CUDA(c, launch_i8_prep_points(c->dI8Xt, c->dI8Ys, dX, x_is_f32, dy, n, c->d, c->dI8Scale, c->dI8Centre,
                                       c->dI8Flags, gate ? c->dI8NormSum : nullptr, c->stream));
@@ -129,6 +132,7 @@ static int launch_stats(Ctx* c, const void* dX, int x_is_f32, const double* dy, 
       if (xsum / static_cast<double>(n) + c->i8_z_norm_mean > c->i8_norm_budget) use_i8 = false;
     }
   }
+  if (first_of_call) c->call_i8 = use_i8;
   if (use_i8) c->i8_used = true;
   c->last_path = use_i8 ? SGP_PREC_I8 : (c->precision == SGP_PREC_F64_STRICT ? SGP_PREC_F64_STRICT : SGP_PREC_F64);
   cudaEvent_t e0, e1;
@@ -362,7 +366,7 @@ int sgp_stats_accumulate_device(sgp_ctx* h, const void* dX, int32_t x_is_f32, co
   if (n < 0 || (n > 0 && (!dX || !dy))) return fail(c, SGP_E_BADARG, "null shard");
   SGP_CUDA(c, cudaSetDevice(c->device));
   if (c->kf.n_terms == 0) return SGP_OK;   // only Eye terms: the cross kernel is identically zero
-  return launch_stats(c, dX, x_is_f32, dy, n, n);
+  return launch_stats(c, dX, x_is_f32, dy, n, n, true);
 }
 
 int sgp_stats_accumulate(sgp_ctx* h, const void* X, int32_t x_is_f32, const double* y, int64_t n) {
@@ -406,7 +410,7 @@ int sgp_stats_accumulate(sgp_ctx* h, const void* X, int32_t x_is_f32, const doub
                                 c->copy_stream));
     SGP_CUDA(c, cudaEventRecord(c->stage_ready[buf], c->copy_stream));
     SGP_CUDA(c, cudaStreamWaitEvent(c->stream, c->stage_ready[buf], 0));
-    int rc = launch_stats(c, c->stageX[buf], x_is_f32, c->stageY[buf], cn, n);
+    int rc = launch_stats(c, c->stageX[buf], x_is_f32, c->stageY[buf], cn, n, p0 == 0);
     if (rc != SGP_OK) return rc;
     SGP_CUDA(c, cudaEventRecord(c->stage_free[buf], c->stream));
   }

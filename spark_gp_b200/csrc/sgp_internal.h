@@ -72,6 +72,7 @@ struct Ctx {
   // tcgen05 int8 path (gram_i8.cu)
   bool i8_ok = false;            // kernel/shape qualifies (one non-Eye term, d <= 32)
   bool i8_used = false;          // an int8 launch contributed to the current statistics
+  bool call_i8 = false;          // AUTO's decision for the current accumulate call (taken on its first chunk)
   double* dI8Scale = nullptr;    // [dp16] sqrt(log2 e) * beta_k
   double* dI8Centre = nullptr;   // [dp16] per-feature centre (active-set mean)
   int* dI8Flags = nullptr;       // bit 0: coordinates out of fp16 operand range
