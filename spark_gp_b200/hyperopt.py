@@ -22,10 +22,36 @@ def group_for_experts(n_points: int, dataset_size_for_expert: int):
 
 
 def pack_experts(X, y, dataset_size_for_expert: int):
-    groups = group_for_experts(len(X), dataset_size_for_expert)
-    order = np.concatenate(groups)
-    offsets = np.concatenate([[0], np.cumsum([len(g) for g in groups])])
-    return np.ascontiguousarray(np.asarray(X, dtype=np.float64)[order]), np.asarray(y, dtype=np.float64)[order], offsets
+    """Expert-major copy of (X, y) for sgp_experts_upload: expert e = points e, e+E, e+2E, ... (GPC:26-31).
+    The grouping is a strided layout, so the bulk of the copy is one reshape/transpose (k = N // E full rounds);
+    the first N % E experts get one more point each."""
+    X = np.asarray(X, dtype=np.float64)
+    y = np.asarray(y, dtype=np.float64)
+    n, d = X.shape
+    n_experts = int(np.floor(n / dataset_size_for_expert + 0.5))           # Math.round(N / n_e), GPC:27
+    if n_experts <= 0:
+        raise ZeroDivisionError("numberOfExperts == 0 (N < datasetSizeForExpert / 2)")
+    k, r = divmod(n, n_experts)                       # every expert has k points, the first r experts k + 1
+    sizes = np.full(n_experts, k, dtype=np.int64)
+    sizes[:r] += 1
+    offsets = np.concatenate([[0], np.cumsum(sizes)])
+    Xp = np.empty((n, d)); yp = np.empty(n)
+    if r == 0:
+        Xp.reshape(n_experts, k, d)[...] = X.reshape(k, n_experts, d).transpose(1, 0, 2)
+        yp.reshape(n_experts, k)[...] = y.reshape(k, n_experts).T
+    else:
+        # experts < r: k+1 points (rows e, e+E, ..., e+kE); experts >= r: k points
+        head_X = X[:k * n_experts].reshape(k, n_experts, d)
+        head_y = y[:k * n_experts].reshape(k, n_experts)
+        a = Xp[:offsets[r]].reshape(r, k + 1, d)
+        a[:, :k] = head_X[:, :r].transpose(1, 0, 2)
+        a[:, k] = X[k * n_experts:]
+        b = yp[:offsets[r]].reshape(r, k + 1)
+        b[:, :k] = head_y[:, :r].T
+        b[:, k] = y[k * n_experts:]
+        Xp[offsets[r]:].reshape(n_experts - r, k, d)[...] = head_X[:, r:].transpose(1, 0, 2)
+        yp[offsets[r]:].reshape(n_experts - r, k)[...] = head_y[:, r:].T
+    return Xp, yp, offsets
 
 
 class BcmObjective:
