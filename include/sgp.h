@@ -149,6 +149,12 @@ int sgp_laplace_nll(sgp_ctx* ctx, const sgp_kernel_desc* kernel, const sgp_hyper
 /* The latent modes f (same packed expert-major order as the uploaded points): the `y := f` of GPCls:62-65. */
 int sgp_experts_get_f(sgp_ctx* ctx, double* f_out);
 
+/* Installs a caller-supplied (vector v, SYMMETRIC matrix M) in place of the pair sgp_magic computes, so that sgp_predict
+ * returns  mean_t = k(x_t, Z) . v  and  var_t = selfKernel + k(x_t, Z) M k(x_t, Z)^T  for them.  This is the per-point
+ * part of GreedilyOptimizingActiveSetProvider.getNext (commons/ActiveSetProvider.scala:109-113: p_i, q_i, mu_i are
+ * exactly such forms with M = inv(K_mm), inv(sigma2 K_mm + G) and v = magicVector).  Needs sgp_stats_begin. */
+int sgp_set_magic(sgp_ctx* ctx, const double* v, const double* M);
+
 /* ---- prediction:  GPC:121-125 for a block of test vectors ----------------------------------- */
 /* mean_t = k(x_t, Z) . magicVector ;  var_t = selfKernel + k(x_t,Z) magicMatrix k(x_t,Z)^T.
  * X: n x d row-major fp64 host.  var_out may be NULL. */

@@ -6,5 +6,6 @@ from .kernels import (Kernel, ARDRBFKernel, RBFKernel, EyeKernel, ConstantTimesK
                       SumOfKernels, Scalar, WhiteNoiseKernel, const)
 from .engine import (ProjectedProcessEngine, NotPositiveDefiniteException, TrainingVectorsNotInitializedException,
                      MatrixSingularException, SgpError, OperandRangeError)
-from .regression import GaussianProcessRegression, GaussianProcessRegressionModel, RandomActiveSetProvider
+from .regression import (GaussianProcessRegression, GaussianProcessRegressionModel, RandomActiveSetProvider,
+                         GreedilyOptimizingActiveSetProvider)
 from .classification import GaussianProcessClassifier, GaussianProcessClassificationModel

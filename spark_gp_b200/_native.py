@@ -22,7 +22,7 @@ EXPORTS = ["sgp_ctx_create", "sgp_ctx_destroy", "sgp_last_error", "sgp_set_preci
            "sgp_stats_accumulate_device", "sgp_stats_finish", "sgp_sync", "sgp_magic", "sgp_predict",
            "sgp_launch_count", "sgp_gram_kernel_time", "sgp_cross_kernel", "sgp_event_record",
            "sgp_event_elapsed_ms", "sgp_debug_i8_tile", "sgp_debug_i8_timeline", "sgp_last_path", "sgp_experts_upload",
-           "sgp_bcm_nll", "sgp_laplace_nll", "sgp_experts_get_f"]
+           "sgp_bcm_nll", "sgp_laplace_nll", "sgp_experts_get_f", "sgp_set_magic"]
 
 
 class KernelTerm(C.Structure):
@@ -69,6 +69,7 @@ def load() -> C.CDLL:
     lib.sgp_sync.argtypes = [vp]
     lib.sgp_magic.argtypes = [vp, vp, vp, vp, vp]
     lib.sgp_predict.argtypes = [vp, vp, i64, vp, vp]
+    lib.sgp_set_magic.argtypes = [vp, vp, vp]
     lib.sgp_launch_count.argtypes = [vp]
     lib.sgp_launch_count.restype = i64
     lib.sgp_gram_kernel_time.argtypes = [vp, dp, C.POINTER(i64)]

@@ -78,7 +78,7 @@ class GaussianProcessClassifier(GaussianProcessParams):
         f[order] = f_packed
         self.last_latent = f
         # GPCls:62-65 -> produceModel with (f, kernel): the same projected-process path as regression
-        active_set = self._activeSetProvider(self._activeSetSize, X, f, self.getKernel, theta, self._seed)
+        active_set = self._activeSetProvider(self._activeSetSize, X, f, self.getKernel, theta, self._seed, gp=self)
         kernel = self.getKernel().setHyperparameters(theta)
         eng.begin(kernel, active_set)
         eng.accumulate(X, f)

@@ -473,6 +473,20 @@ int sgp_magic(sgp_ctx* h, const double* G_in, const double* b_in, double* magic_
   return run_tail(c, magic_vector, magic_matrix);
 }
 
+int sgp_set_magic(sgp_ctx* h, const double* v, const double* M) {
+  Ctx* c = reinterpret_cast<Ctx*>(h);
+  if (!c) return SGP_E_BADARG;
+  if (!c->begun) return fail(c, SGP_E_STATE, "sgp_stats_begin should have been called first");
+  if (!v || !M) return fail(c, SGP_E_BADARG, "sgp_set_magic: null argument");
+  SGP_CUDA(c, cudaSetDevice(c->device));
+  const size_t mm = static_cast<size_t>(c->m) * c->m;
+  SGP_CUDA(c, cudaMemcpyAsync(c->dMagicVec, v, static_cast<size_t>(c->m) * 8, cudaMemcpyHostToDevice, c->stream));
+  SGP_CUDA(c, cudaMemcpyAsync(c->dMagicMat, M, mm * 8, cudaMemcpyHostToDevice, c->stream));
+  SGP_CUDA(c, cudaStreamSynchronize(c->stream));          // the caller may reuse v, M as soon as we return
+  c->has_magic = true;
+  return SGP_OK;
+}
+
 int sgp_predict(sgp_ctx* h, const double* X, int64_t n, double* mean_out, double* var_out) {
   Ctx* c = reinterpret_cast<Ctx*>(h);
   if (!c) return SGP_E_BADARG;

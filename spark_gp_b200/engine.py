@@ -221,6 +221,15 @@ class ProjectedProcessEngine:
         return mv, mm
 
     # ---- predict --------------------------------------------------------------------------------------
+    def set_magic(self, vector, matrix):
+        """Installs a caller-supplied (vector, symmetric matrix) for `predict`:  mean = k.v,  var = selfKernel + k M k^T
+        (the per-point quadratic forms of the greedy active-set provider, ActiveSetProvider.scala:109-113)."""
+        v = np.ascontiguousarray(vector, dtype=np.float64)
+        M = np.ascontiguousarray(matrix, dtype=np.float64)
+        if v.shape != (self.m,) or M.shape != (self.m, self.m):
+            raise ValueError("set_magic: vector must be m, matrix m x m")
+        self._check(self._lib.sgp_set_magic(self._h, N.ptr(v), N.ptr(M)))
+
     def predict(self, X, with_variance: bool = True):
         X = np.ascontiguousarray(X, dtype=np.float64)
         if X.ndim == 1:

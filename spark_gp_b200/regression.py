@@ -10,13 +10,14 @@ from __future__ import annotations
 import numpy as np
 
 from . import _native as N
-from .engine import ProjectedProcessEngine, OperandRangeError
+from .engine import ProjectedProcessEngine, OperandRangeError, NotPositiveDefiniteException
 from .kernels import Kernel, RBFKernel, EyeKernel, const
 
 
 class ActiveSetProvider:
-    """commons/ActiveSetProvider.scala:13-20."""
-    def __call__(self, activeSetSize, X, y, kernel_factory, optimalHyperparameter, seed):
+    """commons/ActiveSetProvider.scala:13-20.  `gp` (keyword) is the estimator that calls the provider: the reference
+    hands over the grouped RDD of experts, here the provider reads datasetSizeForExpert / device from it if it needs to."""
+    def __call__(self, activeSetSize, X, y, kernel_factory, optimalHyperparameter, seed, gp=None):
         raise NotImplementedError
 
 
@@ -24,7 +25,7 @@ class _RandomActiveSetProvider(ActiveSetProvider):
     """commons/ActiveSetProvider.scala:48-56: uniform sample without replacement.  (Spark's `takeSample`
     RNG stream is not reproduced -- the reference pins no test on it; pass an explicit active set through
     `ExplicitActiveSetProvider` when results must be compared.)"""
-    def __call__(self, activeSetSize, X, y, kernel_factory, optimalHyperparameter, seed):
+    def __call__(self, activeSetSize, X, y, kernel_factory, optimalHyperparameter, seed, gp=None):
         rng = np.random.default_rng(seed)
         idx = rng.choice(len(X), size=min(activeSetSize, len(X)), replace=False)
         return np.asarray(X, dtype=np.float64)[idx]
@@ -37,8 +38,93 @@ class ExplicitActiveSetProvider(ActiveSetProvider):
     def __init__(self, active_set):
         self.active_set = np.asarray(active_set, dtype=np.float64)
 
-    def __call__(self, activeSetSize, X, y, kernel_factory, optimalHyperparameter, seed):
+    def __call__(self, activeSetSize, X, y, kernel_factory, optimalHyperparameter, seed, gp=None):
         return self.active_set
+
+
+class GreedilyOptimizingActiveSetProvider(ActiveSetProvider):
+    """commons/ActiveSetProvider.scala:58-139 (Seeger et al. 2003 forward selection as the reference codes it).
+
+    Every round is one pass of the hot path plus two passes of per-point quadratic forms, all on the GPU:
+      (G, b)  = projected-process statistics for the current active set          (sgp_stats_*, ASP:90-96)
+      p_i     = k_i' inv(K_mm) k_i,  q_i = k_i' inv(s2 K_mm + G) k_i,  mu_i = k_i' magicVector     (sgp_set_magic +
+                sgp_predict, ASP:109-113); the small m x m inverses are host LAPACK like the reference's driver code.
+    Reference semantics kept: `s2` is the kernel's whiteNoiseVar (ASP:76); candidates are folded per expert (point i
+    belongs to expert i % E) with later-wins ties and NaN poisoning, NaN experts are dropped (ASP:108-131), the first
+    expert with the best score wins; points already selected are not excluded.  The first point is `takeSample(1,
+    seed)` in the reference (Spark's RNG stream is unpinned): `first_index` fixes it, else a seeded NumPy draw."""
+
+    def __init__(self, first_index=None, precision=None):
+        self.first_index = first_index
+        self.precision = precision            # None: SGP_PREC_F64 (fp64 DMMA kernel); tests use SGP_PREC_F64_STRICT
+
+    def __call__(self, activeSetSize, X, y, kernel_factory, optimalHyperparameter, seed, gp=None):
+        X64 = np.ascontiguousarray(X, dtype=np.float64)
+        y = np.asarray(y, dtype=np.float64)
+        n = len(X64)
+        n_e = gp._datasetSizeForExpert if gp is not None else 100
+        E = int(np.floor(n / n_e + 0.5))
+        if E <= 0:
+            raise ZeroDivisionError("numberOfExperts == 0 (N < datasetSizeForExpert / 2)")
+        first = self.first_index if self.first_index is not None else int(np.random.default_rng(seed).integers(n))
+        active = X64[[first]].copy()
+        theta = np.asarray(optimalHyperparameter, dtype=np.float64)
+        eng = ProjectedProcessEngine(gp._device if gp is not None else 0)
+        eng.set_precision(N.SGP_PREC_F64 if self.precision is None else self.precision)
+        try:
+            while len(active) < activeSetSize:
+                kernel = kernel_factory().setHyperparameters(theta)
+                active = np.vstack([active, self._get_next(eng, kernel, X64, y, active, E)])
+        finally:
+            eng.close()
+        return active
+
+    @staticmethod
+    def _get_next(eng, kernel, X, y, active, E):
+        m, n = len(active), len(X)
+        terms = kernel.flatten()
+        s2 = kernel.whiteNoiseVar                                   # what ASP:76 passes as `sigma2`
+        kii = sum(t["scale"] for t in terms)                        # trainingKernelDiag == selfKernel (Kernel.scala:111-114)
+        eng.begin(kernel, active)
+        eng.accumulate(X, y)
+        G, b = eng.finish()
+        kmm = eng.cross_kernel(active) + s2 * np.eye(m)             # trainingKernel: Eye terms on the diagonal
+        pdm = s2 * kmm + G
+        if np.linalg.eigvalsh((pdm + pdm.T) * 0.5).min() < 0:       # assertSymPositiveDefinite, PGPH:62-65
+            raise NotPositiveDefiniteException()
+        magic_vector = np.linalg.solve(pdm, b)
+        eng.set_magic(np.zeros(m), np.linalg.inv(kmm))
+        _, v = eng.predict(X)
+        p = v - kii
+        eng.set_magic(magic_vector, np.linalg.inv(pdm))
+        mu, v = eng.predict(X)
+        q = v - kii
+        with np.errstate(all="ignore"):                             # ASP:114-124
+            sigma = np.sqrt(s2)
+            li = np.sqrt(kii - p)
+            ksi = 1.0 / ((sigma / li) ** 2 + 1.0 - q)
+            kappa = ksi * (1.0 + 2.0 * (sigma / li) ** 2)
+            delta = -np.log(sigma / li) - (np.log(ksi) + ksi * (1.0 - kappa) / s2 * (y - mu) ** 2 - kappa + 2.0) / 2.0
+        return X[GreedilyOptimizingActiveSetProvider.select_index(delta, E)]
+
+    @staticmethod
+    def select_index(delta, E: int) -> int:
+        """ASP:108-135 vectorised: per-expert fold (expert e = points e, e+E, ...: any NaN drops the expert, ties go to
+        the LATER point), then the FIRST expert with the maximal score."""
+        n = len(delta)
+        rows = -(-n // E)
+        D = np.full(rows * E, -np.inf)
+        D[:n] = delta
+        D = D.reshape(rows, E)
+        poisoned = np.isnan(D).any(axis=0)
+        if poisoned.all():
+            raise ValueError("empty.max")                           # RDD.max() on an empty RDD
+        Dm = np.where(np.isnan(D), -np.inf, D)
+        best = Dm.max(axis=0)
+        last = rows - 1 - np.argmax(Dm[::-1] == best[None, :], axis=0)
+        best = np.where(poisoned, -np.inf, best)
+        e = int(np.argmax(best))                                    # first expert with the maximal score
+        return int(last[e]) * E + e
 
 
 class GaussianProcessParams:
@@ -125,7 +211,7 @@ class GaussianProcessRegression(GaussianProcessParams):
 
     def _produce_model(self, X, y, theta):
         """produceModel -> projectedProcess  (commons/GaussianProcessCommons.scala:40-59, 102-110)."""
-        active_set = self._activeSetProvider(self._activeSetSize, X, y, self.getKernel, theta, self._seed)
+        active_set = self._activeSetProvider(self._activeSetSize, X, y, self.getKernel, theta, self._seed, gp=self)
         kernel = self.getKernel().setHyperparameters(theta)
         eng = ProjectedProcessEngine(self._device)
 

@@ -512,3 +512,33 @@ def test_classifier_fit_mnist68_fixture():
     assert acc > 0.95
     with pytest.raises(RuntimeError):
         gp.fit(Xtr, ytr + 1.0)
+
+
+@pytest.mark.gpu
+def test_greedy_active_set_provider_matches_oracle():
+    """GreedilyOptimizingActiveSetProvider (ActiveSetProvider.scala:58-139).  Statistics and the per-point
+    quadratic forms come from the GPU (sgp_stats_*, sgp_set_magic + sgp_predict); the selected points must be the ones
+    the CPU restatement selects, round by round (first point given explicitly: Spark's takeSample stream is unpinned)."""
+    from oracle.active_set import greedy_active_set
+    rng = np.random.default_rng(21)
+    n, d, m, n_e = 600, 3, 8, 50
+    X = rng.random((n, d)); y = np.sin(3 * X.sum(1)) + 0.05 * rng.standard_normal(n)
+    beta = np.full(d, 1.7)
+    ofac = oracle.get_kernel(lambda: 1.3 * oracle.ARDRBFKernel(beta) + oracle.const(1) * oracle.EyeKernel(), 1e-2)
+    theta = ofac().get_hyperparameters()
+    experts = oracle.get_expert_labels_and_kernels(X, y, ofac, n_e)
+    for _, k in experts:
+        k.set_hyperparameters(theta)
+    want = greedy_active_set(m, experts, ofac, theta, X[5])
+    gp = (sg.GaussianProcessRegression().setKernel(lambda: 1.3 * sg.ARDRBFKernel(beta) + sg.const(1) * sg.EyeKernel())
+          .setSigma2(1e-2).setDatasetSizeForExpert(n_e).setActiveSetSize(m).setMaxIter(0)
+          .setActiveSetProvider(sg.GreedilyOptimizingActiveSetProvider(first_index=5, precision=N.SGP_PREC_F64_STRICT)))
+    got = gp._activeSetProvider(m, X, y, gp.getKernel, theta, 13, gp=gp)
+    assert got.shape == want.shape
+    assert np.array_equal(got, want), "greedy selection differs from the restatement"
+    # and through fit(): the model is the projected process on that active set
+    model = gp.fit(X, y, hyperparameters=theta)
+    k0 = ofac().set_hyperparameters(theta)
+    pred, _, _ = oracle.projected_process(experts, want, ofac, theta)
+    m0, _ = pred.predict_many(X[:50])
+    assert np.abs(model.predict(X[:50]) - m0).max() / np.abs(m0).max() <= TOL_PRED

@@ -155,3 +155,27 @@ def test_expert_packing_matches_reference_grouping():
     assert np.array_equal(yp[:5], [0, 3, 6, 9, 12]) and np.array_equal(Xp[5], X[1])
     with pytest.raises(ZeroDivisionError):
         group_for_experts(40, 100)
+
+
+def test_greedy_provider_selection_matches_scalar_fold():
+    """GreedilyOptimizingActiveSetProvider.select_index (vectorised) vs the oracle's transcription of the reference's
+    per-expert foldLeft + filter(!isNaN) + max (ActiveSetProvider.scala:108-135)."""
+    from oracle.active_set import _fold_expert
+    rng = np.random.default_rng(2)
+    for trial in range(200):
+        n = int(rng.integers(5, 90)); E = int(rng.integers(1, 9))
+        delta = np.round(rng.standard_normal(n), 1)                 # coarse values: plenty of ties
+        if trial % 3 == 0:
+            delta[rng.integers(n)] = np.nan
+        best = None
+        for e in range(E):
+            md, mi = _fold_expert(delta[e::E])
+            if np.isnan(md) or mi < 0:
+                continue
+            if best is None or not (best[0] >= md):
+                best = (md, mi * E + e)
+        if best is None:
+            with pytest.raises(ValueError):
+                sg.GreedilyOptimizingActiveSetProvider.select_index(delta, E)
+        else:
+            assert sg.GreedilyOptimizingActiveSetProvider.select_index(delta, E) == best[1]

@@ -165,3 +165,52 @@ def test_scaling():
     X = np.array([[1.0, 5.0], [3.0, 5.0]])
     s = oracle.scale(X)
     assert np.allclose(s, [[-1.0, 0.0], [1.0, 0.0]])       # population variance; zero variance -> 1
+
+
+# ---- greedy active-set provider (ActiveSetProvider.scala:58-139) --------------------------------------------------
+def test_greedy_provider_fold_semantics():
+    from oracle.active_set import _fold_expert
+    nan = float("nan")
+    assert _fold_expert(np.array([1.0, 3.0, 2.0])) == (3.0, 1)
+    assert _fold_expert(np.array([1.0, 3.0, 3.0])) == (3.0, 2)             # ties: the later point wins (oldMax > delta is false)
+    md, mi = _fold_expert(np.array([1.0, nan, 5.0]))                       # math.max(NaN, x) = NaN poisons the expert
+    assert np.isnan(md) and mi == 2
+    assert _fold_expert(np.array([])) == (-1.7976931348623157e308, -1)
+
+
+def test_greedy_provider_deltas_and_selection():
+    """candidate_deltas (vectorised) against a scalar transcription of ASP:109-124, and the selection loop."""
+    import math
+    from oracle.active_set import candidate_deltas, greedy_active_set, get_next
+    rng = np.random.default_rng(4)
+    n, d = 120, 3
+    X = rng.random((n, d)); y = np.sin(X.sum(1)) + 0.05 * rng.standard_normal(n)
+    fac = oracle.get_kernel(lambda: 1.2 * oracle.ARDRBFKernel(np.full(d, 1.5)) + oracle.const(1) * oracle.EyeKernel(), 1e-2)
+    theta = fac().get_hyperparameters()
+    experts = oracle.get_expert_labels_and_kernels(X, y, fac, 40)
+    for _, k in experts:
+        k.set_hyperparameters(theta)
+    active = X[[5, 17, 60]]
+    inst = fac().set_hyperparameters(theta).set_training_vectors(active)
+    kmm, s2 = inst.training_kernel(), inst.white_noise_var
+    assert abs(s2 - 1.01) < 1e-15                                          # whiteNoiseVar, not the sigma2 parameter
+    ye, ke = experts[1]
+    c = ke.cross_kernel(active)
+    g = sum(k.cross_kernel(active) @ k.cross_kernel(active).T for _, k in experts)
+    b = sum(k.cross_kernel(active) @ yy for yy, k in experts)
+    pdm = s2 * kmm + g
+    kinv, pinv, mv = np.linalg.inv(kmm), np.linalg.inv(pdm), np.linalg.solve(pdm, b)
+    dv = candidate_deltas(c, ye, ke.training_kernel_diag(), kinv, pinv, mv, s2)
+    for i in (0, 7, len(ye) - 1):
+        col = c[:, i]
+        pi, qi, mui = col @ kinv @ col, col @ pinv @ col, col @ mv
+        sigma = math.sqrt(s2); li = math.sqrt(ke.training_kernel_diag()[i] - pi)
+        ksii = 1.0 / ((sigma / li) ** 2 + 1 - qi); kappai = ksii * (1 + 2 * (sigma / li) ** 2)
+        delta = -math.log(sigma / li) - (math.log(ksii) + ksii * (1 - kappai) / s2 * (ye[i] - mui) ** 2 - kappai + 2) / 2
+        assert abs(dv[i] - delta) <= 1e-12 * max(1.0, abs(delta))
+    nxt = get_next(kmm, experts, active, s2)
+    assert any(np.array_equal(nxt, x) for x in X)
+    sel = greedy_active_set(6, experts, fac, theta, X[5])
+    assert sel.shape == (6, d) and np.array_equal(sel[0], X[5])
+    assert len({tuple(r) for r in sel}) == 6                               # distinct points on this data
+    assert np.array_equal(sel, greedy_active_set(6, experts, fac, theta, X[5]))
