@@ -95,7 +95,7 @@ static int launch_stats(Ctx* c, const void* dX, int x_is_f32, const double* dy, 
   p.n_slices = n_slices; p.n_tiles_1d = nt1;
 
   // AUTO: the tcgen05 int8 kernel only inside its measured parity envelope -- shards of >= 262144 points (posterior
-  // mean within 5.6e-6 .. 9.3e-6 of the all-fp64 kernel for N = 250k .. 4M, profiles/r01_i8_scaling.txt; the limit
+  // mean within 1.1e-6 .. 2.4e-6 of the all-fp64 kernel for N = 250k .. 4M, profiles/r01_i8_scaling.txt; the limit
   // is the two dropped low-order digit products, tools/i8_error_model.py) and small scaled norms (gate below).
   // Smaller shards stay on the fp64 DMMA kernel (2e-7), which is fast enough at that size.
   bool use_i8 = c->i8_ok && (c->precision == SGP_PREC_I8 || (c->precision == SGP_PREC_AUTO && n_call >= 262144));

@@ -9,12 +9,13 @@
 // the Gram is ACCUMULATED better than fp32 -- so fp32 TMEM accumulators (kind::f16/tf32) cannot carry the
 // parity gate, while fp32-accurate *elements* are 50x inside it.  kind::i8 accumulates in int32, which is
 // exact.  Every kernel element kappa = exp(-q) in (0,1] becomes a 23-bit fixed-point integer
-// u = rint(kappa * c0) written in balanced base-256 digits u = s2*2^16 + s1*2^8 + s0 (s2 in [0,127]
-// unsigned, s1,s0 in [-128,127] signed), and
-//     sum_n u_ni u_nj = 2^32 [S2'S2] + 2^24 [S2'S1 + S1'S2] + 2^16 [S2'S0 + S0'S2 + S1'S1] + (dropped)
+// u = rint(kappa * c0) written in balanced digits u = s2*2^15 + s1*2^7 + s0 (s2 in [0,255]: the unsigned operand
+// range, s1 in [-128,127], s0 in [-64,63]); the stored planes P2 = s2, P1 = s1, P0 = 2 s0 are the base-256 digits of
+// W = 2u and
+//     4 sum_n u_ni u_nj = 2^32 [P2'P2] + 2^24 [P2'P1 + P1'P2] + 2^16 [P2'P0 + P0'P2 + P1'P1] + (dropped)
 // is six int8 tensor-core products into three int32 TMEM accumulators.  The dropped products (weights 2^8,
-// 2^0) are zero-mean because the low digits are balanced (~4e-8 of full scale per point and pair); they are what
-// bounds this path's accuracy (posterior mean within 5.6e-6 .. 9.3e-6 of the all-fp64 kernel) --
+// 2^0) are zero-mean because the low digits are balanced; they are what bounds this path's accuracy
+// (posterior mean within 1.1e-6 .. 2.4e-6 of the all-fp64 kernel for N = 250k .. 4M) --
 // a 4th accumulator for them does not fit: 4 x 128 int32 columns is all of TMEM at a 128x128 tile.
 //
 // Pipeline of one CTA (owns G tile (I,J), I>=J, 128x128, and a slice of the shard's 64-point units):
@@ -27,7 +28,7 @@
 //   warps 4-19 epilogue, two groups of 8 (group g consumes the distance tiles of TMEM buffer g = panel I / panel J):
 //                       tcgen05.ld T -> ex2 -> fixed point via one FFMA against 2^23 -> byte planes (PRMT) -> 16-byte
 //                       stores into the K-major SWIZZLE_128B int8 operand panels in shared memory (A/B operands of
-//                       the Gram MMAs), b += kappa*y on diagonal tiles; every 32768 points all 16 warps fold the int32
+//                       the Gram MMAs), b += kappa*y on diagonal tiles; every 25600 points all 16 warps fold the int32
 //                       accumulators into the fp64 partial tile (no overflow possible).
 // Measured history of this kernel: profiles/r01_i8_tuning_log.md.
 #include <cuda_fp16.h>
@@ -45,8 +46,15 @@ constexpr int EPI_WARPS = 16;             // two groups of 8 (4 TMEM lane quarte
                                         // the distance tiles with (tile index & 1) == g, i.e. TMEM buffer g
 constexpr int NTHREADS = 128 + EPI_WARPS * 32;
 constexpr uint32_t TM_ACC4 = 0, TM_ACC3 = 128, TM_ACC2 = 256, TM_Q0 = 384;   // TMEM column map
-constexpr float C0 = 8355000.0f;        // fixed-point scale: u <= C0*(1+8e-5) keeps u + 0x8080 < 2^23
-constexpr float MAGIC = 8388608.0f + 32896.0f;   // 2^23 + 0x8080: mantissa of (kappa*C0 + MAGIC) = u + 0x8080
+// Fixed point.  u = rint(kappa * C0) < 2^23 is written in balanced digits  u = s2 * 2^15 + s1 * 2^7 + s0  with
+// s2 in [0, 255] (the UNSIGNED int8 operand range), s1 in [-128, 127], s0 in [-64, 63].  One FFMA produces them:
+// mantissa(kappa * C0 + MAGIC) = t = u + 0x4040, and the bytes of (t << 1) are (2 s0 + 128, s1 + 128, s2).  The stored
+// planes are P0 = 2 s0, P1 = s1, P2 = s2, i.e. the base-256 digits of W = 2 u, so the three accumulators are the usual
+// classes 2^32 [P2'P2], 2^24 [P2'P1 + P1'P2], 2^16 [P2'P0 + P0'P2 + P1'P1] of sum W W' = 4 sum u u'.
+// Compared with byte-aligned digits of u (s2 only 7 bits) the dropped class 2^8 [P1'P0 + P0'P1] is 4x smaller at the
+// same element width: posterior-mean deviation 5.3e-6 -> 1.7e-6 in the exact integer model (tools/i8_error_model.py).
+constexpr float C0 = 8355000.0f;        // fixed-point scale: u <= C0*(1+2e-3) keeps u + 0x4040 < 2^23
+constexpr float MAGIC = 8388608.0f + 16448.0f;   // 2^23 + 0x4040
 constexpr int PANEL_BYTES = 16384;      // 128 rows x 128 bytes, SWIZZLE_128B K-major
 constexpr int XIMG_BYTES = 8192;        // 64 rows x 128 bytes
 
@@ -147,6 +155,8 @@ __device__ __forceinline__ float ex2f(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// kappa -> the word whose bytes are the three digit planes (see the constants above)
+__device__ __forceinline__ uint32_t fixed_word(float kappa) { return __float_as_uint(fmaf(kappa, C0, MAGIC)) << 1; }
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
   uint32_t d;
   asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
@@ -310,10 +320,10 @@ struct I8Params {
   int xstages;          // operand ring depth
   int ksteps_last;      // 16-column k-steps used in the last chunk
   int m_pad, n_tiles_1d, n_slices;
-  int flush_units;      // fold int32 accumulators into fp64 every this many units (<= 512)
+  int flush_units;      // fold int32 accumulators into fp64 every this many units (<= 400)
   double* Gpart;        // [n_slices][m_pad*m_pad]
   double* bpart;        // [n_slices][m_pad]
-  double gscale;        // C^2 / C0^2
+  double gscale;        // C^2 / (4 C0^2)
   double bscale;        // C
   float* dbg_T;         // optional [128*64] : T of the first distance tile of CTA (0,0)
   uint32_t* dbg_w;      // optional [128*64] : fixed-point words of the same tile
@@ -561,7 +571,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_kernel(const I8Params
         if (DBG && dbg && i == 0 && P == 0) {
           for (int k = 0; k < 32; ++k) p.dbg_T[L * UP + ch * 32 + k] = __uint_as_float(T[k]);
         }
-        // kappa = 2^T ; fixed point: mantissa(kappa*C0 + MAGIC) = u + 0x8080
+        // kappa = 2^T ; fixed point: (mantissa(kappa*C0 + MAGIC) << 1) has the digit bytes (2 s0 + 128, s1 + 128, s2)
         // (the Gram MMAs that read this half of the panels two units ago must have drained before we overwrite it:
         //  p_empty is polled between the two halves of the exp block)
         const uint32_t pe_bar = b_pempty + 8 * h, pe_par = static_cast<uint32_t>(((i >> 1) - 1) & 1);
@@ -577,19 +587,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_kernel(const I8Params
                         e2 = ex2f(__uint_as_float(T[4 * g + 2])), e3 = ex2f(__uint_as_float(T[4 * g + 3]));
             bacc = fmaf(e0, y4.x, bacc); bacc = fmaf(e1, y4.y, bacc);
             bacc = fmaf(e2, y4.z, bacc); bacc = fmaf(e3, y4.w, bacc);
-            T[4 * g + 0] = __float_as_uint(fmaf(e0, C0, MAGIC)); T[4 * g + 1] = __float_as_uint(fmaf(e1, C0, MAGIC));
-            T[4 * g + 2] = __float_as_uint(fmaf(e2, C0, MAGIC)); T[4 * g + 3] = __float_as_uint(fmaf(e3, C0, MAGIC));
+            T[4 * g + 0] = fixed_word(e0); T[4 * g + 1] = fixed_word(e1);
+            T[4 * g + 2] = fixed_word(e2); T[4 * g + 3] = fixed_word(e3);
           }
           bsum += static_cast<double>(bacc);
         } else {
 #pragma unroll
-          for (int k = 0; k < 16; ++k) T[k] = __float_as_uint(fmaf(ex2f(__uint_as_float(T[k])), C0, MAGIC));
+          for (int k = 0; k < 16; ++k) T[k] = fixed_word(ex2f(__uint_as_float(T[k])));
           if (!pe_ready) pe_ready = mbar_test(pe_bar, pe_par);
 #pragma unroll
-          for (int k = 16; k < 32; ++k) T[k] = __float_as_uint(fmaf(ex2f(__uint_as_float(T[k])), C0, MAGIC));
+          for (int k = 16; k < 32; ++k) T[k] = fixed_word(ex2f(__uint_as_float(T[k])));
         }
         if (DBG && dbg && i == 0 && P == 0) {
-          for (int k = 0; k < 32; ++k) p.dbg_w[L * UP + ch * 32 + k] = T[k];
+          for (int k = 0; k < 32; ++k) p.dbg_w[L * UP + ch * 32 + k] = T[k] >> 1;     // the fp32 word (sign bit is 0)
         }
         if (tle) SGP_TL(1 + grp, i, 3);
         if (!pe_ready) mbar_wait(pe_bar, pe_par);
@@ -603,10 +613,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_kernel(const I8Params
             const uint32_t w0 = T[g16 * 16 + g * 4 + 0], w1 = T[g16 * 16 + g * 4 + 1], w2 = T[g16 * 16 + g * 4 + 2],
                            w3 = T[g16 * 16 + g * 4 + 3];
             const uint32_t t01 = prmt(w0, w1, 0x5140), t23 = prmt(w2, w3, 0x5140);
-            d0[g] = prmt(t01, t23, 0x5410) ^ 0x80808080u;     // s0 = byte0 - 128 (two's complement)
-            d1[g] = prmt(t01, t23, 0x7632) ^ 0x80808080u;     // s1 = byte1 - 128
+            d0[g] = prmt(t01, t23, 0x5410) ^ 0x80808080u;     // P0 = 2 s0 = byte0 - 128 (two's complement)
+            d1[g] = prmt(t01, t23, 0x7632) ^ 0x80808080u;     // P1 = s1 = byte1 - 128
             const uint32_t u01 = prmt(w0, w1, 0x0062), u23 = prmt(w2, w3, 0x0062);
-            d2[g] = prmt(u01, u23, 0x5410);                   // s2 = byte2 (0..127)
+            d2[g] = prmt(u01, u23, 0x5410);                   // P2 = s2 = byte2 (0..255, unsigned operand)
           }
           if (g16 == 1) q_ready = mbar_test(b_qfull + 8 * grp, q_phase);     // next tile of this group
           uint8_t* dst = pan_base + sw128_off(L, static_cast<int>(h * 4 + ch * 2 + g16));
@@ -720,9 +730,11 @@ cudaError_t launch_gram_i8(const uint8_t* Xt, const float* ys, const uint8_t* Zt
   p.nchunks = i8_nchunks(d);
   p.ksteps_last = (3 * dp + 16) / 16 - 4 * (p.nchunks - 1);
   p.m_pad = m_pad; p.n_tiles_1d = m_pad / kTile; p.n_slices = n_slices;
-  p.flush_units = 512;                       // 32768 points: 3 * 128*128 * 32768 < 2^31
+  // fold every 400 units = 25600 points: guaranteed bounds |ACC4| <= 255^2 n = 1.66e9, |ACC3| <= 2*255*128 n = 1.67e9,
+  // |ACC2| <= (2*255*128 + 128^2) n = 2.09e9, all < 2^31 = 2.147e9
+  p.flush_units = 400;
   p.Gpart = Gpart; p.bpart = bpart;
-  p.gscale = C * C / (static_cast<double>(C0) * static_cast<double>(C0));
+  p.gscale = C * C / (4.0 * static_cast<double>(C0) * static_cast<double>(C0));      // the planes are the digits of 2 u
   p.bscale = C;
   p.dbg_T = dbg_T; p.dbg_w = dbg_w; p.dbg_clk = dbg_clk;
   p.xstages = (p.nchunks == 1) ? 4 : 3;

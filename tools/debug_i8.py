@@ -52,7 +52,7 @@ def case(n, d, m, seed=0, check_dbg=False, label=""):
         dT = np.abs(T[:rows, :cols] - Te[:rows, :cols]).max()
         dd = (T[:rows, :cols] - Te[:rows, :cols])
         print("  [dbg] max|T - T_emul| = %.3e  mean(T - T_emul) = %.3e  rms = %.3e (T range %.2f..%.2f)" % (dT, dd.mean(), np.sqrt((dd ** 2).mean()), Te[:rows, :cols].min(), Te[:rows, :cols].max()))
-        u = (w & 0x7FFFFF).astype(np.int64) - 0x8080
+        u = (w & 0x7FFFFF).astype(np.int64) - 0x4040
         ue = np.rint(np.exp2(T.astype(np.float64)) * C0)
         print("  [dbg] max|u - rint(2^T*C0)| = %d ; top byte ok: %s" % (np.abs(u[:rows, :cols] - ue[:rows, :cols]).max(), bool(np.all((w[:rows, :cols] >> 24) == 0x4B))))
     ex = oracle.get_expert_labels_and_kernels(X.astype(np.float64), y, ok, 100)

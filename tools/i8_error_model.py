@@ -34,16 +34,29 @@ def T_model(X, Z, beta, mode):
     return acc
 
 def gram_from_T(T, y, full_products=False):
+    """The kernel's digit layout: u = s2*2^15 + s1*2^7 + s0, s2 in [0,255] (unsigned operand), s1 in [-128,127],
+    s0 in [-64,63]; stored planes P2 = s2, P1 = s1, P0 = 2 s0 are the base-256 digits of W = 2u."""
+    kap = np.exp2(T)
+    u = np.rint(kap * C0).astype(np.int64)
+    t = u + 0x4040
+    f = lambda a: a.astype(np.float64)      # exact: |sums| < 2^53
+    P0, P1, P2 = f(2 * ((t & 127) - 64)), f(((t >> 7) & 255) - 128), f(t >> 15)
+    g = 2.0 ** 32 * (P2.T @ P2) + 2.0 ** 24 * (P2.T @ P1 + P1.T @ P2) + 2.0 ** 16 * (P2.T @ P0 + P0.T @ P2 + P1.T @ P1)
+    if full_products:
+        g = g + 2.0 ** 8 * (P1.T @ P0 + P0.T @ P1) + P0.T @ P0
+    return g / (4.0 * C0 ** 2), (kap.T @ y)
+
+
+def gram_from_T_byte_aligned(T, y):
+    """The first layout (byte-aligned digits of u: s2 only 7 bits), kept for comparison."""
     kap = np.exp2(T)
     u = np.rint(kap * C0).astype(np.int64)
     t = u + 0x8080
-    s0 = (t & 255) - 128; s1 = ((t >> 8) & 255) - 128; s2 = (t >> 16)
-    f = lambda a: a.astype(np.float64)      # exact: |sums| < 2^53
-    S0, S1, S2 = f(s0), f(s1), f(s2)
+    f = lambda a: a.astype(np.float64)
+    S0, S1, S2 = f((t & 255) - 128), f(((t >> 8) & 255) - 128), f(t >> 16)
     g = 2.0 ** 32 * (S2.T @ S2) + 2.0 ** 24 * (S2.T @ S1 + S1.T @ S2) + 2.0 ** 16 * (S2.T @ S0 + S0.T @ S2 + S1.T @ S1)
-    if full_products:
-        g = g + 2.0 ** 8 * (S1.T @ S0 + S0.T @ S1) + S0.T @ S0
     return g / C0 ** 2, (kap.T @ y)
+
 
 def main(N=200000, d=16, m=1000, chunk=20000):
     rng = np.random.default_rng(13)
@@ -53,7 +66,7 @@ def main(N=200000, d=16, m=1000, chunk=20000):
     beta = np.full(d, np.sqrt(18.0 / d))
     Z = X[np.random.default_rng(7).permutation(N)[:m]]
     variants = {"fp64": None, "fixedpoint_fullprod+exactT": ("exact", True), "digits_dropped+exactT": ("exact", False),
-                "digits+T_rn32": ("rn", False), "digits+T_rz32": ("rz", False)}
+                "digits+T_rn32": ("rn", False), "digits+T_rz32": ("rz", False), "byte_aligned_digits+T_rz32": ("rz", None)}
     G = {k: np.zeros((m, m)) for k in variants}; b = {k: np.zeros(m) for k in variants}
     for s in range(0, N, chunk):
         Xc, yc = X[s:s + chunk], y[s:s + chunk]
@@ -62,7 +75,8 @@ def main(N=200000, d=16, m=1000, chunk=20000):
         K = np.exp(-q); G["fp64"] += K.T @ K; b["fp64"] += K.T @ yc
         for name, cfg in variants.items():
             if cfg is None: continue
-            g, bb = gram_from_T(T_model(Xc, Z, beta, cfg[0]), yc, cfg[1])
+            g, bb = (gram_from_T_byte_aligned(T_model(Xc, Z, beta, cfg[0]), yc) if cfg[1] is None
+                     else gram_from_T(T_model(Xc, Z, beta, cfg[0]), yc, cfg[1]))
             G[name] += g; b[name] += bb
     fac = oracle.get_kernel(lambda: 1 * ARDRBFKernel(d) + const(1) * EyeKernel(), 1e-4)
     kern = fac().set_hyperparameters(np.concatenate([[1.0], beta])).set_training_vectors(Z)
