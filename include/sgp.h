@@ -174,7 +174,7 @@ int sgp_event_elapsed_ms(sgp_ctx* ctx, int slot_start, int slot_stop, double* ms
 int sgp_last_path(const sgp_ctx* ctx);
 /* Debug aid for SGP_PREC_I8: the first call arms a dump; later calls return, for the first 64-point unit of
  * the first CTA of the last launch, T = -q*log2(e) (128 active rows x 64 points, fp32) and the fixed-point words
- * (0x4B000000 | (u + 0x8080)). */
+ * (0x4B000000 | (u + 0x4040)), u = s2*2^15 + s1*2^7 + s0 in balanced digits. */
 int sgp_debug_i8_tile(sgp_ctx* ctx, float* T_out /* 128*64 */, uint32_t* w_out /* 128*64 */);
 /* Debug aid: clock64 timeline [3 roles: MMA warp, epilogue group 0, group 1][32 units: 64..95][8 events] of
  * CTA (1,0) of the last SGP_PREC_I8 launch made while armed (see sgp_debug_i8_tile). */

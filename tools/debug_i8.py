@@ -74,7 +74,7 @@ if __name__ == "__main__":
     case(5000, 5, 300, label="d=5, m ragged")
     case(5000, 32, 384, label="d=32 (2 K chunks)")
     case(20000, 16, 1000, label="36 tiles x 4 slices")
-    case(300000, 16, 256, label="flush boundary (>32768/slice)")
+    case(300000, 16, 256, label="fold boundary (>25600/slice)")
     # throughput at BASELINE configs[1]
     import ctypes as C
     rng = np.random.default_rng(1)
