@@ -165,8 +165,10 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
 
 // UMMA shared-memory descriptor, K-major, SWIZZLE_128B (cute::UMMA::SmemDescriptor): start>>4 [0,14),
 // LBO>>4 [16,30) (unused for swizzled K-major: 1), SBO>>4 [32,46) = 1024 B between 8-row groups,
-// version=1 [46,48), layout_type=2 (SWIZZLE_128B) [61,64).  Tile bases are 1024-byte aligned.
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+// version=1 [46,48), layout_type=2 (SWIZZLE_128B) [61,64).  Tile bases are 1024-byte aligned.  (Reference form of the
+// descriptor: the MMA issuers below assemble the same bits from DESC_HI and a 14-bit start field so that the 64-bit
+// value stays in uniform registers.)
+[[maybe_unused]] __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   return static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
 // UMMA instruction descriptor (cute::UMMA::InstrDescriptor): c_format [4,6), a_format [7,10), b_format [10,13),
