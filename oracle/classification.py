@@ -64,3 +64,16 @@ def classification_likelihood_and_gradient(y: np.ndarray, f: np.ndarray, kernel,
         s3 = bb - K @ (R @ bb)
         grad.append(s1 + float(s2 @ s3))
     return -logZ, -np.array(grad)
+
+
+def classification_model_outputs(f: np.ndarray):
+    """GaussianProcessClassificationModel (GPCls:136-162) for latent predictions f (one per row):
+    rawPrediction = (-f, f) (:152-155); probability = raw2probabilityInPlace (:140-148): values(0) = sigmoid(-values(0)) =
+    sigmoid(f), values(1) = 1 - values(0) -- the reference's quirk; prediction = Spark's raw2prediction with no thresholds
+    set = rawPrediction.argmax (first maximum on ties), i.e. 1.0 iff f > 0."""
+    f = np.atleast_1d(np.asarray(f, dtype=np.float64))
+    raw = np.stack([-f, f], axis=-1)
+    p0 = _sigmoid(-raw[:, 0])
+    prob = np.stack([p0, 1.0 - p0], axis=-1)
+    pred = np.argmax(raw, axis=-1).astype(np.float64)
+    return raw, prob, pred

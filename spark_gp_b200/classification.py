@@ -23,14 +23,17 @@ class GaussianProcessClassificationModel:
         return np.stack([-f, f], axis=-1)
 
     def predictProbability(self, features):
-        """raw2probabilityInPlace (GPCls:141-149), quirk included: values(0) = sigmoid(-values(0)) = sigmoid(f)."""
+        """raw2probabilityInPlace (GPCls:140-148), quirk included: values(0) = sigmoid(-values(0)) = sigmoid(f), so the
+        probability column puts sigmoid(f) on class 0 although f > 0 votes for class 1."""
         raw = self.predictRaw(features)
         p0 = 1.0 / (1.0 + np.exp(raw[..., 0]))          # sigmoid(-(-f))
         return np.stack([p0, 1.0 - p0], axis=-1)
 
     def predict(self, features):
-        """ProbabilisticClassificationModel.predict: argmax of the probability vector."""
-        return np.argmax(self.predictProbability(features), axis=-1).astype(np.float64)
+        """ClassificationModel.predict = raw2prediction(predictRaw(x)); with no thresholds set (the reference sets none)
+        Spark's ProbabilisticClassificationModel.raw2prediction is `rawPrediction.argmax`, i.e. class 1 iff f > 0 (first
+        maximum on a tie) -- NOT the argmax of the (quirky) probability vector."""
+        return np.argmax(self.predictRaw(features), axis=-1).astype(np.float64)
 
 
 class GaussianProcessClassifier(GaussianProcessParams):

@@ -511,8 +511,12 @@ def test_classifier_fit_mnist68_fixture():
     assert np.abs(gp.last_latent - c["f"]).max() < 1e-8
     raw = model.predictRaw(Xte)
     assert rel(raw[:, 1], c["fstar"]) < TOL_PRED and np.allclose(raw[:, 0], -raw[:, 1])
-    acc = np.mean(model.predict(Xte) == (c["y01"][n:n + 100] < 0.5))     # class 0 gets sigmoid(f): the reference's quirk
+    # prediction = argmax of the RAW vector (Spark's raw2prediction without thresholds): class 1 iff f > 0; only the
+    # probability column carries the reference's quirk (sigmoid(f) on class 0)
+    acc = np.mean(model.predict(Xte) == c["y01"][n:n + 100])
     assert acc > 0.95
+    prob = model.predictProbability(Xte)
+    assert np.allclose(prob[:, 0], 1.0 / (1.0 + np.exp(-raw[:, 1]))) and np.allclose(prob.sum(1), 1.0)
     with pytest.raises(RuntimeError):
         gp.fit(Xtr, ytr + 1.0)
 

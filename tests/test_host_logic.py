@@ -179,3 +179,27 @@ def test_greedy_provider_selection_matches_scalar_fold():
                 sg.GreedilyOptimizingActiveSetProvider.select_index(delta, E)
         else:
             assert sg.GreedilyOptimizingActiveSetProvider.select_index(delta, E) == best[1]
+
+
+def test_classification_model_surface_matches_reference_semantics():
+    """predictRaw / probability / prediction of GaussianProcessClassificationModel (GPCls:136-162 + Spark's
+    raw2prediction) through a stub predictor, against the oracle's restatement."""
+    from oracle.classification import classification_model_outputs
+    from spark_gp_b200.classification import GaussianProcessClassificationModel
+
+    class _Engine:
+        def __init__(self, f): self.f = f
+        def predict(self, X, with_variance=True): return self.f[:len(X)], None
+
+    class _Raw:
+        def __init__(self, f): self._engine = _Engine(f)
+
+    f = np.array([-3.0, -0.2, 0.0, 0.4, 5.0])
+    model = GaussianProcessClassificationModel(_Raw(f), np.zeros(1))
+    raw0, prob0, pred0 = classification_model_outputs(f)
+    X = np.zeros((len(f), 2))
+    assert np.array_equal(model.predictRaw(X), raw0)
+    assert np.allclose(model.predictProbability(X), prob0, rtol=0, atol=1e-16)
+    assert np.array_equal(model.predict(X), pred0)
+    assert list(pred0) == [0.0, 0.0, 0.0, 1.0, 1.0]                      # f == 0: argmax takes the first maximum
+    assert prob0[3, 0] > 0.5 and pred0[3] == 1.0                        # the quirk: P(class 0) = sigmoid(f) > 1/2, label 1
