@@ -7,5 +7,5 @@ from .kernels import (Kernel, ARDRBFKernel, RBFKernel, EyeKernel, ConstantTimesK
 from .engine import (ProjectedProcessEngine, NotPositiveDefiniteException, TrainingVectorsNotInitializedException,
                      MatrixSingularException, SgpError, OperandRangeError)
 from .regression import (GaussianProcessRegression, GaussianProcessRegressionModel, RandomActiveSetProvider,
-                         GreedilyOptimizingActiveSetProvider)
+                         GreedilyOptimizingActiveSetProvider, KMeansActiveSetProvider)
 from .classification import GaussianProcessClassifier, GaussianProcessClassificationModel

@@ -42,6 +42,24 @@ class ExplicitActiveSetProvider(ActiveSetProvider):
         return self.active_set
 
 
+class KMeansActiveSetProvider(ActiveSetProvider):
+    """commons/ActiveSetProvider.scala:22-46: K-means on the training features, the centroids are the active set
+    (`new KMeans().setK(activeSetSize).setSeed(seed).setMaxIter(maxIter)`, Spark defaults otherwise: tol 1e-4).
+    Host-side only: the clustering is a library call in the reference too (Spark MLlib); here scikit-learn's Lloyd
+    iterations with k-means++ seeding stand in for Spark's k-means|| -- same objective and stopping rule, but Spark's
+    initialisation RNG stream is unpinned, so results are comparable on metrics (RMSE), not centroid by centroid."""
+
+    def __init__(self, maxIter: int = 20):
+        self.maxIter = int(maxIter)
+
+    def __call__(self, activeSetSize, X, y, kernel_factory, optimalHyperparameter, seed, gp=None):
+        from sklearn.cluster import KMeans
+        km = KMeans(n_clusters=int(activeSetSize), init="k-means++", n_init=1, max_iter=self.maxIter, tol=1e-4,
+                    random_state=int(seed) % (2 ** 32), algorithm="lloyd")
+        km.fit(np.asarray(X, dtype=np.float64))
+        return np.ascontiguousarray(km.cluster_centers_, dtype=np.float64)
+
+
 class GreedilyOptimizingActiveSetProvider(ActiveSetProvider):
     """commons/ActiveSetProvider.scala:58-139 (Seeger et al. 2003 forward selection as the reference codes it).
 

@@ -203,3 +203,17 @@ def test_classification_model_surface_matches_reference_semantics():
     assert np.array_equal(model.predict(X), pred0)
     assert list(pred0) == [0.0, 0.0, 0.0, 1.0, 1.0]                      # f == 0: argmax takes the first maximum
     assert prob0[3, 0] > 0.5 and pred0[3] == 1.0                        # the quirk: P(class 0) = sigmoid(f) > 1/2, label 1
+
+
+def test_kmeans_active_set_provider():
+    """ActiveSetProvider.scala:22-46: centroids of K-means on the features (host-side library call, as in the reference)."""
+    rng = np.random.default_rng(0)
+    centres = rng.random((5, 3)) * 10
+    X = np.concatenate([c + 0.05 * rng.standard_normal((40, 3)) for c in centres])
+    prov = sg.KMeansActiveSetProvider(maxIter=20)
+    A = prov(5, X, None, None, None, 13)
+    assert A.shape == (5, 3) and A.dtype == np.float64 and A.flags["C_CONTIGUOUS"]
+    assert np.array_equal(A, prov(5, X, None, None, None, 13))                    # same seed, same centroids
+    d = np.linalg.norm(A[:, None, :] - centres[None, :, :], axis=2)
+    assert np.all(d.min(axis=0) < 0.05)                                           # every true centre is recovered
+    assert sg.KMeansActiveSetProvider().maxIter == 20                             # the reference's default
