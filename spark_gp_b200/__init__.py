@@ -9,3 +9,4 @@ from .engine import (ProjectedProcessEngine, NotPositiveDefiniteException, Train
 from .regression import (GaussianProcessRegression, GaussianProcessRegressionModel, RandomActiveSetProvider,
                          GreedilyOptimizingActiveSetProvider, KMeansActiveSetProvider)
 from .classification import GaussianProcessClassifier, GaussianProcessClassificationModel
+from .utils import scale

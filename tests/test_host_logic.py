@@ -217,3 +217,10 @@ def test_kmeans_active_set_provider():
     d = np.linalg.norm(A[:, None, :] - centres[None, :, :], axis=2)
     assert np.all(d.min(axis=0) < 0.05)                                           # every true centre is recovered
     assert sg.KMeansActiveSetProvider().maxIter == 20                             # the reference's default
+
+
+def test_scale_matches_oracle():
+    X = np.random.default_rng(1).random((50, 4)) * [1.0, 10.0, 0.0, 3.0] + [0.0, 5.0, 2.0, -1.0]   # column 2 is constant
+    got, want = sg.scale(X), oracle.scale(X)
+    assert np.array_equal(got, want)
+    assert np.allclose(got.mean(0), 0.0, atol=1e-14) and np.allclose(got[:, [0, 1, 3]].std(0), 1.0) and np.all(got[:, 2] == 0.0)
