@@ -112,8 +112,10 @@ int sgp_sync(sgp_ctx* ctx);
 /* ---- the m x m tail:  PGPH:49-65 ------------------------------------------------------------ */
 /* Uses the kernel + active set of the last sgp_stats_begin and the device-resident G, b (after finish),
  * or host G_in/b_in when non-NULL.  K_mm = trainingKernel (Eye terms on the diagonal),
- * A = whiteNoiseVar*K_mm + G; SGP_E_NOT_PD if any eigenvalue of A < 0; magicVector = A \ b (LU);
- * magicMatrix = whiteNoiseVar*inv(A) - inv(K_mm).  Outputs may be NULL (kept on device for predict). */
+ * A = whiteNoiseVar*K_mm + G; SGP_E_NOT_PD if any eigenvalue of A < 0; magicVector = A \ b;
+ * magicMatrix = whiteNoiseVar*inv(A) - inv(K_mm).  Outputs may be NULL (kept on device for predict).
+ * A successful Cholesky factorization of A proves "no eigenvalue < 0" and supplies the solves (SPD: same result as
+ * the reference's LU to rounding); only if it breaks down does the call run the reference's literal dsyevd + LU sequence. */
 int sgp_magic(sgp_ctx* ctx, const double* G_in, const double* b_in,
               double* magic_vector /* m */, double* magic_matrix /* m x m */);
 
@@ -172,6 +174,10 @@ int sgp_event_record(sgp_ctx* ctx, int slot);
 int sgp_event_elapsed_ms(sgp_ctx* ctx, int slot_start, int slot_stop, double* ms);
 /* Which kernel the last statistics launch used: SGP_PREC_F64, SGP_PREC_F64_STRICT or SGP_PREC_I8 (-1: none yet). */
 int sgp_last_path(const sgp_ctx* ctx);
+/* Which path the last sgp_magic took: 1 = Cholesky for both A and K_mm (success of dpotrf IS the reference's positive-
+ * definiteness check PGPH:62-65), 0 = the reference's literal sequence (dsyevd eigenvalue check, LU solves) because a
+ * Cholesky factorization broke down, -1 = sgp_magic has not run. */
+int sgp_last_tail_path(const sgp_ctx* ctx);
 /* Debug aid for SGP_PREC_I8: the first call arms a dump; later calls return, for the first 64-point unit of
  * the first CTA of the last launch, T = -q*log2(e) (128 active rows x 64 points, fp32) and the fixed-point words
  * (0x4B000000 | (u + 0x4040)), u = s2*2^15 + s1*2^7 + s0 in balanced digits. */

@@ -83,9 +83,7 @@ class GaussianProcessClassifier(GaussianProcessParams):
         # GPCls:62-65 -> produceModel with (f, kernel): the same projected-process path as regression
         active_set = self._activeSetProvider(self._activeSetSize, X, f, self.getKernel, theta, self._seed, gp=self)
         kernel = self.getKernel().setHyperparameters(theta)
-        eng.begin(kernel, active_set)
-        eng.accumulate(X, f)
-        G, b = eng.finish()
+        G, b = eng.statistics(kernel, active_set, X, f)             # same helper as regression (fp64-kernel fallback)
         mv, mm = eng.magic()
         self.last_stats = (G, b)
         return GaussianProcessClassificationModel(GaussianProjectedProcessRawPredictor(eng, mv, mm, kernel, active_set), theta)

@@ -117,9 +117,12 @@ static int launch_stats(Ctx* c, const void* dX, int x_is_f32, const double* dy, 
       c->i8_ys_bytes = yb;
     }
     const bool gate = (c->precision == SGP_PREC_AUTO) && first_of_call;
-    if (gate) SGP_CUDA(c, cudaMemsetAsync(c->dI8NormSum, 0, sizeof(double), c->stream));
+    // the scaled squared norms of EVERY chunk are summed on the device (dI8NormSum[0]: whole begin..finish window,
+    // checked against the budget at finish so that an unrepresentative first chunk cannot silently degrade the
+    // statistics; dI8NormSum[1]: this call's first chunk, read back here for the kernel choice)
+    if (gate) SGP_CUDA(c, cudaMemsetAsync(c->dI8NormSum + 1, 0, sizeof(double), c->stream));
     SGP_CUDA(c, launch_i8_prep_points(c->dI8Xt, c->dI8Ys, dX, x_is_f32, dy, n, c->d, c->dI8Scale, c->dI8Centre,
-                                      c->dI8Flags, gate ? c->dI8NormSum : nullptr, c->stream));
+                                      c->dI8Flags, c->dI8NormSum, gate ? c->dI8NormSum + 1 : nullptr, c->stream));
     c->launches += 1;
     if (gate) {
       // AUTO's magnitude gate.  The distance contraction accumulates 2 x^.z^ - |x^|^2 - |z^|^2 in fp32 in tensor
@@ -127,17 +130,22 @@ static int launch_stats(Ctx* c, const void* dX, int x_is_f32, const double* dy, 
       // the elements are good to 2.7e-7 rms (parity holds, tests), at ~12 (airfoil: norms up to 40) they are not
       // (posterior mean off by 5e-4).  Above the budget the shard goes to the fp64 DMMA kernel instead.
       double xsum = 0.0;
-      SGP_CUDA(c, cudaMemcpyAsync(&xsum, c->dI8NormSum, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+      SGP_CUDA(c, cudaMemcpyAsync(&xsum, c->dI8NormSum + 1, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
       SGP_CUDA(c, cudaStreamSynchronize(c->stream));
       if (xsum / static_cast<double>(n) + c->i8_z_norm_mean > c->i8_norm_budget) use_i8 = false;
     }
   }
   if (first_of_call) c->call_i8 = use_i8;
-  if (use_i8) c->i8_used = true;
+  if (use_i8) { c->i8_used = true; c->i8_points += n; }
   c->last_path = use_i8 ? SGP_PREC_I8 : (c->precision == SGP_PREC_F64_STRICT ? SGP_PREC_F64_STRICT : SGP_PREC_F64);
-  cudaEvent_t e0, e1;
-  SGP_CUDA(c, cudaEventCreate(&e0));
-  SGP_CUDA(c, cudaEventCreate(&e1));
+  if (c->gram_events_used == c->gram_events.size()) {          // grow the event pool (steady state: no creation)
+    cudaEvent_t a, b;
+    SGP_CUDA(c, cudaEventCreate(&a));
+    SGP_CUDA(c, cudaEventCreate(&b));
+    c->gram_events.emplace_back(a, b);
+  }
+  cudaEvent_t e0 = c->gram_events[c->gram_events_used].first, e1 = c->gram_events[c->gram_events_used].second;
+  c->gram_events_used += 1;
   SGP_CUDA(c, cudaEventRecord(e0, c->stream));
   if (use_i8)
     SGP_CUDA(c, launch_gram_i8(c->dI8Xt, c->dI8Ys, c->dI8Zt, n, c->d, c->m_pad, n_slices, c->dGpart, c->dBpart,
@@ -145,7 +153,6 @@ static int launch_stats(Ctx* c, const void* dX, int x_is_f32, const double* dy, 
   else
     SGP_CUDA(c, launch_gram_f64(p, c->precision == SGP_PREC_F64_STRICT, c->stream));
   SGP_CUDA(c, cudaEventRecord(e1, c->stream));
-  c->gram_events.emplace_back(e0, e1);
   const size_t mm = static_cast<size_t>(c->m) * c->m;
   SGP_CUDA(c, launch_gram_reduce(c->dGb, c->dGb + mm, c->dGpart, c->dBpart, n_slices, c->m, c->m_pad, c->stream));
   c->launches += 2;
@@ -155,6 +162,7 @@ static int launch_stats(Ctx* c, const void* dX, int x_is_f32, const double* dy, 
 static void drop_gram_events(Ctx* c) {
   for (auto& e : c->gram_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
   c->gram_events.clear();
+  c->gram_events_used = 0;
 }
 
 }  // namespace sgp
@@ -192,7 +200,12 @@ int sgp_ctx_create(sgp_ctx** out, int device) {
     cudaEventCreateWithFlags(&c->stage_free[i], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&c->stage_ready[i], cudaEventDisableTiming);
   }
+  if ((e = cudaStreamCreateWithFlags(&c->tail_stream, cudaStreamNonBlocking)) != cudaSuccess ||
+      (e = cudaEventCreateWithFlags(&c->tail_fork, cudaEventDisableTiming)) != cudaSuccess ||
+      (e = cudaEventCreateWithFlags(&c->tail_join, cudaEventDisableTiming)) != cudaSuccess)
+    return bail(SGP_E_CUDA, cudaGetErrorString(e));
   if (cusolverDnCreate(&c->solver) != CUSOLVER_STATUS_SUCCESS) return bail(SGP_E_CUDA, "cusolverDnCreate failed");
+  if (cusolverDnCreate(&c->solver2) != CUSOLVER_STATUS_SUCCESS) return bail(SGP_E_CUDA, "cusolverDnCreate failed");
   if (cublasCreate(&c->blas) != CUBLAS_STATUS_SUCCESS) return bail(SGP_E_CUDA, "cublasCreate failed");
   *out = reinterpret_cast<sgp_ctx*>(c);
   return SGP_OK;
@@ -215,7 +228,12 @@ int sgp_ctx_destroy(sgp_ctx* h) {
     if (c->stage_ready[i]) cudaEventDestroy(c->stage_ready[i]);
   }
   if (c->comm && nccl().ok) nccl().CommDestroy(c->comm);
+  cudaFree(c->tail_ws.p); cudaFree(c->tail_ws2.p); cudaFree(c->predict_ws.p); cudaFree(c->cross_ws.p);
+  if (c->tail_fork) cudaEventDestroy(c->tail_fork);
+  if (c->tail_join) cudaEventDestroy(c->tail_join);
+  if (c->tail_stream) cudaStreamDestroy(c->tail_stream);
   if (c->solver) cusolverDnDestroy(c->solver);
+  if (c->solver2) cusolverDnDestroy(c->solver2);
   if (c->blas) cublasDestroy(c->blas);
   if (c->stream) cudaStreamDestroy(c->stream);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
@@ -304,13 +322,13 @@ int sgp_stats_begin(sgp_ctx* h, const sgp_kernel_desc* k, const double* Z, int32
     SGP_CUDA(c, cudaMalloc(&c->dZ, static_cast<size_t>(m) * d * 8));
     SGP_CUDA(c, cudaMalloc(&c->dZs, static_cast<size_t>(nt) * c->m_pad * dpad * 8));
     SGP_CUDA(c, cudaMalloc(&c->dBeta, static_cast<size_t>(kMaxTerms) * dpad * 8));
-    SGP_CUDA(c, cudaMalloc(&c->dGb, (mm + m) * 8));
+    SGP_CUDA(c, cudaMalloc(&c->dGb, (mm + m + 1) * 8));     // [G ; b ; status] -- one all-reduce
     SGP_CUDA(c, cudaMalloc(&c->dMagicVec, static_cast<size_t>(m) * 8));
     SGP_CUDA(c, cudaMalloc(&c->dMagicMat, mm * 8));
   }
   SGP_CUDA(c, cudaMemcpyAsync(c->dZ, Z, static_cast<size_t>(m) * d * 8, cudaMemcpyHostToDevice, c->stream));
   SGP_CUDA(c, cudaMemcpyAsync(c->dBeta, beta.data(), beta.size() * 8, cudaMemcpyHostToDevice, c->stream));
-  SGP_CUDA(c, cudaMemsetAsync(c->dGb, 0, (mm + m) * 8, c->stream));
+  SGP_CUDA(c, cudaMemsetAsync(c->dGb, 0, (mm + m + 1) * 8, c->stream));
   for (int t = 0; t < kf.n_terms; ++t) {
     SGP_CUDA(c, launch_scale_rows(c->dZs + static_cast<size_t>(t) * c->m_pad * dpad, c->dZ,
                                   c->dBeta + static_cast<size_t>(t) * dpad, m, c->m_pad, d, dpad, c->stream));
@@ -332,7 +350,7 @@ int sgp_stats_begin(sgp_ctx* h, const sgp_kernel_desc* k, const double* Z, int32
       SGP_CUDA(c, cudaMalloc(&c->dI8Scale, dp16 * 8));
       SGP_CUDA(c, cudaMalloc(&c->dI8Centre, dp16 * 8));
       SGP_CUDA(c, cudaMalloc(&c->dI8Flags, sizeof(int)));
-      SGP_CUDA(c, cudaMalloc(&c->dI8NormSum, sizeof(double)));
+      SGP_CUDA(c, cudaMalloc(&c->dI8NormSum, 2 * sizeof(double)));
       SGP_CUDA(c, cudaMalloc(&c->dI8Zt, i8_active_scratch_bytes(c->m_pad, i8_nchunks(d))));
     }
     {
@@ -348,13 +366,15 @@ int sgp_stats_begin(sgp_ctx* h, const sgp_kernel_desc* k, const double* Z, int32
     SGP_CUDA(c, cudaMemcpyAsync(c->dI8Scale, sc.data(), dp16 * 8, cudaMemcpyHostToDevice, c->stream));
     SGP_CUDA(c, cudaMemcpyAsync(c->dI8Centre, ctr.data(), dp16 * 8, cudaMemcpyHostToDevice, c->stream));
     SGP_CUDA(c, cudaMemsetAsync(c->dI8Flags, 0, sizeof(int), c->stream));
+    SGP_CUDA(c, cudaMemsetAsync(c->dI8NormSum, 0, 2 * sizeof(double), c->stream));
     SGP_CUDA(c, launch_i8_prep_active(c->dI8Zt, c->dZ, m, c->m_pad, d, c->dI8Scale, c->dI8Centre, c->dI8Flags,
                                       c->stream));
     c->launches += 1;
     SGP_CUDA(c, cudaStreamSynchronize(c->stream));               // sc / ctr are locals
   }
   SGP_CUDA(c, cudaStreamSynchronize(c->stream));   // Z / beta are host temporaries of the caller
-  drop_gram_events(c);
+  c->gram_events_used = 0;
+  c->i8_points = 0;
   c->begun = true; c->finished = false; c->has_magic = false; c->i8_used = false;
   return SGP_OK;
 }
@@ -425,25 +445,35 @@ int sgp_stats_finish(sgp_ctx* h, double* G_out, double* b_out) {
   if (!c->begun) return fail(c, SGP_E_STATE, "sgp_stats_begin should have been called first");
   SGP_CUDA(c, cudaSetDevice(c->device));
   const size_t mm = static_cast<size_t>(c->m) * c->m;
-  if (!c->finished && c->i8_ok && c->i8_used && c->dI8Flags) {
-    int flags = 0;
-    SGP_CUDA(c, cudaMemcpyAsync(&flags, c->dI8Flags, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    SGP_CUDA(c, cudaStreamSynchronize(c->stream));
-    if (flags & 1)
-      return fail(c, SGP_E_RANGE, "scaled coordinates exceed the fp16 operand range of SGP_PREC_I8; "
-                                  "rerun the statistics with sgp_set_precision(SGP_PREC_F64)");
-  }
-  if (!c->finished && c->comm && c->nranks > 1) {
-    // PGPH:31-35 combOp: one all-reduce of the packed [G;b] over NVLink
-    ncclResult_t r = nccl().AllReduce(c->dGb, c->dGb, mm + c->m, ncclDouble, ncclSum, c->comm, c->stream);
-    if (r != ncclSuccess) return fail(c, SGP_E_NCCL, std::string("ncclAllReduce: ") + nccl().GetErrorString(r));
+  double status = 0.0;
+  if (!c->finished) {
+    // The rank-local status of the int8 path (fp16 operand range overflow; AUTO's magnitude budget exceeded over the
+    // WHOLE window, not just the first chunk the kernel choice looked at) rides in the last slot of the all-reduced
+    // buffer: every rank sees the same sum and takes the same return decision AFTER the collective -- a rank that
+    // bailed out before it would leave its peers blocked in ncclAllReduce.
+    const bool i8 = c->i8_ok && c->i8_used && c->dI8Flags;
+    const bool budget = i8 && c->precision == SGP_PREC_AUTO;
+    const double limit = (c->i8_norm_budget - c->i8_z_norm_mean) * static_cast<double>(c->i8_points) * 1.25;
+    SGP_CUDA(c, launch_status_to_double(c->dGb + mm + c->m, i8 ? c->dI8Flags : nullptr, 1,
+                                        budget ? c->dI8NormSum : nullptr, limit, c->stream));
     c->launches += 1;
+    if (c->comm && c->nranks > 1) {
+      // PGPH:31-35 combOp: one all-reduce of the packed [G;b;status] over NVLink
+      ncclResult_t r = nccl().AllReduce(c->dGb, c->dGb, mm + c->m + 1, ncclDouble, ncclSum, c->comm, c->stream);
+      if (r != ncclSuccess) return fail(c, SGP_E_NCCL, std::string("ncclAllReduce: ") + nccl().GetErrorString(r));
+      c->launches += 1;
+    }
+    SGP_CUDA(c, cudaMemcpyAsync(&status, c->dGb + mm + c->m, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   }
   c->finished = true;
   if (G_out) SGP_CUDA(c, cudaMemcpyAsync(G_out, c->dGb, mm * 8, cudaMemcpyDeviceToHost, c->stream));
   if (b_out)
     SGP_CUDA(c, cudaMemcpyAsync(b_out, c->dGb + mm, static_cast<size_t>(c->m) * 8, cudaMemcpyDeviceToHost, c->stream));
   SGP_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (status != 0.0)
+    return fail(c, SGP_E_RANGE, "SGP_PREC_I8 cannot represent this shard on some rank (scaled coordinates outside the "
+                                "fp16 operand range, or scaled squared norms above AUTO's magnitude budget); "
+                                "rerun the statistics with sgp_set_precision(SGP_PREC_F64)");
   return SGP_OK;
 }
 
@@ -508,13 +538,13 @@ int sgp_gram_kernel_time(sgp_ctx* h, double* total_ms, int64_t* launches) {
   SGP_CUDA(c, cudaSetDevice(c->device));
   SGP_CUDA(c, cudaStreamSynchronize(c->stream));
   double tot = 0.0;
-  for (auto& e : c->gram_events) {
+  for (size_t i = 0; i < c->gram_events_used; ++i) {
     float ms = 0.f;
-    SGP_CUDA(c, cudaEventElapsedTime(&ms, e.first, e.second));
+    SGP_CUDA(c, cudaEventElapsedTime(&ms, c->gram_events[i].first, c->gram_events[i].second));
     tot += ms;
   }
   if (total_ms) *total_ms = tot;
-  if (launches) *launches = static_cast<int64_t>(c->gram_events.size());
+  if (launches) *launches = static_cast<int64_t>(c->gram_events_used);
   return SGP_OK;
 }
 
@@ -609,7 +639,7 @@ int objective_setup(Ctx* c, const sgp_kernel_desc* k, const sgp_hyper* hypers, i
     }
   }
   // one scratch allocation: [beta | coef | value | total] doubles, then [kind | term | dim | flags] ints
-  const size_t n_dbl = beta.size() + coef.size() + value.size() + W;
+  const size_t n_dbl = beta.size() + coef.size() + value.size() + W + 1;    // ... + totals [W] + status [1]
   const size_t n_int = 3 * static_cast<size_t>(nh) + 1;
   std::vector<double> hd(n_dbl, 0.0);
   std::vector<int> hi(n_int, 0);
@@ -641,17 +671,18 @@ int objective_setup(Ctx* c, const sgp_kernel_desc* k, const sgp_hyper* hypers, i
 
 // all-reduce over ranks, copy the (objective, gradient) row back, map a bad pivot to SGP_E_NOT_PD
 int objective_finish(Ctx* c, const ObjectiveArgs& o, double* val_out, double* grad_out) {
+  // the rank-local "bad pivot" flag is all-reduced WITH the totals so that every rank raises (or none does)
+  SGP_CUDA(c, launch_status_to_double(o.dTotal + o.W, o.dFlags, 1, nullptr, 0.0, c->stream));
+  c->launches += 1;
   if (c->comm && c->nranks > 1) {
-    ncclResult_t r = nccl().AllReduce(o.dTotal, o.dTotal, o.W, ncclDouble, ncclSum, c->comm, c->stream);
+    ncclResult_t r = nccl().AllReduce(o.dTotal, o.dTotal, o.W + 1, ncclDouble, ncclSum, c->comm, c->stream);
     if (r != ncclSuccess) return fail(c, SGP_E_NCCL, std::string("ncclAllReduce: ") + nccl().GetErrorString(r));
     c->launches += 1;
   }
-  std::vector<double> tot(o.W);
-  int flags = 0;
-  SGP_CUDA(c, cudaMemcpyAsync(tot.data(), o.dTotal, static_cast<size_t>(o.W) * 8, cudaMemcpyDeviceToHost, c->stream));
-  SGP_CUDA(c, cudaMemcpyAsync(&flags, o.dFlags, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  std::vector<double> tot(o.W + 1);
+  SGP_CUDA(c, cudaMemcpyAsync(tot.data(), o.dTotal, static_cast<size_t>(o.W + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
   SGP_CUDA(c, cudaStreamSynchronize(c->stream));
-  if (flags & 1) return fail(c, SGP_E_NOT_PD, "an expert's kernel matrix is not positive definite (increase sigma2)");
+  if (tot[o.W] != 0.0) return fail(c, SGP_E_NOT_PD, "an expert's kernel matrix is not positive definite (increase sigma2)");
   *val_out = tot[0];
   for (int i = 1; i < o.W; ++i) grad_out[i - 1] = tot[i];
   return SGP_OK;
@@ -703,6 +734,12 @@ int sgp_experts_get_f(sgp_ctx* h, double* f_out) {
 int sgp_last_path(const sgp_ctx* h) {
   const Ctx* c = reinterpret_cast<const Ctx*>(h);
   return c ? c->last_path : -1;
+}
+
+int sgp_last_tail_path(const sgp_ctx* h) {
+  const Ctx* c = reinterpret_cast<const Ctx*>(h);
+  if (!c || !c->has_magic_run) return -1;
+  return c->tail_fast ? 1 : 0;
 }
 
 int sgp_debug_i8_tile(sgp_ctx* h, float* T_out, uint32_t* w_out) {
@@ -763,22 +800,19 @@ int sgp_cross_kernel(sgp_ctx* h, const double* X, int64_t n, double* K_out) {
   if (n <= 0 || !X || !K_out) return fail(c, SGP_E_BADARG, "null argument");
   if (n > 65535 * 8) return fail(c, SGP_E_BADARG, "sgp_cross_kernel: n too large for one call");
   SGP_CUDA(c, cudaSetDevice(c->device));
-  double *dX = nullptr, *dK = nullptr;
-  SGP_CUDA(c, cudaMalloc(&dX, static_cast<size_t>(n) * c->d * 8));
-  cudaError_t e = cudaMalloc(&dK, static_cast<size_t>(n) * c->m * 8);
-  if (e != cudaSuccess) { cudaFree(dX); return fail(c, SGP_E_CUDA, cudaGetErrorString(e)); }
-  cudaMemcpyAsync(dX, X, static_cast<size_t>(n) * c->d * 8, cudaMemcpyHostToDevice, c->stream);
+  int rc = ctx_scratch(c, c->cross_ws, (static_cast<size_t>(n) * c->d + static_cast<size_t>(n) * c->m) * 8);
+  if (rc != SGP_OK) return rc;
+  double* dX = static_cast<double*>(c->cross_ws.p);
+  double* dK = dX + static_cast<size_t>(n) * c->d;
+  SGP_CUDA(c, cudaMemcpyAsync(dX, X, static_cast<size_t>(n) * c->d * 8, cudaMemcpyHostToDevice, c->stream));
   if (c->kf.n_terms > 0) {
-    e = launch_cross_kernel(dK, dX, c->dZs, c->dBeta, c->kf, n, c->d, c->dpad, c->m, c->m_pad, c->stream);
+    SGP_CUDA(c, launch_cross_kernel(dK, dX, c->dZs, c->dBeta, c->kf, n, c->d, c->dpad, c->m, c->m_pad, c->stream));
     c->launches += 1;
   } else {
-    e = cudaMemsetAsync(dK, 0, static_cast<size_t>(n) * c->m * 8, c->stream);
+    SGP_CUDA(c, cudaMemsetAsync(dK, 0, static_cast<size_t>(n) * c->m * 8, c->stream));
   }
-  if (e == cudaSuccess)
-    e = cudaMemcpyAsync(K_out, dK, static_cast<size_t>(n) * c->m * 8, cudaMemcpyDeviceToHost, c->stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-  cudaFree(dX); cudaFree(dK);
-  if (e != cudaSuccess) return fail(c, SGP_E_CUDA, cudaGetErrorString(e));
+  SGP_CUDA(c, cudaMemcpyAsync(K_out, dK, static_cast<size_t>(n) * c->m * 8, cudaMemcpyDeviceToHost, c->stream));
+  SGP_CUDA(c, cudaStreamSynchronize(c->stream));
   return SGP_OK;
 }
 

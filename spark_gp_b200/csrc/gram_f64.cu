@@ -391,24 +391,20 @@ cudaError_t launch_gram_f64(const GramParams& p, bool strict_elements, cudaStrea
     const int nt = p.n_tiles_1d * (p.n_tiles_1d + 1) / 2;
     dim3 grid(nt, p.n_slices);
     constexpr size_t smem = gram_smem_bytes<double>();
-    static bool attr_set = false;
-    if (!attr_set) {
+    {   // the attribute is per DEVICE (one JVM may hold contexts on several GPUs): set it on every launch, it is cheap
       cudaError_t e = cudaFuncSetAttribute(kmn_gram_f64_kernel<double, 128>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return e;
-      attr_set = true;
     }
     kmn_gram_f64_kernel<double, 128><<<grid, NT, smem, s>>>(p);
   } else {
     const int nt = p.n_tiles_1d * (p.n_tiles_1d + 1);       // 128 x 64 staircase; two CTAs per SM
     dim3 grid(nt, p.n_slices);
     constexpr size_t smem = gram_smem_bytes<float>();
-    static bool attr_set = false;
-    if (!attr_set) {
+    {
       cudaError_t e = cudaFuncSetAttribute(kmn_gram_f64_kernel<float, 64>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return e;
-      attr_set = true;
     }
     kmn_gram_f64_kernel<float, 64><<<grid, NT, smem, s>>>(p);
   }

@@ -248,7 +248,7 @@ __global__ void prep_points_kernel(uint8_t* __restrict__ Xt, float* __restrict__
                                    int x_is_f32, const double* __restrict__ y, long long n, long long n_units,
                                    int d, int dp, int nchunks, const double* __restrict__ scale /*[dp]*/,
                                    const double* __restrict__ centre /*[dp]*/, int* __restrict__ flags,
-                                   double* __restrict__ norm_sum) {
+                                   double* __restrict__ norm_sum, double* __restrict__ norm_sum_call) {
   const long long pt = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (pt >= n_units * UP) return;
   const bool valid = pt < n;
@@ -269,7 +269,10 @@ __global__ void prep_points_kernel(uint8_t* __restrict__ Xt, float* __restrict__
   if (norm_sum) {                                                // sum of scaled squared norms (AUTO's magnitude gate)
     double v2 = valid ? norm2 : 0.0;
     for (int o = 16; o > 0; o >>= 1) v2 += __shfl_xor_sync(0xffffffffu, v2, o);
-    if ((threadIdx.x & 31) == 0 && v2 > 0.0) atomicAdd(norm_sum, v2);
+    if ((threadIdx.x & 31) == 0 && v2 > 0.0) {
+      atomicAdd(norm_sum, v2);
+      if (norm_sum_call) atomicAdd(norm_sum_call, v2);
+    }
   }
   ys[pt] = valid ? static_cast<float>(y[pt]) : 0.f;
   const long long unit = pt / UP;
@@ -712,13 +715,13 @@ cudaError_t launch_i8_prep_active(uint8_t* Zt, const double* dZ, int m, int m_pa
 
 cudaError_t launch_i8_prep_points(uint8_t* Xt, float* ys, const void* dX, int x_is_f32, const double* dy, long long n,
                                   int d, const double* dScale, const double* dCentre, int* dFlags, double* dNormSum,
-                                  cudaStream_t s) {
+                                  double* dNormSumCall, cudaStream_t s) {
   const int dp = (d + 15) / 16 * 16;
   const long long units = (n + UP - 1) / UP;
   const long long threads = units * UP;
   prep_points_kernel<<<static_cast<unsigned>((threads + 127) / 128), 128, 0, s>>>(Xt, ys, dX, x_is_f32, dy, n, units, d, dp,
                                                                                 i8_nchunks(d), dScale, dCentre, dFlags,
-                                                                                dNormSum);
+                                                                                dNormSum, dNormSumCall);
   return cudaGetLastError();
 }
 
@@ -742,13 +745,10 @@ cudaError_t launch_gram_i8(const uint8_t* Xt, const float* ys, const uint8_t* Zt
   p.xstages = (p.nchunks == 1) ? 4 : 3;
   const size_t smem = 1024 + 6 * PANEL_BYTES + 2 * p.nchunks * PANEL_BYTES + p.xstages * p.nchunks * XIMG_BYTES +
                       YSTAGES * UP * 4 + 4 * 128 * 8 + 256;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kmn_gram_i8_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(kmn_gram_i8_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  {   // per-device attribute: set on every launch (contexts on several GPUs may live in one process)
+    cudaError_t e = dbg_T ? cudaFuncSetAttribute(kmn_gram_i8_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)
+                          : cudaFuncSetAttribute(kmn_gram_i8_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
-    attr_set = true;
   }
   const int nt = p.n_tiles_1d * (p.n_tiles_1d + 1) / 2;
   dim3 grid(nt, n_slices);

@@ -73,8 +73,9 @@ __global__ void identity_kernel(double* __restrict__ I, int m) {
   if (i < static_cast<size_t>(m) * m) I[i] = (i / m == i % m) ? 1.0 : 0.0;
 }
 
-__global__ void magic_matrix_kernel(double* __restrict__ out, const double* __restrict__ invA,
-                                    const double* __restrict__ invK, double wn, size_t n) {
+// (out may alias invA: run_tail finishes inv(A) in place)
+__global__ void magic_matrix_kernel(double* out, const double* invA, const double* __restrict__ invK, double wn,
+                                    size_t n) {
   const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
   if (i < n) out[i] = invA[i] * wn - invK[i];   // PGPH:59
 }
@@ -112,6 +113,14 @@ __global__ void predict_finish_kernel(double* __restrict__ mean, double* __restr
       if (var) var[r] = self_k + sv;
     }
   }
+}
+
+// status words that must be agreed on by every rank travel inside the all-reduced buffers as doubles
+__global__ void status_to_double_kernel(double* __restrict__ dst, const int* __restrict__ flags, int mask,
+                                        const double* __restrict__ norm_sum, double norm_limit) {
+  double v = (flags && (*flags & mask)) ? 1.0 : 0.0;
+  if (norm_sum && *norm_sum > norm_limit) v += 2.0;
+  *dst = v;
 }
 
 Scales to_scales(const KernelFlat& kf) {
@@ -160,6 +169,12 @@ cudaError_t launch_magic_matrix(double* out, const double* invA, const double* i
                                 cudaStream_t s) {
   const size_t n = static_cast<size_t>(m) * m;
   magic_matrix_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(out, invA, invK, wn, n);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_status_to_double(double* dst, const int* flags, int mask, const double* norm_sum, double norm_limit,
+                                    cudaStream_t s) {
+  status_to_double_kernel<<<1, 1, 0, s>>>(dst, flags, mask, norm_sum, norm_limit);
   return cudaGetLastError();
 }
 

@@ -44,6 +44,12 @@ struct GramParams {
   int n_tiles_1d;       // m_pad / kTile
 };
 
+// Grow-only device scratch block owned by a context (no cudaMalloc / cudaFree in steady state).
+struct DevScratch {
+  void* p = nullptr;
+  size_t cap = 0;
+};
+
 struct Ctx {
   int device = 0;
   int precision = SGP_PREC_AUTO;
@@ -51,8 +57,14 @@ struct Ctx {
   std::string err;
   cudaStream_t stream = nullptr;       // compute
   cudaStream_t copy_stream = nullptr;  // H2D staging
+  cudaStream_t tail_stream = nullptr;  // second chain of the m x m tail (inv(K_mm) next to the A chain)
   cusolverDnHandle_t solver = nullptr;
+  cusolverDnHandle_t solver2 = nullptr;   // bound to tail_stream
   cublasHandle_t blas = nullptr;
+  cudaEvent_t tail_fork = nullptr, tail_join = nullptr;
+  DevScratch tail_ws, tail_ws2, predict_ws, cross_ws;
+  bool has_magic_run = false;
+  bool tail_fast = false;              // last sgp_magic took the Cholesky path for both matrices
   ncclComm_t comm = nullptr;
   int rank = 0, nranks = 1;
   int num_sms = kSMsB200;
@@ -76,7 +88,8 @@ struct Ctx {
   double* dI8Scale = nullptr;    // [dp16] sqrt(log2 e) * beta_k
   double* dI8Centre = nullptr;   // [dp16] per-feature centre (active-set mean)
   int* dI8Flags = nullptr;       // bit 0: coordinates out of fp16 operand range
-  double* dI8NormSum = nullptr;  // sum over the current shard of |x^|^2 (scaled, centred)
+  double* dI8NormSum = nullptr;  // [0]: sum of |x^|^2 over every int8 chunk since begin; [1]: first chunk of this call
+  long long i8_points = 0;       // points that went through the int8 kernel since begin
   double i8_z_norm_mean = 0.0;   // mean over the active set of |z^|^2
   double i8_norm_budget = 8.0;   // AUTO: int8 path only if mean|x^|^2 + mean|z^|^2 <= budget
   uint8_t* dI8Zt = nullptr;      // active-set operand images
@@ -101,7 +114,8 @@ struct Ctx {
   cudaEvent_t stage_ready[2] = {nullptr, nullptr};  // recorded when the H2D into buffer i is done
   // instrumentation
   int64_t launches = 0;
-  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> gram_events;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> gram_events;   // event POOL (created once, reused)
+  size_t gram_events_used = 0;                                    // pairs recorded since the last begin
   cudaEvent_t user_events[8] = {nullptr};
   float* dbgT = nullptr;       // sgp_debug_i8_tile
   uint32_t* dbgW = nullptr;
@@ -132,6 +146,8 @@ cudaError_t launch_axpby_diag(double* A, const double* K, const double* G, doubl
 cudaError_t launch_set_identity(double* I, int m, cudaStream_t s);
 cudaError_t launch_magic_matrix(double* out, const double* invA, const double* invK, double wn, int m,
                                 cudaStream_t s);
+cudaError_t launch_status_to_double(double* dst, const int* flags, int mask, const double* norm_sum, double norm_limit,
+                                    cudaStream_t s);
 cudaError_t launch_predict_finish(double* mean, double* var, const double* K /*n x m*/,
                                   const double* W /*n x m = K*M*/, const double* mv, double self_k,
                                   long long n, int m, cudaStream_t s);
@@ -144,7 +160,7 @@ cudaError_t launch_i8_prep_active(uint8_t* Zt, const double* dZ, int m, int m_pa
                                   const double* dCentre, int* dFlags, cudaStream_t s);
 cudaError_t launch_i8_prep_points(uint8_t* Xt, float* ys, const void* dX, int x_is_f32, const double* dy, long long n,
                                   int d, const double* dScale, const double* dCentre, int* dFlags, double* dNormSum,
-                                  cudaStream_t s);
+                                  double* dNormSumCall, cudaStream_t s);
 cudaError_t launch_gram_i8(const uint8_t* Xt, const float* ys, const uint8_t* Zt, long long n, int d, int m_pad,
                            int n_slices, double* Gpart, double* bpart, double C, float* dbg_T, uint32_t* dbg_w,
                            long long* dbg_clk, cudaStream_t s);
@@ -164,6 +180,7 @@ cudaError_t launch_laplace(const double* dX, const double* dy, double* df, const
                            double tol,
                            double* dPerExpert, double* dTotal, int* dFlags, cudaStream_t s);
 
+int ctx_scratch(Ctx* c, DevScratch& s, size_t bytes);
 int run_tail(Ctx* c, double* magic_vector, double* magic_matrix);
 int run_predict(Ctx* c, const double* X, long long n, double* mean_out, double* var_out);
 

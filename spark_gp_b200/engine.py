@@ -142,6 +142,21 @@ class ProjectedProcessEngine:
     def sync(self):
         self._check(self._lib.sgp_sync(self._h))
 
+    def statistics(self, kernel: Kernel, active_set, X, y, shard_points: int = 1 << 22):
+        """`getMatrixKmnKnmAndVectorKmny` over host data in shards (PGPH:23 broadcast, PGPH:25-35 seqOp over shards).
+        When the tcgen05 int8 path reports SGP_E_RANGE (coordinates outside its operand range, or AUTO's magnitude
+        budget exceeded over the whole window) the pass is repeated on the fp64 DMMA kernel -- still on the GPU."""
+        def run():
+            self.begin(kernel, active_set)
+            for s in range(0, len(X), shard_points):
+                self.accumulate(X[s:s + shard_points], y[s:s + shard_points])
+            return self.finish()
+        try:
+            return run()
+        except OperandRangeError:
+            self.set_precision(N.SGP_PREC_F64)
+            return run()
+
     # ---- the BCM hyper-parameter objective (GPR:55-68 over all experts, GPC:73-78) ----------------------------------
     def experts_upload(self, X, y, offsets):
         """Experts packed expert-major: expert e owns rows offsets[e]..offsets[e+1]-1."""
@@ -265,6 +280,10 @@ class ProjectedProcessEngine:
     def last_path(self) -> int:
         """SGP_PREC_F64 / SGP_PREC_F64_STRICT / SGP_PREC_I8: the kernel the last statistics launch ran."""
         return int(self._lib.sgp_last_path(self._h))
+
+    def last_tail_path(self) -> int:
+        """1: the tail ran on Cholesky factors (PD check included); 0: the reference's dsyevd + LU sequence; -1: never ran."""
+        return int(self._lib.sgp_last_tail_path(self._h))
 
     def launch_count(self) -> int:
         return int(self._lib.sgp_launch_count(self._h))

@@ -233,16 +233,7 @@ class GaussianProcessRegression(GaussianProcessParams):
         kernel = self.getKernel().setHyperparameters(theta)
         eng = ProjectedProcessEngine(self._device)
 
-        def stats():
-            eng.begin(kernel, active_set)                               # PGPH:23 broadcast(activeSet)
-            for s in range(0, len(X), self._shard_points):              # PGPH:25-35 seqOp over shards
-                eng.accumulate(X[s:s + self._shard_points], y[s:s + self._shard_points])
-            return eng.finish()
-        try:
-            G, b = stats()
-        except OperandRangeError:                                       # still on the GPU: fp64 DMMA kernel
-            eng.set_precision(N.SGP_PREC_F64)
-            G, b = stats()
+        G, b = eng.statistics(kernel, active_set, X, y, self._shard_points)   # PGPH:20-36 (+ fp64-kernel fallback)
         mv, mm = eng.magic()                                            # PGPH:49-60
         self.last_stats = (G, b)
         return GaussianProcessRegressionModel(GaussianProjectedProcessRawPredictor(eng, mv, mm, kernel, active_set),
