@@ -604,15 +604,15 @@ def test_i8_headline_path_vs_oracle(eng):
 def test_i8_config_shapes_vs_oracle(eng, n, d, m):
     """Sub-shards of BASELINE configs[3] (d=32, m=2000: two 64-column K chunks of the distance contraction, 136 G tiles)
     and configs[4] (d=8, m=4000: 528 G tiles = more CTAs than SMs), plus d = 17 / 31 / 1 and a ragged point count, on
-    the forced int8 kernel against the oracle.  Tolerance: on shards this small the zero-mean element errors have not
-    averaged out yet (they shrink like 1/sqrt(N)): TOL_I8 here, the 1e-6 gate on >= 262144 points above."""
+    the forced int8 kernel against the oracle, at the SURVEY 8(d) gate of 1e-6 (measured 1.3e-7 .. 7.7e-7,
+    profiles/r02a_gpu_tests_r1kernel.log)."""
     X, y, Z, k, ok = _bench_workload(n, d, m, seed=100 + d)
     G0, b0 = _oracle_stats_chunked(ok, X, y, Z)
     G, b = run_stats(eng, k, X, y, Z, N.SGP_PREC_I8)
     assert eng.last_path() == N.SGP_PREC_I8
     eg, eb = rel(G, G0), rel(b, b0)
     print("int8 vs oracle n=%d d=%d m=%d: dG=%.2e db=%.2e" % (n, d, m, eg, eb))
-    assert eg < TOL_I8 and eb < TOL_I8
+    assert eg < TOL_STATS and eb < TOL_STATS
     assert np.array_equal(G, G.T)
     Gs, bs = run_stats(eng, k, X, y, Z, N.SGP_PREC_F64)               # the fp64 DMMA kernel on the same shapes
     assert rel(Gs, G0) < TOL_STATS and rel(bs, b0) < TOL_STATS
