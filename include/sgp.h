@@ -182,9 +182,10 @@ int sgp_last_tail_path(const sgp_ctx* ctx);
  * the first CTA of the last launch, T = -q*log2(e) (128 active rows x 64 points, fp32) and the fixed-point words
  * (0x4B000000 | (u + 0x4040)), u = s2*2^15 + s1*2^7 + s0 in balanced digits. */
 int sgp_debug_i8_tile(sgp_ctx* ctx, float* T_out /* 128*64 */, uint32_t* w_out /* 128*64 */);
-/* Debug aid: clock64 timeline [3 roles: MMA warp, epilogue group 0, group 1][32 units: 64..95][8 events] of
- * CTA (1,0) of the last SGP_PREC_I8 launch made while armed (see sgp_debug_i8_tile). */
-int sgp_debug_i8_timeline(sgp_ctx* ctx, long long* out /* 768 */);
+/* Debug aid: clock64 timeline [2 CTAs: tile (0,0) = publisher, tile (1,0) = consumer][5 roles: distance issuer, Gram
+ * issuer, epilogue group 0, group 1, sharing warp][32 units: 64..95][8 events] of the last SGP_PREC_I8 launch made while
+ * armed (see sgp_debug_i8_tile). */
+int sgp_debug_i8_timeline(sgp_ctx* ctx, long long* out /* 2560 */);
 /* Evaluate K(X_test, Z) (n x m row-major fp64 out) with the current kernel -- the `crossKernel`
  * contract of kernel/Kernel.scala:69-74 (used by the golden-vector tests). */
 int sgp_cross_kernel(sgp_ctx* ctx, const double* X, int64_t n, double* K_out);

@@ -40,7 +40,19 @@ static NcclApi& nccl() {
 }
 
 int fail(Ctx* c, int code, const std::string& msg) {
-  if (c) c->err = msg; else g_create_err = msg;
+  if (c) {
+    c->err = msg;
+    if (code == SGP_E_CUDA && c->i8_pm_host && c->i8_pm_host[0] != 0) {
+      const int* pm = c->i8_pm_host;            // int8 kernel post-mortem: first wait that made no progress for ~1 s
+      long long unit;
+      std::memcpy(&unit, pm + 4, sizeof(unit));
+      c->err += " [kmn_gram_i8 post-mortem: wait site " + std::to_string(pm[0]) + " block (" + std::to_string(pm[1]) + "," +
+                std::to_string(pm[2]) + ") warp " + std::to_string(pm[3]) + " unit " + std::to_string(unit) + " a=" +
+                std::to_string(static_cast<unsigned>(pm[6])) + " b=" + std::to_string(static_cast<unsigned>(pm[7])) + "]";
+    }
+  } else {
+    g_create_err = msg;
+  }
   return code;
 }
 
@@ -78,11 +90,18 @@ static int launch_stats(Ctx* c, const void* dX, int x_is_f32, const double* dy, 
   if (n <= 0) return SGP_OK;
   const int nt1 = c->m_pad / kTile;
   const int ntiles = nt1 * (nt1 + 1) / 2;
-  int n_slices = c->num_sms / ntiles;            // fill the SMs: tiles x point-slices
+  int n_slices = c->num_sms / ntiles;            // fp64 kernel: fill the SMs with tiles x point-slices
   if (n_slices < 1) n_slices = 1;
   const long long blocks = (n + 15) / 16;
   if (n_slices > blocks) n_slices = static_cast<int>(blocks);
-  int rc = ensure_partials(c, n_slices);
+  // int8 kernel: cooperative launches of whole tile columns (all CTAs of a launch are co-resident)
+  I8Launch plan[64];
+  int n_plan = 0, plan_slices = 1;
+  if (c->i8_ok && c->i8_impl == 1) {
+    n_plan = i8_plan(c->m_pad, c->num_sms, (n + 63) / 64, plan, 64);
+    for (int i = 0; i < n_plan; ++i) plan_slices = plan[i].n_slices > plan_slices ? plan[i].n_slices : plan_slices;
+  }
+  int rc = ensure_partials(c, n_slices > plan_slices ? n_slices : plan_slices);
   if (rc != SGP_OK) return rc;
 
   GramParams p{};
@@ -102,6 +121,10 @@ static int launch_stats(Ctx* c, const void* dX, int x_is_f32, const double* dy, 
   if (c->precision == SGP_PREC_AUTO && !first_of_call) use_i8 = use_i8 && c->call_i8;
   if (c->precision == SGP_PREC_I8 && !c->i8_ok)
     return fail(c, SGP_E_BADARG, "SGP_PREC_I8 needs a kernel with exactly one non-Eye term and d <= 32");
+  if (use_i8 && c->i8_impl == 1 && n_plan <= 0) {
+    if (c->precision == SGP_PREC_I8) return fail(c, SGP_E_BADARG, "active set too large for the int8 kernel's launch plan");
+    use_i8 = false;
+  }
   if (use_i8) {
     const int nch = i8_nchunks(c->d);
     const size_t xb = i8_points_scratch_bytes(n, nch);
@@ -110,6 +133,10 @@ static int launch_stats(Ctx* c, const void* dX, int x_is_f32, const double* dy, 
       cudaFree(c->dI8Xt); c->dI8Xt = nullptr; c->i8_xt_bytes = 0;
       SGP_CUDA(c, cudaMalloc(&c->dI8Xt, xb));
       c->i8_xt_bytes = xb;
+    }
+    if (c->i8_impl == 1) {
+      rc = ctx_scratch(c, c->i8_share, i8_share_bytes(c->m_pad, plan_slices));
+      if (rc != SGP_OK) return rc;
     }
     if (yb > c->i8_ys_bytes) {
       cudaFree(c->dI8Ys); c->dI8Ys = nullptr; c->i8_ys_bytes = 0;
@@ -147,13 +174,32 @@ static int launch_stats(Ctx* c, const void* dX, int x_is_f32, const double* dy, 
   cudaEvent_t e0 = c->gram_events[c->gram_events_used].first, e1 = c->gram_events[c->gram_events_used].second;
   c->gram_events_used += 1;
   SGP_CUDA(c, cudaEventRecord(e0, c->stream));
-  if (use_i8)
-    SGP_CUDA(c, launch_gram_i8(c->dI8Xt, c->dI8Ys, c->dI8Zt, n, c->d, c->m_pad, n_slices, c->dGpart, c->dBpart,
-                               c->kf.scale[0], c->dbgT, c->dbgW, c->dbgClk, c->stream));
-  else
-    SGP_CUDA(c, launch_gram_f64(p, c->precision == SGP_PREC_F64_STRICT, c->stream));
-  SGP_CUDA(c, cudaEventRecord(e1, c->stream));
   const size_t mm = static_cast<size_t>(c->m) * c->m;
+  if (use_i8 && c->i8_impl == 0) {
+    SGP_CUDA(c, launch_gram_i8(c->dI8Xt, c->dI8Ys, c->dI8Zt, n, c->d, c->m_pad, n_slices, c->dGpart, c->dBpart,
+                               c->kf.scale[0], c->dbgT, c->dbgW, nullptr, c->stream));
+    SGP_CUDA(c, cudaEventRecord(e1, c->stream));
+    SGP_CUDA(c, launch_gram_reduce(c->dGb, c->dGb + mm, c->dGpart, c->dBpart, n_slices, c->m, c->m_pad, c->stream));
+    c->launches += 2;
+    return SGP_OK;
+  }
+  if (use_i8) {
+    for (int i = 0; i < n_plan; ++i) {
+      SGP_CUDA(c, launch_gram_i8_ring(c->dI8Xt, c->dI8Ys, c->dI8Zt, n, c->d, c->m_pad, plan[i], c->dGpart, c->dBpart,
+                                 c->kf.scale[0], static_cast<uint8_t*>(c->i8_share.p), c->dbgT, c->dbgW, c->dbgClk,
+                                 c->i8_pm_dev, c->stream));
+      c->launches += 1;
+    }
+    SGP_CUDA(c, cudaEventRecord(e1, c->stream));
+    for (int i = 0; i < n_plan; ++i) {          // deterministic slice reduction, per launch (its columns, its slices)
+      SGP_CUDA(c, launch_gram_reduce_cols(c->dGb, c->dGb + mm, c->dGpart, c->dBpart, plan[i].n_slices, c->m, c->m_pad,
+                                          plan[i].col_lo * kTile, plan[i].col_hi * kTile, c->stream));
+      c->launches += 1;
+    }
+    return SGP_OK;
+  }
+  SGP_CUDA(c, launch_gram_f64(p, c->precision == SGP_PREC_F64_STRICT, c->stream));
+  SGP_CUDA(c, cudaEventRecord(e1, c->stream));
   SGP_CUDA(c, launch_gram_reduce(c->dGb, c->dGb + mm, c->dGpart, c->dBpart, n_slices, c->m, c->m_pad, c->stream));
   c->launches += 2;
   return SGP_OK;
@@ -204,6 +250,11 @@ int sgp_ctx_create(sgp_ctx** out, int device) {
       (e = cudaEventCreateWithFlags(&c->tail_fork, cudaEventDisableTiming)) != cudaSuccess ||
       (e = cudaEventCreateWithFlags(&c->tail_join, cudaEventDisableTiming)) != cudaSuccess)
     return bail(SGP_E_CUDA, cudaGetErrorString(e));
+  if (cudaHostAlloc(reinterpret_cast<void**>(&c->i8_pm_host), 64, cudaHostAllocMapped) == cudaSuccess) {
+    std::memset(c->i8_pm_host, 0, 64);
+    if (cudaHostGetDevicePointer(&c->i8_pm_dev, c->i8_pm_host, 0) != cudaSuccess) c->i8_pm_dev = nullptr;
+  }
+  if (const char* ev = getenv("SGP_I8_IMPL")) c->i8_impl = (std::string(ev) == "ring") ? 1 : 0;
   if (cusolverDnCreate(&c->solver) != CUSOLVER_STATUS_SUCCESS) return bail(SGP_E_CUDA, "cusolverDnCreate failed");
   if (cusolverDnCreate(&c->solver2) != CUSOLVER_STATUS_SUCCESS) return bail(SGP_E_CUDA, "cusolverDnCreate failed");
   if (cublasCreate(&c->blas) != CUBLAS_STATUS_SUCCESS) return bail(SGP_E_CUDA, "cublasCreate failed");
@@ -221,13 +272,14 @@ int sgp_ctx_destroy(sgp_ctx* h) {
   free_active_set(c);
   cudaFree(c->dGpart); cudaFree(c->dBpart);
   cudaFree(c->dEx); cudaFree(c->dEy); cudaFree(c->dEoff); cudaFree(c->dEf); cudaFree(c->dNllPer); cudaFree(c->dNllScratch);
-  cudaFree(c->dI8Xt); cudaFree(c->dI8Ys); cudaFree(c->dbgT); cudaFree(c->dbgW); cudaFree(c->dbgClk);
+  cudaFree(c->dI8Xt); cudaFree(c->dI8Ys); cudaFree(c->dbgT); cudaFree(c->dbgW); cudaFree(c->dbgClk); cudaFree(c->i8_share.p);
   for (int i = 0; i < 2; ++i) {
     cudaFree(c->stageX[i]); cudaFree(c->stageY[i]);
     if (c->stage_free[i]) cudaEventDestroy(c->stage_free[i]);
     if (c->stage_ready[i]) cudaEventDestroy(c->stage_ready[i]);
   }
   if (c->comm && nccl().ok) nccl().CommDestroy(c->comm);
+  if (c->i8_pm_host) cudaFreeHost(c->i8_pm_host);
   cudaFree(c->tail_ws.p); cudaFree(c->tail_ws2.p); cudaFree(c->predict_ws.p); cudaFree(c->cross_ws.p);
   if (c->tail_fork) cudaEventDestroy(c->tail_fork);
   if (c->tail_join) cudaEventDestroy(c->tail_join);
@@ -751,8 +803,8 @@ int sgp_debug_i8_tile(sgp_ctx* h, float* T_out, uint32_t* w_out) {
     SGP_CUDA(c, cudaMalloc(&c->dbgW, 128 * 64 * 4));
     SGP_CUDA(c, cudaMemset(c->dbgT, 0, 128 * 64 * 4));
     SGP_CUDA(c, cudaMemset(c->dbgW, 0, 128 * 64 * 4));
-    SGP_CUDA(c, cudaMalloc(&c->dbgClk, 3 * 32 * 8 * 8));
-    SGP_CUDA(c, cudaMemset(c->dbgClk, 0, 3 * 32 * 8 * 8));
+    SGP_CUDA(c, cudaMalloc(&c->dbgClk, 2 * 5 * 32 * 8 * 8));
+    SGP_CUDA(c, cudaMemset(c->dbgClk, 0, 2 * 5 * 32 * 8 * 8));
   }
   SGP_CUDA(c, cudaStreamSynchronize(c->stream));
   if (T_out) SGP_CUDA(c, cudaMemcpy(T_out, c->dbgT, 128 * 64 * 4, cudaMemcpyDeviceToHost));
@@ -766,7 +818,7 @@ int sgp_debug_i8_timeline(sgp_ctx* h, long long* out) {
   if (!c->dbgClk) return fail(c, SGP_E_STATE, "arm with sgp_debug_i8_tile first");
   SGP_CUDA(c, cudaSetDevice(c->device));
   SGP_CUDA(c, cudaStreamSynchronize(c->stream));
-  SGP_CUDA(c, cudaMemcpy(out, c->dbgClk, 3 * 32 * 8 * 8, cudaMemcpyDeviceToHost));
+  SGP_CUDA(c, cudaMemcpy(out, c->dbgClk, 2 * 5 * 32 * 8 * 8, cudaMemcpyDeviceToHost));
   return SGP_OK;
 }
 

@@ -367,9 +367,10 @@ __global__ void __launch_bounds__(NT, (TN == 64) ? 2 : 1) kmn_gram_f64_kernel(co
 // G[i][j] (+ mirror) += sum_s Gpart[s][i][j] for i >= j ;  b[i] += sum_s bpart[s][i]
 __global__ void gram_reduce_kernel(double* __restrict__ G, double* __restrict__ b,
                                    const double* __restrict__ Gpart, const double* __restrict__ bpart,
-                                   int n_slices, int m, int m_pad) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+                                   int n_slices, int m, int m_pad, int col_lo, int col_hi) {
+  const int j = col_lo + blockIdx.x * blockDim.x + threadIdx.x;
   const int i = blockIdx.y * blockDim.y + threadIdx.y;
+  if (j >= col_hi) return;
   if (i < m && j <= i) {
     double v = 0.0;
     const size_t stride = static_cast<size_t>(m_pad) * m_pad;
@@ -411,12 +412,19 @@ cudaError_t launch_gram_f64(const GramParams& p, bool strict_elements, cudaStrea
   return cudaGetLastError();
 }
 
+cudaError_t launch_gram_reduce_cols(double* G, double* b, const double* Gpart, const double* bpart, int n_slices,
+                                    int m, int m_pad, int col_lo, int col_hi, cudaStream_t s) {
+  if (col_hi > m) col_hi = m;
+  if (col_hi <= col_lo) return cudaSuccess;
+  dim3 block(32, 8);
+  dim3 grid((col_hi - col_lo + 31) / 32, (m + 7) / 8);
+  gram_reduce_kernel<<<grid, block, 0, s>>>(G, b, Gpart, bpart, n_slices, m, m_pad, col_lo, col_hi);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_gram_reduce(double* G, double* b, const double* Gpart, const double* bpart, int n_slices,
                                int m, int m_pad, cudaStream_t s) {
-  dim3 block(32, 8);
-  dim3 grid((m + 31) / 32, (m + 7) / 8);
-  gram_reduce_kernel<<<grid, block, 0, s>>>(G, b, Gpart, bpart, n_slices, m, m_pad);
-  return cudaGetLastError();
+  return launch_gram_reduce_cols(G, b, Gpart, bpart, n_slices, m, m_pad, 0, m, s);
 }
 
 }  // namespace sgp

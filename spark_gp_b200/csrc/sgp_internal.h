@@ -119,7 +119,11 @@ struct Ctx {
   cudaEvent_t user_events[8] = {nullptr};
   float* dbgT = nullptr;       // sgp_debug_i8_tile
   uint32_t* dbgW = nullptr;
-  long long* dbgClk = nullptr; // [3][32][8] clock64 timeline
+  long long* dbgClk = nullptr; // [2 CTAs][5 roles][32 units][8 events] clock64 timeline
+  int* i8_pm_host = nullptr;   // host-mapped post-mortem record of the int8 kernel (8 ints), and its device alias
+  void* i8_pm_dev = nullptr;
+  int i8_impl = 0;             // 0: self-contained kernel (gram_i8.cu), 1: shared-panel ring kernel (gram_i8_ring.cu)
+  DevScratch i8_share;         // L2 ring + flags through which diagonal CTAs publish their digit planes
 };
 
 // error helpers ---------------------------------------------------------------------------------
@@ -135,6 +139,9 @@ int fail(Ctx* c, int code, const std::string& msg);
 cudaError_t launch_gram_f64(const GramParams& p, bool strict_elements, cudaStream_t s);
 cudaError_t launch_gram_reduce(double* G /*m x m*/, double* b, const double* Gpart, const double* bpart,
                                int n_slices, int m, int m_pad, cudaStream_t s);
+// same, restricted to the G columns / b entries [col_lo, col_hi) (one int8 launch covers whole tile columns)
+cudaError_t launch_gram_reduce_cols(double* G, double* b, const double* Gpart, const double* bpart, int n_slices, int m,
+                                    int m_pad, int col_lo, int col_hi, cudaStream_t s);
 cudaError_t launch_scale_rows(double* out /*[rows][dpad]*/, const double* in /*rows x d*/, const double* beta,
                               int rows_in, int rows_out, int d, int dpad, cudaStream_t s);
 cudaError_t launch_kmm_build(double* Kmm /*m x m*/, const double* Zs, const double* scale_dev_or_null,
@@ -161,6 +168,17 @@ cudaError_t launch_i8_prep_active(uint8_t* Zt, const double* dZ, int m, int m_pa
 cudaError_t launch_i8_prep_points(uint8_t* Xt, float* ys, const void* dX, int x_is_f32, const double* dy, long long n,
                                   int d, const double* dScale, const double* dCentre, int* dFlags, double* dNormSum,
                                   double* dNormSumCall, cudaStream_t s);
+// One cooperative launch of the int8 Gram kernel: whole tile columns [col_lo, col_hi) x n_slices point slices.
+struct I8Launch {
+  int col_lo, col_hi, tiles, n_slices;
+};
+int i8_plan(int m_pad, int num_sms, long long n_units, I8Launch* out, int max_out);
+size_t i8_share_bytes(int m_pad, int n_slices);
+size_t i8_share_flag_bytes(int m_pad, int n_slices);
+cudaError_t launch_gram_i8_ring(const uint8_t* Xt, const float* ys, const uint8_t* Zt, long long n, int d, int m_pad,
+                                const I8Launch& plan, double* Gpart, double* bpart, double C, uint8_t* share, float* dbg_T,
+                                uint32_t* dbg_w, long long* dbg_clk, void* post_mortem, cudaStream_t s);
+// round-1 kernel (every CTA builds both panels of its tile): the default until the ring kernel beats it
 cudaError_t launch_gram_i8(const uint8_t* Xt, const float* ys, const uint8_t* Zt, long long n, int d, int m_pad,
                            int n_slices, double* Gpart, double* bpart, double C, float* dbg_T, uint32_t* dbg_w,
                            long long* dbg_clk, cudaStream_t s);

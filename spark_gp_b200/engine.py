@@ -272,7 +272,7 @@ class ProjectedProcessEngine:
         return T, w
 
     def debug_i8_timeline(self):
-        out = np.zeros((3, 32, 8), dtype=np.int64)
+        out = np.zeros((2, 5, 32, 8), dtype=np.int64)
         self._check(self._lib.sgp_debug_i8_timeline(self._h, N.ptr(out)))
         return out
 
