@@ -137,8 +137,11 @@ typedef struct {
 } sgp_hyper;
 
 /* nll = sum_e [ 1/2 y_e^T K_e^-1 y_e + 1/2 log|det K_e| ]  and its gradient (n_hypers entries), summed over the
- * uploaded experts and over ranks (ncclAllReduce of 1 + n_hypers doubles if a communicator exists).
- * SGP_E_NOT_PD if some expert's kernel matrix has a non-positive Cholesky pivot. */
+ * uploaded experts and over ranks (ncclAllReduce of 1 + n_hypers doubles + a status word if a communicator exists).
+ * Experts of any size (GaussianProcessParams.scala:36 sets no bound).  Fast path: on-chip Cholesky per expert (<= ~165
+ * points, SPD).  When an expert is larger, or a Cholesky pivot is not positive, the evaluation runs the reference's own
+ * arithmetic instead -- LU with partial pivoting, log|det| with the sign dropped (logDetAndInv.scala:36-63, GPR:59) --
+ * and only an exactly singular matrix fails, with SGP_E_SINGULAR (Breeze's MatrixSingularException). */
 int sgp_bcm_nll(sgp_ctx* ctx, const sgp_kernel_desc* kernel, const sgp_hyper* hypers, int32_t n_hypers,
                 double* nll_out, double* grad_out);
 
@@ -178,6 +181,8 @@ int sgp_last_path(const sgp_ctx* ctx);
  * definiteness check PGPH:62-65), 0 = the reference's literal sequence (dsyevd eigenvalue check, LU solves) because a
  * Cholesky factorization broke down, -1 = sgp_magic has not run. */
 int sgp_last_tail_path(const sgp_ctx* ctx);
+/* Which path the last sgp_bcm_nll took: 0 = on-chip Cholesky kernel, 1 = global-memory LU (reference arithmetic). */
+int sgp_last_bcm_path(const sgp_ctx* ctx);
 /* Debug aid for SGP_PREC_I8: the first call arms a dump; later calls return, for the first 64-point unit of
  * the first CTA of the last launch, T = -q*log2(e) (128 active rows x 64 points, fp32) and the fixed-point words
  * (0x4B000000 | (u + 0x4040)), u = s2*2^15 + s1*2^7 + s0 in balanced digits. */
@@ -185,7 +190,7 @@ int sgp_debug_i8_tile(sgp_ctx* ctx, float* T_out /* 128*64 */, uint32_t* w_out /
 /* Debug aid: clock64 timeline [2 CTAs: tile (0,0) = publisher, tile (1,0) = consumer][5 roles: distance issuer, Gram
  * issuer, epilogue group 0, group 1, sharing warp][32 units: 64..95][8 events] of the last SGP_PREC_I8 launch made while
  * armed (see sgp_debug_i8_tile). */
-int sgp_debug_i8_timeline(sgp_ctx* ctx, long long* out /* 2560 */);
+int sgp_debug_i8_timeline(sgp_ctx* ctx, long long* out /* 2560 + 148*32: timeline, then per-CTA progress marks */);
 /* Evaluate K(X_test, Z) (n x m row-major fp64 out) with the current kernel -- the `crossKernel`
  * contract of kernel/Kernel.scala:69-74 (used by the golden-vector tests). */
 int sgp_cross_kernel(sgp_ctx* ctx, const double* X, int64_t n, double* K_out);

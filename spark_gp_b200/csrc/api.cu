@@ -254,7 +254,8 @@ int sgp_ctx_create(sgp_ctx** out, int device) {
     std::memset(c->i8_pm_host, 0, 64);
     if (cudaHostGetDevicePointer(&c->i8_pm_dev, c->i8_pm_host, 0) != cudaSuccess) c->i8_pm_dev = nullptr;
   }
-  if (const char* ev = getenv("SGP_I8_IMPL")) c->i8_impl = (std::string(ev) == "ring") ? 1 : 0;
+  c->i8_impl = 1;                 // shared-panel ring kernel; SGP_I8_IMPL=v1 selects round 1's self-contained kernel
+  if (const char* ev = getenv("SGP_I8_IMPL")) c->i8_impl = (std::string(ev) == "v1") ? 0 : 1;
   if (cusolverDnCreate(&c->solver) != CUSOLVER_STATUS_SUCCESS) return bail(SGP_E_CUDA, "cusolverDnCreate failed");
   if (cusolverDnCreate(&c->solver2) != CUSOLVER_STATUS_SUCCESS) return bail(SGP_E_CUDA, "cusolverDnCreate failed");
   if (cublasCreate(&c->blas) != CUBLAS_STATUS_SUCCESS) return bail(SGP_E_CUDA, "cublasCreate failed");
@@ -612,8 +613,8 @@ int sgp_experts_upload(sgp_ctx* h, const double* X, const double* y, const int64
     if (ne <= 0) return fail(c, SGP_E_BADARG, "empty expert");
     if (ne > nmax) nmax = static_cast<int>(ne);
   }
-  if (bcm_nll_smem_bytes(nmax) > 227 * 1024)
-    return fail(c, SGP_E_BADARG, "datasetSizeForExpert too large for the on-chip BCM kernel (max ~165 points per expert)");
+  // (no upper bound on the expert size -- GaussianProcessParams.scala:36: experts above the on-chip kernel's ~165 points
+  //  take the global-memory LU path of sgp_bcm_nll)
   SGP_CUDA(c, cudaStreamSynchronize(c->stream));
   cudaFree(c->dEx); cudaFree(c->dEy); cudaFree(c->dEoff); cudaFree(c->dEf);
   c->dEx = c->dEy = c->dEf = nullptr; c->dEoff = nullptr;
@@ -722,9 +723,10 @@ int objective_setup(Ctx* c, const sgp_kernel_desc* k, const sgp_hyper* hypers, i
 }
 
 // all-reduce over ranks, copy the (objective, gradient) row back, map a bad pivot to SGP_E_NOT_PD
-int objective_finish(Ctx* c, const ObjectiveArgs& o, double* val_out, double* grad_out) {
-  // the rank-local "bad pivot" flag is all-reduced WITH the totals so that every rank raises (or none does)
-  SGP_CUDA(c, launch_status_to_double(o.dTotal + o.W, o.dFlags, 1, nullptr, 0.0, c->stream));
+int objective_finish(Ctx* c, const ObjectiveArgs& o, double* val_out, double* grad_out, int mask, int err_code,
+                     const char* err_msg) {
+  // the rank-local status flag is all-reduced WITH the totals so that every rank raises (or none does)
+  SGP_CUDA(c, launch_status_to_double(o.dTotal + o.W, o.dFlags, mask, nullptr, 0.0, c->stream));
   c->launches += 1;
   if (c->comm && c->nranks > 1) {
     ncclResult_t r = nccl().AllReduce(o.dTotal, o.dTotal, o.W + 1, ncclDouble, ncclSum, c->comm, c->stream);
@@ -734,7 +736,7 @@ int objective_finish(Ctx* c, const ObjectiveArgs& o, double* val_out, double* gr
   std::vector<double> tot(o.W + 1);
   SGP_CUDA(c, cudaMemcpyAsync(tot.data(), o.dTotal, static_cast<size_t>(o.W + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
   SGP_CUDA(c, cudaStreamSynchronize(c->stream));
-  if (tot[o.W] != 0.0) return fail(c, SGP_E_NOT_PD, "an expert's kernel matrix is not positive definite (increase sigma2)");
+  if (tot[o.W] != 0.0) return fail(c, err_code, err_msg);
   *val_out = tot[0];
   for (int i = 1; i < o.W; ++i) grad_out[i - 1] = tot[i];
   return SGP_OK;
@@ -750,10 +752,35 @@ int sgp_bcm_nll(sgp_ctx* h, const sgp_kernel_desc* k, const sgp_hyper* hypers, i
   ObjectiveArgs o;
   int rc = objective_setup(c, k, hypers, nh, o);
   if (rc != SGP_OK) return rc;
-  SGP_CUDA(c, launch_bcm_nll(c->dEx, c->dEy, c->dEoff, c->n_experts, c->ex_d, c->ex_nmax, o.kf, o.dBeta, nh, o.dKind,
-                             o.dTerm, o.dDim, o.dCoef, o.dValue, o.any_ard, c->dNllPer, o.dTotal, o.dFlags, c->stream));
-  c->launches += 2;
-  return objective_finish(c, o, nll_out, grad_out);
+  // fast path: on-chip Cholesky per expert (SPD kernel matrices of <= ~165 points -- every default configuration).
+  // general path: experts of any size, or a kernel matrix on which Cholesky broke down (not positive definite): the
+  // reference's own arithmetic, LU with partial pivoting and log|det| with the sign dropped (logDetAndInv.scala:36-63,
+  // GPR:59), on kernel matrices staged in global memory.  The choice is rank-local; the one all-reduce per evaluation
+  // happens afterwards on every rank.
+  bool general = bcm_nll_smem_bytes(c->ex_nmax) > 227 * 1024;
+  if (!general) {
+    SGP_CUDA(c, launch_bcm_nll(c->dEx, c->dEy, c->dEoff, c->n_experts, c->ex_d, c->ex_nmax, o.kf, o.dBeta, nh, o.dKind,
+                               o.dTerm, o.dDim, o.dCoef, o.dValue, o.any_ard, c->dNllPer, o.dTotal, o.dFlags, c->stream));
+    c->launches += 2;
+    int flags = 0;
+    SGP_CUDA(c, cudaMemcpyAsync(&flags, o.dFlags, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    SGP_CUDA(c, cudaStreamSynchronize(c->stream));
+    general = (flags & 1) != 0;
+  }
+  c->bcm_general = general;
+  if (general) {
+    rc = ctx_scratch(c, c->bcm_ws, bcm_general_workspace_bytes(c->n_experts, c->ex_nmax));
+    if (rc != SGP_OK) return rc;
+    SGP_CUDA(c, cudaMemsetAsync(o.dFlags, 0, sizeof(int), c->stream));
+    int blas_status = 0;
+    SGP_CUDA(c, launch_bcm_nll_general(c->blas, &blas_status, c->bcm_ws.p, c->dEx, c->dEy, c->dEoff, c->n_experts, c->ex_d,
+                                       c->ex_nmax, o.kf, o.dBeta, nh, o.dKind, o.dTerm, o.dDim, o.dCoef, o.dValue,
+                                       o.any_ard, c->dNllPer, o.dTotal, o.dFlags, c->stream));
+    if (blas_status != 0) return fail(c, SGP_E_CUDA, "cuBLAS batched LU failed, status " + std::to_string(blas_status));
+    c->launches += 5;
+  }
+  return objective_finish(c, o, nll_out, grad_out, 2, SGP_E_SINGULAR,
+                          "an expert's kernel matrix is singular (MatrixSingularException, logDetAndInv.scala:27-28)");
 }
 
 int sgp_laplace_nll(sgp_ctx* h, const sgp_kernel_desc* k, const sgp_hyper* hypers, int32_t nh, double tol,
@@ -770,7 +797,8 @@ int sgp_laplace_nll(sgp_ctx* h, const sgp_kernel_desc* k, const sgp_hyper* hyper
   SGP_CUDA(c, launch_laplace(c->dEx, c->dEy, c->dEf, c->dEoff, c->n_experts, c->ex_d, c->ex_nmax, o.kf, o.dBeta, nh,
                              o.dKind, o.dTerm, o.dDim, o.dCoef, o.dValue, o.any_ard, tol, c->dNllPer, o.dTotal, o.dFlags, c->stream));
   c->launches += 2;
-  return objective_finish(c, o, neg_log_z_out, grad_out);
+  return objective_finish(c, o, neg_log_z_out, grad_out, 1, SGP_E_NOT_PD,
+                          "an expert's B = I + sqrt(W) K sqrt(W) is not positive definite (increase sigma2)");
 }
 
 int sgp_experts_get_f(sgp_ctx* h, double* f_out) {
@@ -788,6 +816,11 @@ int sgp_last_path(const sgp_ctx* h) {
   return c ? c->last_path : -1;
 }
 
+int sgp_last_bcm_path(const sgp_ctx* h) {
+  const Ctx* c = reinterpret_cast<const Ctx*>(h);
+  return c ? (c->bcm_general ? 1 : 0) : -1;
+}
+
 int sgp_last_tail_path(const sgp_ctx* h) {
   const Ctx* c = reinterpret_cast<const Ctx*>(h);
   if (!c || !c->has_magic_run) return -1;
@@ -803,8 +836,8 @@ int sgp_debug_i8_tile(sgp_ctx* h, float* T_out, uint32_t* w_out) {
     SGP_CUDA(c, cudaMalloc(&c->dbgW, 128 * 64 * 4));
     SGP_CUDA(c, cudaMemset(c->dbgT, 0, 128 * 64 * 4));
     SGP_CUDA(c, cudaMemset(c->dbgW, 0, 128 * 64 * 4));
-    SGP_CUDA(c, cudaMalloc(&c->dbgClk, 2 * 5 * 32 * 8 * 8));
-    SGP_CUDA(c, cudaMemset(c->dbgClk, 0, 2 * 5 * 32 * 8 * 8));
+    SGP_CUDA(c, cudaMalloc(&c->dbgClk, (2560 + 148 * 32) * 8));
+    SGP_CUDA(c, cudaMemset(c->dbgClk, 0, (2560 + 148 * 32) * 8));
   }
   SGP_CUDA(c, cudaStreamSynchronize(c->stream));
   if (T_out) SGP_CUDA(c, cudaMemcpy(T_out, c->dbgT, 128 * 64 * 4, cudaMemcpyDeviceToHost));
@@ -818,7 +851,7 @@ int sgp_debug_i8_timeline(sgp_ctx* h, long long* out) {
   if (!c->dbgClk) return fail(c, SGP_E_STATE, "arm with sgp_debug_i8_tile first");
   SGP_CUDA(c, cudaSetDevice(c->device));
   SGP_CUDA(c, cudaStreamSynchronize(c->stream));
-  SGP_CUDA(c, cudaMemcpy(out, c->dbgClk, 2 * 5 * 32 * 8 * 8, cudaMemcpyDeviceToHost));
+  SGP_CUDA(c, cudaMemcpy(out, c->dbgClk, (2560 + 148 * 32) * 8, cudaMemcpyDeviceToHost));
   return SGP_OK;
 }
 

@@ -53,13 +53,19 @@ namespace sgp {
 namespace {
 
 constexpr int UP = 64;                  // points per pipeline unit
-constexpr int XSTAGES_MAX = 4;          // operand ring depth: 4 stages with one K chunk, 3 with two
-constexpr int YSTAGES = 8;               // y ring is deeper than the operand ring: the epilogue reads y after the
+constexpr int XSTAGES_MAX = 8;          // operand ring depth: 8 stages with one K chunk, 5 with two
+constexpr int YSTAGES = 16;              // y ring is deeper than the operand ring: the epilogue reads y after the
                                         // operand stage of the same unit may already have been recycled
 constexpr int EPI_WARPS = 16;             // two groups of 8 (4 TMEM lane quarters x 2 column halves); group g owns
                                         // the units with (unit & 1) == g, i.e. TMEM distance buffer g
 constexpr int NTHREADS = 128 + EPI_WARPS * 32;
-constexpr uint32_t TM_ACC4 = 0, TM_ACC3 = 128, TM_ACC2 = 256, TM_Q0 = 384;   // TMEM column map
+// TMEM column map: three int32 accumulators, ONE 64-point distance tile (the epilogue copies it to registers at once and
+// frees it), and the A operand of the Gram MMAs -- panel I's digit planes, [k-step of 32 points][plane][8 columns] --
+// which the epilogue writes with tcgen05.st straight from registers: the A side of the Gram products never touches
+// shared memory (the kind::i8 128x128x32 MMA reads 4 KB of A + 4 KB of B per 64 clk = the whole 128 B/clk of the
+// shared-memory port when both come from smem; that port, not the tensor pipe, bounded variants 17-21).
+constexpr uint32_t TM_ACC4 = 0, TM_ACC3 = 128, TM_ACC2 = 256, TM_Q0 = 384, TM_A0 = 448;
+constexpr uint32_t A_KS_COLS = 24;      // TMEM columns of one k-step of the A operand: 3 planes x 8 (32 int8 per row)
 // Fixed point.  u = rint(kappa * C0) < 2^23 is written in balanced digits  u = s2 * 2^15 + s1 * 2^7 + s0  with
 // s2 in [0, 255] (the UNSIGNED int8 operand range), s1 in [-128, 127], s0 in [-64, 63].  One FFMA produces them:
 // mantissa(kappa * C0 + MAGIC) = t = u + 0x4040, and the bytes of (t << 1) are (2 s0 + 128, s1 + 128, s2).  The stored
@@ -86,6 +92,8 @@ constexpr int NPJ_MAX = 5;              // panel-J ring depth (off-diagonal CTAs
 // back-pressure poll, every hop of which is ~1 unit period: with 16 slots the loop lag (6 + 1 + 2 + 5 + polls) was the
 // ring depth itself and the whole column throttled to 3500 clk per unit (profiles/r02_i8_tuning_log.md).
 constexpr int RING_D = 32;
+constexpr int FLAG_STRIDE = 32;         // every counter owns a 128-byte line: 28 publishers + 112 pollers on ONE line (all the
+                                        // `ready` words of m = 1000 fit in 128 bytes) serialised at that L2 bank
 constexpr int PUB_LAG = 4;              // bulk stores the publisher keeps in flight before it publishes a unit
 
 // ---------------------------------------------------------------------------------------------------
@@ -174,6 +182,19 @@ __device__ __forceinline__ void mma_i8(uint32_t d_tmem, uint64_t a_desc, uint64_
       "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
 }
+// A operand from tensor memory (rows = lanes, K bytes packed along 32-bit columns), B from shared memory
+__device__ __forceinline__ void mma_i8_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -310,7 +331,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_ring_kernel(const I8P
   uint8_t* sm = smem_raw + (base - raw);
   // carve-up (all operand tiles 1024-byte aligned)
   const uint32_t s_slot = base;                                           // [NSLOTS][3 planes][8192]  int8 digit planes
-  const uint32_t s_zt = s_slot + (NPI + p.npj) * SLOT_BYTES;              // [nchunks][16384]          active tile I, fp16
+  // (slots: a diagonal CTA keeps its own panel I here -- 4 slots, B operand + publishing; an off-diagonal CTA keeps panel J
+  //  here -- npj slots; panel I of an off-diagonal CTA lives only in tensor memory)
+  const uint32_t s_zt = s_slot + (p.npj > NPI_PUB ? p.npj : NPI_PUB) * SLOT_BYTES;   // [nchunks][16384]  active tile I, fp16
   const uint32_t s_xs = s_zt + p.nchunks * ZPANEL_BYTES;                  // [xstages][nchunks][8192]  point images, fp16
   const uint32_t s_ys = s_xs + p.xstages * p.nchunks * XIMG_BYTES;        // [YSTAGES][64] float
   const uint32_t s_bred = s_ys + YSTAGES * UP * 4;                        // [4][128] double
@@ -318,7 +341,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_ring_kernel(const I8P
   const uint32_t b_xfull = s_bar, b_xempty = b_xfull + 8 * XSTAGES_MAX, b_qfull = b_xempty + 8 * XSTAGES_MAX,
                  b_qempty = b_qfull + 16, b_pifull = b_qempty + 16, b_piempty = b_pifull + 8 * NPI_PUB,
                  b_pjfull = b_piempty + 8 * NPI_PUB, b_pjempty = b_pjfull + 8 * NPJ_MAX, b_accfull = b_pjempty + 8 * NPJ_MAX,
-                 b_accempty = b_accfull + 8, b_zfull = b_accempty + 8, s_tmem = b_zfull + 8;
+                 b_accempty = b_accfull + 8, b_zfull = b_accempty + 8, b_afull = b_zfull + 8 /*[ks][unit parity]*/,
+                 b_aempty = b_afull + 32, s_tmem = b_aempty + 32;
   float* sm_ys = reinterpret_cast<float*>(sm + (s_ys - base));
   double* sm_bred = reinterpret_cast<double*>(sm + (s_bred - base));
   volatile uint32_t* sm_tmem = reinterpret_cast<volatile uint32_t*>(sm + (s_tmem - base));
@@ -336,7 +360,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_ring_kernel(const I8P
   const bool diag = (ti == tj);
   const int n_cons = diag ? (p.nt - 1 - tj) : 0;     // CTAs (I, tj), I > tj, of this slice that read the panel we publish
   const bool publisher = n_cons > 0;
-  const int npi = publisher ? NPI_PUB : NPI;
+  const int npi = NPI_PUB;                        // panel-I smem slots (diagonal CTAs only)
 
   const long long ups = (p.n_units + p.n_slices - 1) / p.n_slices;
   const long long u_lo = ups * blockIdx.y;
@@ -364,6 +388,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_ring_kernel(const I8P
     }
     for (int i = 0; i < NPJ_MAX; ++i) { mbar_init(b_pjfull + 8 * i, 1); mbar_init(b_pjempty + 8 * i, 1); }
     mbar_init(b_accfull, 1); mbar_init(b_accempty, EPI_WARPS); mbar_init(b_zfull, 1);
+    for (int i = 0; i < 4; ++i) { mbar_init(b_afull + 8 * i, 4); mbar_init(b_aempty + 8 * i, 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -383,7 +408,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_ring_kernel(const I8P
                static_cast<uint32_t>(p.nchunks * ZPANEL_BYTES), b_zfull);
       const uint32_t xbytes = static_cast<uint32_t>(p.nchunks * XIMG_BYTES);
       uint32_t s = 0, e_phase = 1;      // parity of the x_empty completion to wait for (first lap: none)
+      constexpr int PF = 24;               // units of X images kept warm in L2 ahead of the copies (HBM latency cover)
+      for (long long i = 0; i < PF && i < nu; ++i)
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.Xt + static_cast<size_t>(u_lo + i) * xbytes), "r"(xbytes) : "memory");
       for (long long i = 0; i < nu; ++i) {
+        if (i + PF < nu)
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.Xt + static_cast<size_t>(u_lo + i + PF) * xbytes), "r"(xbytes) : "memory");
         if (i >= p.xstages) MBAR_WAIT(b_xempty + 8 * s, e_phase, 1, i);
         mbar_expect_tx(b_xfull + 8 * s, xbytes + UP * 4);
         bulk_g2s(s_xs + s * xbytes, p.Xt + static_cast<size_t>(u_lo + i) * xbytes, xbytes, b_xfull + 8 * s);
@@ -419,10 +449,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_ring_kernel(const I8P
         MBAR_WAIT(b_xfull + 8 * s, x_phase, 3, i);
         SGP_TL(0, i, 1);
         const uint32_t qb = static_cast<uint32_t>(i & 1);
-        if (i >= 2) MBAR_WAIT(b_qempty + 8 * qb, static_cast<uint32_t>(((i >> 1) - 1) & 1), 4, i);
+        // ONE distance buffer: unit i-1's epilogue group (the other one) must have copied its tile to registers
+        if (i >= 1) MBAR_WAIT(b_qempty + 8 * (qb ^ 1), static_cast<uint32_t>(((i - 1) >> 1) & 1), 4, i);
         tc_fence_after();
         SGP_TL(0, i, 2);
-        const uint32_t d_tmem = tmem + TM_Q0 + qb * UP;
+        const uint32_t d_tmem = tmem + TM_Q0;
         const uint32_t a0 = zt_lo, b0 = xs_lo + s * xstride;
         if (elected) {
           const int nks0 = (p.nchunks == 1) ? p.ksteps_last : 4;
@@ -455,33 +486,38 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_ring_kernel(const I8P
       uint32_t si = 0, pi_phase = 0, sj = 0, pj_phase = 0;
       for (long long j = 0; j < nu; ++j) {
         SGP_TL(1, j, 0);
-        MBAR_WAIT(b_pifull + 8 * si, pi_phase, 5, j);
-        SGP_TL(1, j, 1);
-        if (!diag) MBAR_WAIT(b_pjfull + 8 * sj, pj_phase, 6, j);
-        tc_fence_after();
-        SGP_TL(1, j, 2);
+        if (DBG && p.dbg_clk != nullptr && (j & 127) == 0 && (j >> 7) < 32 && lane == 0)     // coarse progress of EVERY CTA
+          p.dbg_clk[2560 + (blockIdx.y * gridDim.x + blockIdx.x) * 32 + (j >> 7)] = clock64();
+        const uint32_t up = static_cast<uint32_t>(j & 1), a_phase = static_cast<uint32_t>((j >> 1) & 1);
         const uint32_t fresh = fresh_acc ? 0u : 1u;
         fresh_acc = false;
-        const uint32_t pa = slot_lo + si * SLD;
-        const uint32_t pb = diag ? pa : slot_lo + (NPI + sj) * SLD;
-        if (elected) {
-          // weight 2^32 : P2'P2
-          mma_i8(tmem + TM_ACC4, D(pa + 2 * PL), D(pb + 2 * PL), ID_UU, fresh);
-          mma_i8(tmem + TM_ACC4, D(pa + 2 * PL + 2), D(pb + 2 * PL + 2), ID_UU, 1u);
-          // weight 2^24 : P2'P1 + P1'P2
-          mma_i8(tmem + TM_ACC3, D(pa + 2 * PL), D(pb + 1 * PL), ID_US, fresh);
-          mma_i8(tmem + TM_ACC3, D(pa + 2 * PL + 2), D(pb + 1 * PL + 2), ID_US, 1u);
-          mma_i8(tmem + TM_ACC3, D(pa + 1 * PL), D(pb + 2 * PL), ID_SU, 1u);
-          mma_i8(tmem + TM_ACC3, D(pa + 1 * PL + 2), D(pb + 2 * PL + 2), ID_SU, 1u);
-          // weight 2^16 : P2'P0 + P0'P2 + P1'P1
-          mma_i8(tmem + TM_ACC2, D(pa + 2 * PL), D(pb), ID_US, fresh);
-          mma_i8(tmem + TM_ACC2, D(pa + 2 * PL + 2), D(pb + 2), ID_US, 1u);
-          mma_i8(tmem + TM_ACC2, D(pa), D(pb + 2 * PL), ID_SU, 1u);
-          mma_i8(tmem + TM_ACC2, D(pa + 2), D(pb + 2 * PL + 2), ID_SU, 1u);
-          mma_i8(tmem + TM_ACC2, D(pa + 1 * PL), D(pb + 1 * PL), ID_SS, 1u);
-          mma_i8(tmem + TM_ACC2, D(pa + 1 * PL + 2), D(pb + 1 * PL + 2), ID_SS, 1u);
-          tc_commit(b_piempty + 8 * si);
-          if (!diag) tc_commit(b_pjempty + 8 * sj);
+        const uint32_t pb = diag ? slot_lo + si * SLD : slot_lo + sj * SLD;
+#pragma unroll
+        for (uint32_t ks = 0; ks < 2; ++ks) {
+          MBAR_WAIT(b_afull + 8 * (2 * ks + up), a_phase, 5, j);           // A planes of this k-step are in TMEM
+          if (ks == 0) {
+            SGP_TL(1, j, 1);
+            if (diag) MBAR_WAIT(b_pifull + 8 * si, pi_phase, 14, j);        // B = our own planes in smem
+            else MBAR_WAIT(b_pjfull + 8 * sj, pj_phase, 6, j);             // B = panel J's planes from the ring
+            SGP_TL(1, j, 2);
+          }
+          tc_fence_after();
+          if (elected) {
+            const uint32_t a0 = tmem + TM_A0 + ks * A_KS_COLS, a1 = a0 + 8, a2 = a0 + 16;   // planes P0, P1, P2
+            const uint32_t b0 = pb + 2 * ks, b1 = b0 + PL, b2 = b0 + 2 * PL;
+            const uint32_t f = ks == 0 ? fresh : 1u;
+            mma_i8_ts(tmem + TM_ACC4, a2, D(b2), ID_UU, f);                // weight 2^32 : P2'P2
+            mma_i8_ts(tmem + TM_ACC3, a2, D(b1), ID_US, f);                // weight 2^24 : P2'P1 + P1'P2
+            mma_i8_ts(tmem + TM_ACC3, a1, D(b2), ID_SU, 1u);
+            mma_i8_ts(tmem + TM_ACC2, a2, D(b0), ID_US, f);                // weight 2^16 : P2'P0 + P0'P2 + P1'P1
+            mma_i8_ts(tmem + TM_ACC2, a0, D(b2), ID_SU, 1u);
+            mma_i8_ts(tmem + TM_ACC2, a1, D(b1), ID_SS, 1u);
+            tc_commit(b_aempty + 8 * (2 * ks + up));                       // this k-step's A columns may be rewritten
+            if (ks == 1) {
+              if (diag) tc_commit(b_piempty + 8 * si);
+              else tc_commit(b_pjempty + 8 * sj);
+            }
+          }
         }
         SGP_TL(1, j, 3);
         if (++si == static_cast<uint32_t>(npi)) { si = 0; pi_phase ^= 1; }
@@ -502,10 +538,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_ring_kernel(const I8P
     // ================= panel sharing through L2 ===============================================================
     const size_t col = static_cast<size_t>(blockIdx.y) * p.nt + tj;          // (slice, tile column)
     uint8_t* ring = p.ring + col * RING_D * SLOT_BYTES;
-    unsigned* ready = p.ready + col;
+    unsigned* ready = p.ready + col * FLAG_STRIDE;
     if (publisher) {
       // ---- diagonal CTA: ship the finished planes of every unit to the ring, then release the ready counter --------
-      const unsigned* cons = p.consumed + col * p.nt + (tj + 1);              // [n_cons] counters of CTAs (tj+1.., tj)
+      const unsigned* cons = p.consumed + (col * p.nt + (tj + 1)) * FLAG_STRIDE;   // [n_cons] counters of CTAs (tj+1.., tj)
       unsigned min_cons = 0;                                                   // units every consumer has copied out
       uint32_t si = 0, pi_phase = 0;
       for (long long u = 0; u < nu; ++u) {
@@ -517,7 +553,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_ring_kernel(const I8P
           unsigned it = 0;
           for (;;) {
             unsigned v = 0xFFFFFFFFu;
-            for (int k = lane; k < n_cons; k += 32) { const unsigned c = ld_relaxed_u32(cons + k); v = c < v ? c : v; }
+            for (int k = lane; k < n_cons; k += 32) { const unsigned c = ld_relaxed_u32(cons + k * FLAG_STRIDE); v = c < v ? c : v; }
             v = __reduce_min_sync(0xffffffffu, v);
             if (v >= static_cast<unsigned>(u - RING_D + 1)) { min_cons = v; break; }
             __nanosleep(64);
@@ -560,7 +596,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_ring_kernel(const I8P
       }
     } else if (!diag) {
       // ---- off-diagonal CTA: copy panel J's planes out of the ring into the B-operand ring ------------------------
-      unsigned* mine = p.consumed + col * p.nt + ti;
+      unsigned* mine = p.consumed + (col * p.nt + ti) * FLAG_STRIDE;
       if (lane == 0) {
         // One thread, two duties, neither may block the other: (a) issue the copy of unit `ni` as soon as its smem slot
         // has drained (Gram MMAs of unit ni - npj) and the publisher's counter covers it; (b) report every copy that has
@@ -576,6 +612,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_ring_kernel(const I8P
         while (nr < nu) {
           bool progressed = false;
           if (nr < ni && mbar_test(b_pjfull + 8 * sr, pr_phase)) {
+            SGP_TL(4, nr, 4);
             ++nr;
             st_relaxed_u32(mine, static_cast<unsigned>(nr));
             if (++sr == npj) { sr = 0; pr_phase ^= 1; }
@@ -583,13 +620,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_ring_kernel(const I8P
           }
           if (ni < nu && ni < nr + npj) {      // slot reuse only after the previous occupant's landing has been REPORTED:
                                                // keeps pj_full at most one phase ahead of the parity tested above
-            if (seen < static_cast<unsigned>(ni + 1)) seen = ld_relaxed_u32(ready);
+            if (seen < static_cast<unsigned>(ni + 1)) { SGP_TL(4, ni, 0); seen = ld_relaxed_u32(ready); SGP_TL(4, ni, 1); }
             if (seen >= static_cast<unsigned>(ni + 1) && (ni < npj || mbar_test(b_pjempty + 8 * sj, pj_phase ^ 1))) {
               // (the planes were acknowledged by L2 before the counter was written and this copy is issued after the
               //  counter was read, also from L2: program order + the control dependency replace an acquire fence)
               SGP_TL(4, ni, 2);
               mbar_expect_tx(b_pjfull + 8 * sj, SLOT_BYTES);
-              bulk_g2s(s_slot + (NPI + sj) * SLOT_BYTES, ring + static_cast<size_t>(ni % RING_D) * SLOT_BYTES, SLOT_BYTES,
+              bulk_g2s(s_slot + sj * SLOT_BYTES, ring + static_cast<size_t>(ni % RING_D) * SLOT_BYTES, SLOT_BYTES,
                        b_pjfull + 8 * sj);
               SGP_TL(4, ni, 3);
               ++ni;
@@ -611,7 +648,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_ring_kernel(const I8P
     const int cq = ew >> 2;             // 0..3: which 32 of the 128 accumulator columns in a flush
     const int L = lq * 32 + lane;       // TMEM lane == active-set row inside the tile
     const uint32_t lane_bits = static_cast<uint32_t>(lq * 32) << 16;
-    const uint32_t q_taddr = tmem + lane_bits + TM_Q0 + grp * UP + ch * 32;
+    const uint32_t q_taddr = tmem + lane_bits + TM_Q0 + ch * 32;
+    const uint32_t a_taddr = tmem + lane_bits + TM_A0 + ch * A_KS_COLS;      // this warp's 32 points = k-step `ch`
     double bsum = 0.0;
     uint32_t flush_idx = 0, q_phase = 0;
     int until_flush = p.flush_units;
@@ -621,7 +659,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_ring_kernel(const I8P
     // exp block
     bool q_ready = false;
     const bool dbg = DBG && (p.dbg_T != nullptr) && blockIdx.x == 0 && blockIdx.y == 0;
-    const int npi_shift = publisher ? 2 : 1;                                     // npi is 4 or 2
+    const int npi_shift = 2;                                                     // npi == 4
     for (long long i = 0; i < nu; ++i) {
       if ((i & 1) == grp) {
         // ---- one distance tile (128 active rows x 64 points) -> three int8 digit planes of unit i ---------------
@@ -642,18 +680,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_ring_kernel(const I8P
           for (int k = 0; k < 32; ++k) p.dbg_T[L * UP + ch * 32 + k] = __uint_as_float(T[k]);
         }
         // kappa = 2^T ; fixed point: (mantissa(kappa*C0 + MAGIC) << 1) has the digit bytes (2 s0 + 128, s1 + 128, s2)
-        // unit i lives in slot i % npi; before overwriting it the Gram MMAs of unit i - npi (and, on a publishing CTA, the
-        // bulk store that shipped it) must have drained: completion (i / npi - 1) of pi_empty[slot]
-        const uint32_t si = static_cast<uint32_t>(i) & static_cast<uint32_t>(npi - 1);
-        const uint32_t pe_bar = b_piempty + 8 * si;
-        const uint32_t pe_phase = static_cast<uint32_t>(((i >> npi_shift) - 1) & 1);
-        bool pe_ready = (i < npi);
         if (diag) {
           const float4* yv = reinterpret_cast<const float4*>(sm_ys + static_cast<int>(i & (YSTAGES - 1)) * UP + ch * 32);
           float bacc = 0.f;
 #pragma unroll
           for (int g = 0; g < 8; ++g) {
-            if (g == 4 && !pe_ready) pe_ready = mbar_test(pe_bar, pe_phase);
             const float4 y4 = yv[g];
             const float e0 = ex2f(__uint_as_float(T[4 * g + 0])), e1 = ex2f(__uint_as_float(T[4 * g + 1])),
                         e2 = ex2f(__uint_as_float(T[4 * g + 2])), e3 = ex2f(__uint_as_float(T[4 * g + 3]));
@@ -665,41 +696,55 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_ring_kernel(const I8P
           bsum += static_cast<double>(bacc);
         } else {
 #pragma unroll
-          for (int k = 0; k < 16; ++k) T[k] = fixed_word(ex2f(__uint_as_float(T[k])));
-          if (!pe_ready) pe_ready = mbar_test(pe_bar, pe_phase);
-#pragma unroll
-          for (int k = 16; k < 32; ++k) T[k] = fixed_word(ex2f(__uint_as_float(T[k])));
+          for (int k = 0; k < 32; ++k) T[k] = fixed_word(ex2f(__uint_as_float(T[k])));
         }
         if (DBG && dbg && i == 0) {
           for (int k = 0; k < 32; ++k) p.dbg_w[L * UP + ch * 32 + k] = T[k] >> 1;     // the fp32 word (sign bit is 0)
         }
         if (tle) SGP_TL(2 + grp, i, 3);
-        if (!pe_ready) MBAR_WAIT(pe_bar, pe_phase, 10, i);
-        if (tle) SGP_TL(2 + grp, i, 4);
-        // byte planes: 4 consecutive points -> one word per digit; 16 points -> one 16-byte store per digit
-        uint8_t* const slot = sm + si * SLOT_BYTES;
+        // byte planes: 4 consecutive points -> one word per digit, 32 points -> 8 words per digit = one k-step of A
+        uint32_t d0[8], d1[8], d2[8];
 #pragma unroll
-        for (int g16 = 0; g16 < 2; ++g16) {
-          uint32_t d0[4], d1[4], d2[4];
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const uint32_t w0 = T[g16 * 16 + g * 4 + 0], w1 = T[g16 * 16 + g * 4 + 1], w2 = T[g16 * 16 + g * 4 + 2],
-                           w3 = T[g16 * 16 + g * 4 + 3];
-            const uint32_t t01 = prmt(w0, w1, 0x5140), t23 = prmt(w2, w3, 0x5140);
-            d0[g] = prmt(t01, t23, 0x5410) ^ 0x80808080u;     // P0 = 2 s0 = byte0 - 128 (two's complement)
-            d1[g] = prmt(t01, t23, 0x7632) ^ 0x80808080u;     // P1 = s1 = byte1 - 128
-            const uint32_t u01 = prmt(w0, w1, 0x0062), u23 = prmt(w2, w3, 0x0062);
-            d2[g] = prmt(u01, u23, 0x5410);                   // P2 = s2 = byte2 (0..255, unsigned operand)
-          }
-          if (g16 == 1) q_ready = mbar_test(b_qfull + 8 * grp, q_phase);     // next tile of this group
-          uint8_t* dst = slot + sw64_off(L, ch * 2 + g16);
-          *reinterpret_cast<uint4*>(dst + 0 * PLANE_BYTES) = make_uint4(d0[0], d0[1], d0[2], d0[3]);
-          *reinterpret_cast<uint4*>(dst + 1 * PLANE_BYTES) = make_uint4(d1[0], d1[1], d1[2], d1[3]);
-          *reinterpret_cast<uint4*>(dst + 2 * PLANE_BYTES) = make_uint4(d2[0], d2[1], d2[2], d2[3]);
+        for (int g = 0; g < 8; ++g) {
+          const uint32_t w0 = T[g * 4 + 0], w1 = T[g * 4 + 1], w2 = T[g * 4 + 2], w3 = T[g * 4 + 3];
+          const uint32_t t01 = prmt(w0, w1, 0x5140), t23 = prmt(w2, w3, 0x5140);
+          d0[g] = prmt(t01, t23, 0x5410) ^ 0x80808080u;     // P0 = 2 s0 = byte0 - 128 (two's complement)
+          d1[g] = prmt(t01, t23, 0x7632) ^ 0x80808080u;     // P1 = s1 = byte1 - 128
+          const uint32_t u01 = prmt(w0, w1, 0x0062), u23 = prmt(w2, w3, 0x0062);
+          d2[g] = prmt(u01, u23, 0x5410);                   // P2 = s2 = byte2 (0..255, unsigned operand)
         }
-        fence_proxy_async();             // generic-proxy plane writes -> visible to the tensor core / bulk copy (async proxy)
+        if (diag) {
+          // the diagonal tile also needs its panel as the B operand (and publishes it): K-major SWIZZLE_64B image in smem,
+          // written BEFORE the wait for the A columns so that pi_full (B side, publisher) is never behind a_full.
+          // unit i lives in slot i % 4; before overwriting it the Gram MMAs of unit i - 4 (and, on a publishing CTA,
+          // the bulk store that shipped it) must have drained: completion (i / 4 - 1) of pi_empty[slot]
+          const uint32_t si = static_cast<uint32_t>(i) & static_cast<uint32_t>(npi - 1);
+          if (i >= npi) MBAR_WAIT(b_piempty + 8 * si, static_cast<uint32_t>(((i >> npi_shift) - 1) & 1), 15, i);
+          uint8_t* const slot = sm + si * SLOT_BYTES;
+#pragma unroll
+          for (int g16 = 0; g16 < 2; ++g16) {
+            uint8_t* dst = slot + sw64_off(L, ch * 2 + g16);
+            *reinterpret_cast<uint4*>(dst + 0 * PLANE_BYTES) = make_uint4(d0[4 * g16], d0[4 * g16 + 1], d0[4 * g16 + 2], d0[4 * g16 + 3]);
+            *reinterpret_cast<uint4*>(dst + 1 * PLANE_BYTES) = make_uint4(d1[4 * g16], d1[4 * g16 + 1], d1[4 * g16 + 2], d1[4 * g16 + 3]);
+            *reinterpret_cast<uint4*>(dst + 2 * PLANE_BYTES) = make_uint4(d2[4 * g16], d2[4 * g16 + 1], d2[4 * g16 + 2], d2[4 * g16 + 3]);
+          }
+          fence_proxy_async();           // generic-proxy plane writes -> visible to the tensor core / bulk copy (async proxy)
+          __syncwarp();
+          if (lane == 0) mbar_arrive(b_pifull + 8 * si);
+        }
+        if (tle) SGP_TL(2 + grp, i, 4);
+        // A operand: straight into tensor memory once the Gram MMAs of the previous unit's k-step `ch` have drained
+        // (barriers are split by unit parity so that a group, which sees only every other unit, never lags a phase)
+        if (i >= 1) MBAR_WAIT(b_aempty + 8 * (2 * ch + (grp ^ 1)), static_cast<uint32_t>(((i - 1) >> 1) & 1), 10, i);
+        tc_fence_after();
+        tmem_st8(a_taddr + 0, d0);
+        tmem_st8(a_taddr + 8, d1);
+        tmem_st8(a_taddr + 16, d2);
+        tmem_wait_st();
+        tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(b_pifull + 8 * si);
+        if (lane == 0) mbar_arrive(b_afull + 8 * (2 * ch + grp));
+        q_ready = mbar_test(b_qfull + 8 * grp, q_phase);     // next tile of this group
         if (tle) SGP_TL(2 + grp, i, 5);
       }
 
@@ -769,7 +814,7 @@ size_t i8_share_bytes(int m_pad, int n_slices) {
 }
 size_t i8_share_flag_bytes(int m_pad, int n_slices) {
   const size_t nt = m_pad / kTile;
-  return (static_cast<size_t>(n_slices) * nt + static_cast<size_t>(n_slices) * nt * nt) * sizeof(unsigned);
+  return (static_cast<size_t>(n_slices) * nt + static_cast<size_t>(n_slices) * nt * nt) * FLAG_STRIDE * sizeof(unsigned);
 }
 
 // Launch plan: whole tile columns per launch, at most `num_sms` CTAs each (every CTA of a launch must be resident).
@@ -813,15 +858,15 @@ cudaError_t launch_gram_i8_ring(const uint8_t* Xt, const float* ys, const uint8_
   if (const char* e = getenv("SGP_I8_TL_U0")) p.tl_u0 = atoll(e);
   if (const char* e = getenv("SGP_I8_TL_SLICE")) p.tl_slice = atoi(e);
   p.dbg_T = dbg_T; p.dbg_w = dbg_w; p.dbg_clk = dbg_clk; p.pm = static_cast<I8PostMortem*>(post_mortem);
-  p.xstages = (p.nchunks == 1) ? 4 : 3;
+  p.xstages = (p.nchunks == 1) ? 8 : 5;
   p.npj = (p.nchunks == 1) ? NPJ_MAX : 3;
   const size_t ring_bytes = static_cast<size_t>(plan.n_slices) * p.nt * RING_D * SLOT_BYTES;
   p.ring = share;
   p.ready = reinterpret_cast<unsigned*>(share + ring_bytes);
-  p.consumed = p.ready + static_cast<size_t>(plan.n_slices) * p.nt;
+  p.consumed = p.ready + static_cast<size_t>(plan.n_slices) * p.nt * FLAG_STRIDE;
   cudaError_t e = cudaMemsetAsync(p.ready, 0, i8_share_flag_bytes(m_pad, plan.n_slices), s);
   if (e != cudaSuccess) return e;
-  const size_t smem = 1024 + (NPI + p.npj) * SLOT_BYTES + p.nchunks * ZPANEL_BYTES + p.xstages * p.nchunks * XIMG_BYTES +
+  const size_t smem = 1024 + (p.npj > NPI_PUB ? p.npj : NPI_PUB) * SLOT_BYTES + p.nchunks * ZPANEL_BYTES + p.xstages * p.nchunks * XIMG_BYTES +
                       YSTAGES * UP * 4 + 4 * 128 * 8 + 512;
   const void* fn = dbg_T ? reinterpret_cast<const void*>(kmn_gram_i8_ring_kernel<true>)
                          : reinterpret_cast<const void*>(kmn_gram_i8_ring_kernel<false>);

@@ -62,7 +62,7 @@ struct Ctx {
   cusolverDnHandle_t solver2 = nullptr;   // bound to tail_stream
   cublasHandle_t blas = nullptr;
   cudaEvent_t tail_fork = nullptr, tail_join = nullptr;
-  DevScratch tail_ws, tail_ws2, predict_ws, cross_ws;
+  DevScratch tail_ws, tail_ws2, predict_ws, cross_ws, bcm_ws;
   bool has_magic_run = false;
   bool tail_fast = false;              // last sgp_magic took the Cholesky path for both matrices
   ncclComm_t comm = nullptr;
@@ -100,6 +100,7 @@ struct Ctx {
   double* dEf = nullptr;         // per-point latent mode of the Laplace approximation (warm start across evaluations)
   long long n_experts = 0, ex_n = 0; int ex_d = 0; int ex_nmax = 0;
   double* dNllPer = nullptr; size_t nll_per_cap = 0;
+  bool bcm_general = false;      // the last sgp_bcm_nll took the global-memory LU path
   void* dNllScratch = nullptr;   // hyper descriptors + totals + flags
   // tail / predict state
   double* dMagicVec = nullptr;   // m
@@ -178,7 +179,7 @@ size_t i8_share_flag_bytes(int m_pad, int n_slices);
 cudaError_t launch_gram_i8_ring(const uint8_t* Xt, const float* ys, const uint8_t* Zt, long long n, int d, int m_pad,
                                 const I8Launch& plan, double* Gpart, double* bpart, double C, uint8_t* share, float* dbg_T,
                                 uint32_t* dbg_w, long long* dbg_clk, void* post_mortem, cudaStream_t s);
-// round-1 kernel (every CTA builds both panels of its tile): the default until the ring kernel beats it
+// round-1 kernel (every CTA builds both panels of its tile; SGP_I8_IMPL=v1): kept as the A/B reference of the ring kernel
 cudaError_t launch_gram_i8(const uint8_t* Xt, const float* ys, const uint8_t* Zt, long long n, int d, int m_pad,
                            int n_slices, double* Gpart, double* bpart, double C, float* dbg_T, uint32_t* dbg_w,
                            long long* dbg_clk, cudaStream_t s);
@@ -190,6 +191,14 @@ cudaError_t launch_bcm_nll(const double* dX, const double* dy, const long long* 
                            const KernelFlat& kf, const double* dBeta, int n_hypers, const int* dKind, const int* dTerm,
                            const int* dDim, const double* dCoef, const double* dValue, int any_ard,
                            double* dPerExpert, double* dTotal, int* dFlags, cudaStream_t s);
+
+// general path (any expert size, LU like the reference): global-memory kernel matrices + cuBLAS batched LU / inverse
+size_t bcm_general_workspace_bytes(long long E, int n_max);
+cudaError_t launch_bcm_nll_general(cublasHandle_t blas, int* blas_status, void* ws, const double* dX, const double* dy,
+                                   const long long* dOff, long long E, int d, int n_max, const KernelFlat& kf,
+                                   const double* dBeta, int n_hypers, const int* dKind, const int* dTerm, const int* dDim,
+                                   const double* dCoef, const double* dValue, int any_ard, double* dPerExpert,
+                                   double* dTotal, int* dFlags, cudaStream_t s);
 
 size_t laplace_smem_bytes(int n_max);
 cudaError_t launch_laplace(const double* dX, const double* dy, double* df, const long long* dOff, long long E, int d,

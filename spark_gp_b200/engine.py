@@ -272,14 +272,19 @@ class ProjectedProcessEngine:
         return T, w
 
     def debug_i8_timeline(self):
-        out = np.zeros((2, 5, 32, 8), dtype=np.int64)
+        out = np.zeros(2560 + 148 * 32, dtype=np.int64)
         self._check(self._lib.sgp_debug_i8_timeline(self._h, N.ptr(out)))
-        return out
+        self.i8_progress = out[2560:].reshape(148, 32)        # [CTA][unit / 128] clock64 of the Gram issuer
+        return out[:2560].reshape(2, 5, 32, 8)
 
     # ---- introspection ---------------------------------------------------------------------------------
     def last_path(self) -> int:
         """SGP_PREC_F64 / SGP_PREC_F64_STRICT / SGP_PREC_I8: the kernel the last statistics launch ran."""
         return int(self._lib.sgp_last_path(self._h))
+
+    def last_bcm_path(self) -> int:
+        """0: on-chip Cholesky objective kernel; 1: global-memory LU path (large experts / not positive definite)."""
+        return int(self._lib.sgp_last_bcm_path(self._h))
 
     def last_tail_path(self) -> int:
         """1: the tail ran on Cholesky factors (PD check included); 0: the reference's dsyevd + LU sequence; -1: never ran."""

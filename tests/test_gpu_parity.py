@@ -697,3 +697,40 @@ def test_auto_budget_checked_over_whole_window(eng):
     assert eng.last_path() == N.SGP_PREC_F64
     eng.set_precision(N.SGP_PREC_AUTO)
     assert np.all(np.isfinite(G))
+
+
+def test_bcm_large_experts_general_path(eng):
+    """datasetSizeForExpert has no upper bound in the reference (GaussianProcessParams.scala:36).  Experts of 400 points
+    exceed the on-chip objective kernel: the evaluation takes the global-memory LU path (the reference's own arithmetic,
+    logDetAndInv.scala:36-63) and must match the oracle like the fast path does."""
+    from spark_gp_b200.hyperopt import pack_experts
+    rng = np.random.default_rng(44)
+    n, d, n_e = 2030, 5, 400
+    X = rng.random((n, d)); y = np.sin(3 * X.sum(1)) + 0.1 * rng.standard_normal(n)
+    mk = lambda: 1.3 * sg.ARDRBFKernel(np.linspace(0.6, 1.8, d)) + 0.4 * sg.RBFKernel(1.5) + sg.const(1e-2) * sg.EyeKernel()
+    mo = lambda: 1.3 * oracle.ARDRBFKernel(np.linspace(0.6, 1.8, d)) + 0.4 * oracle.RBFKernel(1.5) + oracle.const(1e-2) * oracle.EyeKernel()
+    k = mk()
+    experts = oracle.get_expert_labels_and_kernels(X, y, mo, n_e)
+    nll0, g0 = oracle.regression.bcm_objective(experts, k.getHyperparameters())
+    eng.experts_upload(*pack_experts(X, y, n_e))
+    nll, g = eng.bcm_nll(k)
+    assert eng.last_bcm_path() == 1
+    assert abs(nll - nll0) / abs(nll0) < TOL_NLL
+    assert np.abs(g - g0).max() / np.abs(g0).max() < 1e-8
+    # the same path on small experts (forced by a matrix Cholesky cannot factor: duplicated points, no Eye term):
+    # no NotPositiveDefinite error -- the reference's LU carries on; only an exactly singular matrix may fail
+    Xd = np.vstack([X[:60], X[:60]]); yd = np.concatenate([y[:60], y[:60]])
+    eng.experts_upload(*pack_experts(Xd, yd, 120))
+    try:
+        v, gg = eng.bcm_nll(1.0 * sg.ARDRBFKernel(np.full(d, 0.7)))
+        assert np.isfinite(v) and np.all(np.isfinite(gg))
+    except sg.MatrixSingularException:
+        pass
+    assert eng.last_bcm_path() == 1
+    # and the fast path is still the one taken for the default expert size
+    eng.experts_upload(*pack_experts(X, y, 100))
+    nll1, g1 = eng.bcm_nll(k)
+    assert eng.last_bcm_path() == 0
+    ex100 = oracle.get_expert_labels_and_kernels(X, y, mo, 100)
+    nll2, g2 = oracle.regression.bcm_objective(ex100, k.getHyperparameters())
+    assert abs(nll1 - nll2) / abs(nll2) < TOL_NLL

@@ -14,6 +14,7 @@ X = rng.random((n, d), dtype=np.float32)
 y = rng.random(n)
 Z = X[:m].astype(np.float64)
 k = 1 * sg.ARDRBFKernel(np.full(d, np.sqrt(18.0 / d))) + sg.const(1) * sg.EyeKernel()
+import os; os.environ.setdefault("SGP_I8_IMPL", "ring")
 eng = sg.ProjectedProcessEngine(0)
 eng.set_precision(N.SGP_PREC_I8)
 eng.debug_i8_tile()                       # arm
@@ -48,4 +49,19 @@ for cta, cname in enumerate(["publisher (0,0)", "consumer (1,0)"]):
         print(line)
     base = t[t > 0].min()
     print("  window start (clk since first event of either CTA): %d" % (base - tl[tl > 0].min()))
+    g0 = tl[tl > 0].min()
+    for u in (10, 11, 12):
+        print("  unit +%d:" % u, {roles[r]: [int(x - g0) if x > 0 else -1 for x in t[r, u, :7]] for r in range(5)})
+
+P = eng.i8_progress if hasattr(eng, "i8_progress") else None
+if P is not None:
+    g0 = P[P > 0].min()
+    print("per-CTA progress: clk/unit between marks (every 128 units), CTA = slice*36 + tile")
+    for cta in list(range(0, 10)) + [35, 36, 37, 72, 108, 143]:
+        t = P[cta]
+        k = int((t > 0).sum())
+        if k < 2:
+            continue
+        rate = np.diff(t[:k]) / 128.0
+        print("  cta %3d start %8d  rates:" % (cta, t[0] - g0), " ".join("%4.0f" % r for r in rate))
 eng.close()
