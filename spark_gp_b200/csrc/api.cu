@@ -192,8 +192,8 @@ static int launch_stats(Ctx* c, const void* dX, int x_is_f32, const double* dy, 
     }
     SGP_CUDA(c, cudaEventRecord(e1, c->stream));
     for (int i = 0; i < n_plan; ++i) {          // deterministic slice reduction, per launch (its columns, its slices)
-      SGP_CUDA(c, launch_gram_reduce_cols(c->dGb, c->dGb + mm, c->dGpart, c->dBpart, plan[i].n_slices, c->m, c->m_pad,
-                                          plan[i].col_lo * kTile, plan[i].col_hi * kTile, c->stream));
+      SGP_CUDA(c, launch_gram_reduce_upper(c->dGb, c->dGb + mm, c->dGpart, c->dBpart, plan[i].n_slices, c->m, c->m_pad,
+                                           plan[i].col_lo * kTile, plan[i].col_hi * kTile, c->stream));
       c->launches += 1;
     }
     return SGP_OK;

@@ -372,8 +372,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_ring_kernel(const I8P
   double* bp = p.bpart + static_cast<size_t>(blockIdx.y) * p.m_pad;
 
   if (nu == 0) {   // empty slice (every CTA of the slice sees it): the partial tile must still be defined
-    for (int e = tid; e < kTile * kTile; e += NTHREADS)
-      Gp[static_cast<size_t>(ti * kTile + e / kTile) * p.m_pad + tj * kTile + (e % kTile)] = 0.0;
+    for (int e = tid; e < kTile * kTile; e += NTHREADS)      // (transposed storage, see the fold)
+      Gp[static_cast<size_t>(tj * kTile + e / kTile) * p.m_pad + ti * kTile + (e % kTile)] = 0.0;
     if (diag && tid < kTile) bp[ti * kTile + tid] = 0.0;
     return;
   }
@@ -682,18 +682,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_ring_kernel(const I8P
         // kappa = 2^T ; fixed point: (mantissa(kappa*C0 + MAGIC) << 1) has the digit bytes (2 s0 + 128, s1 + 128, s2)
         if (diag) {
           const float4* yv = reinterpret_cast<const float4*>(sm_ys + static_cast<int>(i & (YSTAGES - 1)) * UP + ch * 32);
-          float bacc = 0.f;
+          float b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;        // four independent chains (a single one serialised 32 FFMAs)
 #pragma unroll
           for (int g = 0; g < 8; ++g) {
             const float4 y4 = yv[g];
             const float e0 = ex2f(__uint_as_float(T[4 * g + 0])), e1 = ex2f(__uint_as_float(T[4 * g + 1])),
                         e2 = ex2f(__uint_as_float(T[4 * g + 2])), e3 = ex2f(__uint_as_float(T[4 * g + 3]));
-            bacc = fmaf(e0, y4.x, bacc); bacc = fmaf(e1, y4.y, bacc);
-            bacc = fmaf(e2, y4.z, bacc); bacc = fmaf(e3, y4.w, bacc);
+            b0 = fmaf(e0, y4.x, b0); b1 = fmaf(e1, y4.y, b1);
+            b2 = fmaf(e2, y4.z, b2); b3 = fmaf(e3, y4.w, b3);
             T[4 * g + 0] = fixed_word(e0); T[4 * g + 1] = fixed_word(e1);
             T[4 * g + 2] = fixed_word(e2); T[4 * g + 3] = fixed_word(e3);
           }
-          bsum += static_cast<double>(bacc);
+          bsum += static_cast<double>((b0 + b1) + (b2 + b3));
         } else {
 #pragma unroll
           for (int k = 0; k < 32; ++k) T[k] = fixed_word(ex2f(__uint_as_float(T[k])));
@@ -728,7 +728,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_ring_kernel(const I8P
             *reinterpret_cast<uint4*>(dst + 1 * PLANE_BYTES) = make_uint4(d1[4 * g16], d1[4 * g16 + 1], d1[4 * g16 + 2], d1[4 * g16 + 3]);
             *reinterpret_cast<uint4*>(dst + 2 * PLANE_BYTES) = make_uint4(d2[4 * g16], d2[4 * g16 + 1], d2[4 * g16 + 2], d2[4 * g16 + 3]);
           }
-          fence_proxy_async();           // generic-proxy plane writes -> visible to the tensor core / bulk copy (async proxy)
+          // generic-proxy plane writes -> visible to the tensor core / bulk copy (async proxy).  The fence costs 400-600 clk
+          // of this warp; it sits BEFORE the wait for the A columns, which would idle anyway (tried: after the A store
+          // 1600 clk per unit, deferred into the next tile's TMEM load 2130 -- the Gram issuer then waits for pi_full)
+          fence_proxy_async();
           __syncwarp();
           if (lane == 0) mbar_arrive(b_pifull + 8 * si);
         }
@@ -753,7 +756,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_ring_kernel(const I8P
         // ---- fold the exact int32 accumulators into the fp64 partial tile (all 16 warps) -----------------
         MBAR_WAIT(b_accfull, flush_idx & 1, 11, i);
         tc_fence_after();
-        double* grow = Gp + static_cast<size_t>(ti * kTile + L) * p.m_pad + tj * kTile;
+        // The partial tile is stored TRANSPOSED, i.e. at the mirror position (tile (tj,ti) of the upper block triangle):
+        // a thread owns one ROW of the TMEM tile, so for a fixed column the 32 lanes of a warp write 32 consecutive
+        // doubles of the transposed image -- two full 128-byte lines per instruction instead of 32 half-used sectors 8 KB
+        // apart (the row-major fold cost 30k clk, 7 % of the kernel).  gram_reduce reads the upper triangle.
+        double* gcol = Gp + static_cast<size_t>(tj * kTile) * p.m_pad + ti * kTile + L;
         for (int cg = 0; cg < 2; ++cg) {
           const int col0 = cq * 32 + cg * 16;
           uint32_t a4[16], a3[16], a2[16];
@@ -762,22 +769,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_ring_kernel(const I8P
           tmem_ld16(tmem + lane_bits + TM_ACC2 + col0, a2);
           tmem_wait_ld();
 #pragma unroll
-          for (int k = 0; k < 16; k += 2) {
-            double v0 = 4294967296.0 * static_cast<double>(static_cast<int>(a4[k])) +
-                        16777216.0 * static_cast<double>(static_cast<int>(a3[k])) +
-                        65536.0 * static_cast<double>(static_cast<int>(a2[k]));
-            double v1 = 4294967296.0 * static_cast<double>(static_cast<int>(a4[k + 1])) +
-                        16777216.0 * static_cast<double>(static_cast<int>(a3[k + 1])) +
-                        65536.0 * static_cast<double>(static_cast<int>(a2[k + 1]));
-            v0 *= p.gscale; v1 *= p.gscale;
-            double2* dst = reinterpret_cast<double2*>(grow + col0 + k);
-            if (first_flush) {
-              *dst = make_double2(v0, v1);
-            } else {
-              double2 o = *dst;
-              o.x += v0; o.y += v1;
-              *dst = o;
-            }
+          for (int k = 0; k < 16; ++k) {
+            double v = 4294967296.0 * static_cast<double>(static_cast<int>(a4[k])) +
+                       16777216.0 * static_cast<double>(static_cast<int>(a3[k])) +
+                       65536.0 * static_cast<double>(static_cast<int>(a2[k]));
+            v *= p.gscale;
+            double* dst = gcol + static_cast<size_t>(col0 + k) * p.m_pad;
+            if (first_flush) *dst = v;
+            else *dst += v;
           }
         }
         first_flush = false;

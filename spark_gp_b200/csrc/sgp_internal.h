@@ -140,6 +140,8 @@ int fail(Ctx* c, int code, const std::string& msg);
 cudaError_t launch_gram_f64(const GramParams& p, bool strict_elements, cudaStream_t s);
 cudaError_t launch_gram_reduce(double* G /*m x m*/, double* b, const double* Gpart, const double* bpart,
                                int n_slices, int m, int m_pad, cudaStream_t s);
+cudaError_t launch_gram_reduce_upper(double* G, double* b, const double* Gpart, const double* bpart, int n_slices, int m,
+                                     int m_pad, int row_lo, int row_hi, cudaStream_t s);
 // same, restricted to the G columns / b entries [col_lo, col_hi) (one int8 launch covers whole tile columns)
 cudaError_t launch_gram_reduce_cols(double* G, double* b, const double* Gpart, const double* bpart, int n_slices, int m,
                                     int m_pad, int col_lo, int col_hi, cudaStream_t s);
