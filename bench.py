@@ -416,10 +416,46 @@ def run_ours(args):
             out["allreduce_check"] = rp["allreduce_check"]
         if world == 1 and args.fit:
             out["fit"] = fit_number(sg, args)
+        if world == 1 and args.sweep:
+            out["sweep"] = sweep_number(sg, eng, torch, dev)
         print(json.dumps(out))
     eng.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def sweep_number(sg, eng, torch, dev):
+    """BASELINE configs[4] shape per GPU (12.5M x 8, active=4000): the HBM-bound K_nm sweep -- materialise the fp32 cross
+    kernel of a 262144-point chunk (the full shard's 200 GB of K_nm does not fit in HBM; the chunk buffer is rewritten),
+    CUDA events on the library's stream, vs the measured HBM copy bandwidth."""
+    n, d, m = 262_144, 8, 4000
+    rng = np.random.default_rng(5)
+    X = rng.random((n, d), dtype=np.float32)
+    Z = X[rng.permutation(n)[:m]].astype(np.float64)
+    kernel = 1 * sg.ARDRBFKernel(np.full(d, np.sqrt(18.0 / d))) + sg.const(1) * sg.EyeKernel()
+    eng.begin(kernel, Z)
+    Xd = torch.from_numpy(X).to(dev)
+    Kd = torch.empty((n, m), dtype=torch.float32, device=dev)
+    for _ in range(2):
+        eng.kmn_sweep_device(Xd.data_ptr(), True, n, Kd.data_ptr())
+    eng.sync()
+    reps = 5
+    eng.event_record(2)
+    for _ in range(reps):
+        eng.kmn_sweep_device(Xd.data_ptr(), True, n, Kd.data_ptr())
+    eng.event_record(3)
+    ms = eng.event_elapsed_ms(2, 3) / reps
+    bytes_alg = n * m * 4.0 + n * d * 4.0
+    peak = None
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        pass
+    gbs = bytes_alg / (ms / 1e3) / 1e9
+    return {"workload": "BASELINE configs[4] shard shape: K_nm sweep of %d x %d points against active=%d, fp32 out" % (n, d, m),
+            "ms_per_chunk": ms, "points_per_sec": n / (ms / 1e3), "elements_per_sec": n * m / (ms / 1e3),
+            "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": (gbs / peak) if peak else None,
+                         "algorithmic_bytes": bytes_alg, "note": "bytes = n*m*4 written + n*d*4 read; prep of the fp16 images included"}}
 
 
 def fit_number(sg, args):
@@ -451,6 +487,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fit", dest="fit", action="store_false", help="skip the whole-fit number (N=1 only)")
+    ap.add_argument("--no-sweep", dest="sweep", action="store_false", help="skip the K_nm sweep number (N=1 only)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

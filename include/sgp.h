@@ -124,6 +124,13 @@ int sgp_magic(sgp_ctx* ctx, const double* G_in, const double* b_in,
  * columns, fp64) and of y.  Kept on the device until replaced (the L-BFGS-B loop evaluates the objective many times). */
 int sgp_experts_upload(sgp_ctx* ctx, const double* X, const double* y, const int64_t* offsets, int64_t n_experts, int32_t d);
 
+/* Same result as sgp_experts_upload, but the grouping itself (commons/GaussianProcessCommons.scala:26-31: E =
+ * Math.round(N / datasetSizeForExpert), point i in zipWithIndex order -> expert i % E) runs on the device: the caller
+ * passes the points as they are (row-major, fp32 or fp64) and the library gathers them into the expert-major layout while
+ * the copy streams in -- the reference's zipWithIndex / groupByKey shuffle, here a strided gather.  Latent modes start at 0. */
+int sgp_experts_upload_grouped(sgp_ctx* ctx, const void* X, int32_t x_is_f32, const double* y, int64_t n, int32_t d,
+                               int32_t dataset_size_for_expert);
+
 /* One hyper-parameter, in the order of Kernel.getHyperparameters (depth first, trainable scalar prepended). */
 enum { SGP_HYPER_SCALE = 0, SGP_HYPER_ARD_BETA = 1, SGP_HYPER_RBF_SIGMA = 2 };
 typedef struct {
@@ -194,6 +201,16 @@ int sgp_debug_i8_timeline(sgp_ctx* ctx, long long* out /* 2560 + 148*32: timelin
 /* Evaluate K(X_test, Z) (n x m row-major fp64 out) with the current kernel -- the `crossKernel`
  * contract of kernel/Kernel.scala:69-74 (used by the golden-vector tests). */
 int sgp_cross_kernel(sgp_ctx* ctx, const double* X, int64_t n, double* K_out);
+
+/* ---- K_nm sweep (BASELINE configs[4]: the HBM-bound member of the family) ---------------------------------------
+ * Materialises crossKernel(X) against the active set of the last sgp_stats_begin: K[i][j] = k(x_i, z_j), n x m row-major,
+ * in FP32 (elements good to ~3e-7 relative; sgp_cross_kernel is the fp64 form).  What commons/ActiveSetProvider.scala:90-92
+ * materialises and caches per expert (transposed) and commons/GaussianProcessCommons.scala:121-125 evaluates row by row.
+ * Tensor-core distance contraction + exp + coalesced stores; kernels with one non-Eye term, d <= 32.
+ * _device: X (fp32 / fp64) and K_out are device pointers, asynchronous on the context's stream (bench leg).
+ * SGP_E_RANGE (host form) if coordinates leave the fp16 operand range. */
+int sgp_kmn_sweep(sgp_ctx* ctx, const void* X, int32_t x_is_f32, int64_t n, float* K_out);
+int sgp_kmn_sweep_device(sgp_ctx* ctx, const void* dX, int32_t x_is_f32, int64_t n, float* dK_out);
 
 #ifdef __cplusplus
 }

@@ -22,7 +22,7 @@ EXPORTS = ["sgp_ctx_create", "sgp_ctx_destroy", "sgp_last_error", "sgp_set_preci
            "sgp_stats_accumulate_device", "sgp_stats_finish", "sgp_sync", "sgp_magic", "sgp_predict",
            "sgp_launch_count", "sgp_gram_kernel_time", "sgp_cross_kernel", "sgp_event_record",
            "sgp_event_elapsed_ms", "sgp_debug_i8_tile", "sgp_debug_i8_timeline", "sgp_last_path", "sgp_experts_upload",
-           "sgp_bcm_nll", "sgp_laplace_nll", "sgp_experts_get_f", "sgp_set_magic", "sgp_last_tail_path", "sgp_last_bcm_path"]
+           "sgp_bcm_nll", "sgp_laplace_nll", "sgp_experts_get_f", "sgp_set_magic", "sgp_last_tail_path", "sgp_last_bcm_path", "sgp_experts_upload_grouped", "sgp_kmn_sweep", "sgp_kmn_sweep_device"]
 
 
 class KernelTerm(C.Structure):
@@ -80,6 +80,9 @@ def load() -> C.CDLL:
     lib.sgp_last_tail_path.argtypes = [vp]
     lib.sgp_last_bcm_path.argtypes = [vp]
     lib.sgp_experts_upload.argtypes = [vp, vp, vp, vp, i64, i32]
+    lib.sgp_experts_upload_grouped.argtypes = [vp, vp, i32, vp, i64, i32, i32]
+    lib.sgp_kmn_sweep.argtypes = [vp, vp, i32, i64, vp]
+    lib.sgp_kmn_sweep_device.argtypes = [vp, vp, i32, i64, vp]
     lib.sgp_bcm_nll.argtypes = [vp, C.POINTER(KernelDesc), vp, i32, dp, vp]
     lib.sgp_laplace_nll.argtypes = [vp, C.POINTER(KernelDesc), vp, i32, C.c_double, dp, vp]
     lib.sgp_experts_get_f.argtypes = [vp, vp]

@@ -52,8 +52,7 @@ class GaussianProcessClassifier(GaussianProcessParams):
         eng = ProjectedProcessEngine(self._device)
         groups = group_for_experts(len(X), self._datasetSizeForExpert)
         order = np.concatenate(groups)
-        Xp, yp, off = pack_experts(X, y, self._datasetSizeForExpert)
-        eng.experts_upload(Xp, yp, off)                             # f = zeros per expert (GPCls:53-55)
+        eng.experts_upload_grouped(X, y, self._datasetSizeForExpert)  # grouping on the device; f = zeros per expert (GPCls:53-55)
         memo = {}
 
         def objective(theta):                                       # memoised like DiffFunctionMemoized; f warm-starts

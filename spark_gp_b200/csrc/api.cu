@@ -281,7 +281,7 @@ int sgp_ctx_destroy(sgp_ctx* h) {
   }
   if (c->comm && nccl().ok) nccl().CommDestroy(c->comm);
   if (c->i8_pm_host) cudaFreeHost(c->i8_pm_host);
-  cudaFree(c->tail_ws.p); cudaFree(c->tail_ws2.p); cudaFree(c->predict_ws.p); cudaFree(c->cross_ws.p);
+  cudaFree(c->sweep_ws.p); cudaFree(c->bcm_ws.p); cudaFree(c->tail_ws.p); cudaFree(c->tail_ws2.p); cudaFree(c->predict_ws.p); cudaFree(c->cross_ws.p);
   if (c->tail_fork) cudaEventDestroy(c->tail_fork);
   if (c->tail_join) cudaEventDestroy(c->tail_join);
   if (c->tail_stream) cudaStreamDestroy(c->tail_stream);
@@ -631,6 +631,62 @@ int sgp_experts_upload(sgp_ctx* h, const double* X, const double* y, const int64
   return SGP_OK;
 }
 
+int sgp_experts_upload_grouped(sgp_ctx* h, const void* X, int32_t x_is_f32, const double* y, int64_t n, int32_t d,
+                               int32_t dataset_size_for_expert) {
+  Ctx* c = reinterpret_cast<Ctx*>(h);
+  if (!c) return SGP_E_BADARG;
+  if (!X || !y || n <= 0 || d <= 0 || dataset_size_for_expert <= 0)
+    return fail(c, SGP_E_BADARG, "sgp_experts_upload_grouped: null or empty argument");
+  SGP_CUDA(c, cudaSetDevice(c->device));
+  // GPC:27  numberOfExperts = Math.round(points.count() / datasetSizeForExpert)  (round half up on a positive double)
+  const long long E = static_cast<long long>(std::floor(static_cast<double>(n) / dataset_size_for_expert + 0.5));
+  if (E <= 0) return fail(c, SGP_E_BADARG, "numberOfExperts == 0 (N < datasetSizeForExpert / 2): the reference fails with / by zero");
+  SGP_CUDA(c, cudaStreamSynchronize(c->stream));
+  cudaFree(c->dEx); cudaFree(c->dEy); cudaFree(c->dEoff); cudaFree(c->dEf);
+  c->dEx = c->dEy = c->dEf = nullptr; c->dEoff = nullptr;
+  SGP_CUDA(c, cudaMalloc(&c->dEx, static_cast<size_t>(n) * d * 8));
+  SGP_CUDA(c, cudaMalloc(&c->dEy, static_cast<size_t>(n) * 8));
+  SGP_CUDA(c, cudaMalloc(&c->dEoff, static_cast<size_t>(E + 1) * 8));
+  SGP_CUDA(c, cudaMalloc(&c->dEf, static_cast<size_t>(n) * 8));
+  SGP_CUDA(c, cudaMemsetAsync(c->dEf, 0, static_cast<size_t>(n) * 8, c->stream));   // f = zeros (GPCls:54)
+  SGP_CUDA(c, launch_expert_offsets(c->dEoff, n, E, c->stream));
+  // stream the row-major input through the double-buffered staging area of the statistics path, gather on the device
+  const size_t esz = x_is_f32 ? 4 : 8;
+  const size_t row = static_cast<size_t>(d) * esz;
+  long long chunk = static_cast<long long>((32u << 20) / row);
+  if (chunk < 65536) chunk = 65536;
+  if (chunk > n) chunk = n;
+  if (chunk > c->stage_points || row * chunk > c->stage_bytes) {
+    SGP_CUDA(c, cudaStreamSynchronize(c->copy_stream));
+    for (int i = 0; i < 2; ++i) {
+      cudaFree(c->stageX[i]); cudaFree(c->stageY[i]);
+      c->stageX[i] = nullptr; c->stageY[i] = nullptr;
+      SGP_CUDA(c, cudaMalloc(&c->stageX[i], row * chunk));
+      SGP_CUDA(c, cudaMalloc(&c->stageY[i], static_cast<size_t>(chunk) * 8));
+      SGP_CUDA(c, cudaEventRecord(c->stage_free[i], c->stream));
+    }
+    c->stage_bytes = row * chunk; c->stage_points = chunk;
+  }
+  const char* Xb = static_cast<const char*>(X);
+  int buf = 0;
+  for (long long p0 = 0; p0 < n; p0 += chunk, buf ^= 1) {
+    const long long cn = (n - p0 < chunk) ? (n - p0) : chunk;
+    SGP_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->stage_free[buf], 0));
+    SGP_CUDA(c, cudaMemcpyAsync(c->stageX[buf], Xb + static_cast<size_t>(p0) * row, row * cn, cudaMemcpyHostToDevice, c->copy_stream));
+    SGP_CUDA(c, cudaMemcpyAsync(c->stageY[buf], y + p0, static_cast<size_t>(cn) * 8, cudaMemcpyHostToDevice, c->copy_stream));
+    SGP_CUDA(c, cudaEventRecord(c->stage_ready[buf], c->copy_stream));
+    SGP_CUDA(c, cudaStreamWaitEvent(c->stream, c->stage_ready[buf], 0));
+    SGP_CUDA(c, launch_group_experts(c->dEx, c->dEy, c->stageX[buf], x_is_f32, c->stageY[buf], n, d, E, p0, cn, c->stream));
+    SGP_CUDA(c, cudaEventRecord(c->stage_free[buf], c->stream));
+    c->launches += 1;
+  }
+  SGP_CUDA(c, cudaStreamSynchronize(c->copy_stream));
+  SGP_CUDA(c, cudaStreamSynchronize(c->stream));
+  const long long kq = n / E;
+  c->n_experts = E; c->ex_d = d; c->ex_nmax = static_cast<int>(kq + ((n % E) ? 1 : 0)); c->ex_n = n;
+  return SGP_OK;
+}
+
 namespace {
 struct ObjectiveArgs {          // device-side view of (kernel, hyper-parameter descriptors) for the per-expert objectives
   KernelFlat kf;
@@ -875,6 +931,72 @@ int sgp_event_elapsed_ms(sgp_ctx* h, int a, int b, double* ms) {
   float f = 0.f;
   SGP_CUDA(c, cudaEventElapsedTime(&f, c->user_events[a], c->user_events[b]));
   *ms = f;
+  return SGP_OK;
+}
+
+// One sweep launch over n device-resident points (prep of the fp16 operand images + the sweep kernel).
+static int sweep_device(Ctx* c, const void* dX, int x_is_f32, long long n, float* dK) {
+  const int nch = i8_nchunks(c->d);
+  const size_t xb = i8_points_scratch_bytes(n, nch);
+  const size_t yb = static_cast<size_t>((n + 63) / 64) * 64 * sizeof(float);
+  if (xb > c->i8_xt_bytes) {
+    SGP_CUDA(c, cudaStreamSynchronize(c->stream));
+    cudaFree(c->dI8Xt); c->dI8Xt = nullptr; c->i8_xt_bytes = 0;
+    SGP_CUDA(c, cudaMalloc(&c->dI8Xt, xb));
+    c->i8_xt_bytes = xb;
+  }
+  if (yb > c->i8_ys_bytes) {
+    SGP_CUDA(c, cudaStreamSynchronize(c->stream));
+    cudaFree(c->dI8Ys); c->dI8Ys = nullptr; c->i8_ys_bytes = 0;
+    SGP_CUDA(c, cudaMalloc(&c->dI8Ys, yb));
+    c->i8_ys_bytes = yb;
+  }
+  SGP_CUDA(c, launch_i8_prep_points(c->dI8Xt, c->dI8Ys, dX, x_is_f32, nullptr, n, c->d, c->dI8Scale, c->dI8Centre, c->dI8Flags,
+                                    c->dI8NormSum, nullptr, c->stream));
+  SGP_CUDA(c, launch_kmn_sweep(c->dI8Xt, c->dI8Zt, n, c->d, c->m, c->m_pad, c->num_sms, c->kf.scale[0], dK, c->stream));
+  c->launches += 2;
+  return SGP_OK;
+}
+
+int sgp_kmn_sweep_device(sgp_ctx* h, const void* dX, int32_t x_is_f32, int64_t n, float* dK_out) {
+  Ctx* c = reinterpret_cast<Ctx*>(h);
+  if (!c) return SGP_E_BADARG;
+  if (!c->begun) return fail(c, SGP_E_STATE, "setTrainingVectors method should have been called first");
+  if (n <= 0 || !dX || !dK_out) return fail(c, SGP_E_BADARG, "null argument");
+  if (!c->i8_ok) return fail(c, SGP_E_BADARG, "sgp_kmn_sweep needs a kernel with exactly one non-Eye term and d <= 32");
+  SGP_CUDA(c, cudaSetDevice(c->device));
+  return sweep_device(c, dX, x_is_f32, n, dK_out);
+}
+
+int sgp_kmn_sweep(sgp_ctx* h, const void* X, int32_t x_is_f32, int64_t n, float* K_out) {
+  Ctx* c = reinterpret_cast<Ctx*>(h);
+  if (!c) return SGP_E_BADARG;
+  if (!c->begun) return fail(c, SGP_E_STATE, "setTrainingVectors method should have been called first");
+  if (n <= 0 || !X || !K_out) return fail(c, SGP_E_BADARG, "null argument");
+  if (!c->i8_ok) return fail(c, SGP_E_BADARG, "sgp_kmn_sweep needs a kernel with exactly one non-Eye term and d <= 32");
+  SGP_CUDA(c, cudaSetDevice(c->device));
+  const size_t esz = x_is_f32 ? 4 : 8;
+  const long long chunk = 65536;
+  const long long cn0 = n < chunk ? n : chunk;
+  int rc = ctx_scratch(c, c->sweep_ws, static_cast<size_t>(cn0) * c->d * esz + static_cast<size_t>(cn0) * c->m * sizeof(float));
+  if (rc != SGP_OK) return rc;
+  float* dK = static_cast<float*>(c->sweep_ws.p);
+  void* dX = dK + static_cast<size_t>(cn0) * c->m;
+  for (long long p0 = 0; p0 < n; p0 += chunk) {
+    const long long cn = (n - p0 < chunk) ? (n - p0) : chunk;
+    SGP_CUDA(c, cudaMemcpyAsync(dX, static_cast<const char*>(X) + static_cast<size_t>(p0) * c->d * esz,
+                                static_cast<size_t>(cn) * c->d * esz, cudaMemcpyHostToDevice, c->stream));
+    rc = sweep_device(c, dX, x_is_f32, cn, dK);
+    if (rc != SGP_OK) return rc;
+    SGP_CUDA(c, cudaMemcpyAsync(K_out + static_cast<size_t>(p0) * c->m, dK, static_cast<size_t>(cn) * c->m * sizeof(float),
+                                cudaMemcpyDeviceToHost, c->stream));
+    SGP_CUDA(c, cudaStreamSynchronize(c->stream));
+  }
+  int flags = 0;
+  SGP_CUDA(c, cudaMemcpy(&flags, c->dI8Flags, sizeof(int), cudaMemcpyDeviceToHost));
+  if (flags & 1)
+    return fail(c, SGP_E_RANGE, "scaled coordinates exceed the fp16 operand range of the tensor-core distance contraction; "
+                                "use sgp_cross_kernel");
   return SGP_OK;
 }
 

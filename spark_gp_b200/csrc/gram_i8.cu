@@ -274,7 +274,7 @@ __global__ void prep_points_kernel(uint8_t* __restrict__ Xt, float* __restrict__
       if (norm_sum_call) atomicAdd(norm_sum_call, v2);
     }
   }
-  ys[pt] = valid ? static_cast<float>(y[pt]) : 0.f;
+  ys[pt] = (valid && y) ? static_cast<float>(y[pt]) : 0.f;
   const long long unit = pt / UP;
   const int r = static_cast<int>(pt % UP);
   for (int c = 0; c < nchunks; ++c) {

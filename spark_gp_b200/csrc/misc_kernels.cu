@@ -123,6 +123,34 @@ __global__ void status_to_double_kernel(double* __restrict__ dst, const int* __r
   *dst = v;
 }
 
+// Expert grouping on the device (GPC:26-31): E = Math.round(N / n_e); point i (zipWithIndex order) belongs to expert
+// i % E and is its (i / E)-th point.  With k = N / E and r = N % E, experts < r own k+1 points: expert e starts at
+// e*k + min(e, r).  One thread per (point, feature): a strided gather from the row-major input into the expert-major
+// fp64 layout the objective kernels read.
+__global__ void group_experts_kernel(double* __restrict__ Xe, double* __restrict__ ye, const void* __restrict__ X,
+                                     int x_is_f32, const double* __restrict__ y, long long n, int d, long long E,
+                                     long long p0, long long cn) {
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (idx >= cn * d) return;
+  const long long li = idx / d;                 // point inside this chunk
+  const int k = static_cast<int>(idx % d);
+  const long long i = p0 + li;                  // global point index
+  const long long e = i % E, pos = i / E;
+  const long long kq = n / E, r = n % E;
+  const long long dst = e * kq + (e < r ? e : r) + pos;
+  const double v = x_is_f32 ? static_cast<double>(static_cast<const float*>(X)[li * d + k])
+                            : static_cast<const double*>(X)[li * d + k];
+  Xe[dst * d + k] = v;
+  if (k == 0) ye[dst] = y[li];
+}
+
+__global__ void expert_offsets_kernel(long long* __restrict__ off, long long n, long long E) {
+  const long long e = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (e > E) return;
+  const long long kq = n / E, r = n % E;
+  off[e] = e * kq + (e < r ? e : r);
+}
+
 Scales to_scales(const KernelFlat& kf) {
   Scales s;
   for (int t = 0; t < kMaxTerms; ++t) s.s[t] = kf.scale[t];
@@ -169,6 +197,18 @@ cudaError_t launch_magic_matrix(double* out, const double* invA, const double* i
                                 cudaStream_t s) {
   const size_t n = static_cast<size_t>(m) * m;
   magic_matrix_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(out, invA, invK, wn, n);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_group_experts(double* Xe, double* ye, const void* dX, int x_is_f32, const double* dy, long long n, int d,
+                                 long long E, long long p0, long long cn, cudaStream_t s) {
+  const long long total = cn * d;
+  group_experts_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(Xe, ye, dX, x_is_f32, dy, n, d, E, p0, cn);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_expert_offsets(long long* off, long long n, long long E, cudaStream_t s) {
+  expert_offsets_kernel<<<static_cast<unsigned>((E + 1 + 255) / 256), 256, 0, s>>>(off, n, E);
   return cudaGetLastError();
 }
 

@@ -62,7 +62,7 @@ struct Ctx {
   cusolverDnHandle_t solver2 = nullptr;   // bound to tail_stream
   cublasHandle_t blas = nullptr;
   cudaEvent_t tail_fork = nullptr, tail_join = nullptr;
-  DevScratch tail_ws, tail_ws2, predict_ws, cross_ws, bcm_ws;
+  DevScratch tail_ws, tail_ws2, predict_ws, cross_ws, bcm_ws, sweep_ws;
   bool has_magic_run = false;
   bool tail_fast = false;              // last sgp_magic took the Cholesky path for both matrices
   ncclComm_t comm = nullptr;
@@ -156,6 +156,9 @@ cudaError_t launch_axpby_diag(double* A, const double* K, const double* G, doubl
 cudaError_t launch_set_identity(double* I, int m, cudaStream_t s);
 cudaError_t launch_magic_matrix(double* out, const double* invA, const double* invK, double wn, int m,
                                 cudaStream_t s);
+cudaError_t launch_group_experts(double* Xe, double* ye, const void* dX, int x_is_f32, const double* dy, long long n, int d,
+                                 long long E, long long p0, long long cn, cudaStream_t s);
+cudaError_t launch_expert_offsets(long long* off, long long n, long long E, cudaStream_t s);
 cudaError_t launch_status_to_double(double* dst, const int* flags, int mask, const double* norm_sum, double norm_limit,
                                     cudaStream_t s);
 cudaError_t launch_predict_finish(double* mean, double* var, const double* K /*n x m*/,
@@ -185,6 +188,10 @@ cudaError_t launch_gram_i8_ring(const uint8_t* Xt, const float* ys, const uint8_
 cudaError_t launch_gram_i8(const uint8_t* Xt, const float* ys, const uint8_t* Zt, long long n, int d, int m_pad,
                            int n_slices, double* Gpart, double* bpart, double C, float* dbg_T, uint32_t* dbg_w,
                            long long* dbg_clk, cudaStream_t s);
+
+// K_nm sweep (kmn_sweep.cu): fp32 cross kernel of a block of points, row-major n x m
+cudaError_t launch_kmn_sweep(const uint8_t* Xt, const uint8_t* Zt, long long n, int d, int m, int m_pad, int num_sms, double C,
+                             float* K, cudaStream_t s);
 
 // BCM objective (bcm_nll.cu)
 size_t bcm_nll_smem_bytes(int n_max);

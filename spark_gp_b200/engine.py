@@ -166,6 +166,19 @@ class ProjectedProcessEngine:
         self._check(self._lib.sgp_experts_upload(self._h, N.ptr(X), N.ptr(y), N.ptr(off), len(off) - 1, X.shape[1]))
         self._experts_d = X.shape[1]
 
+    def experts_upload_grouped(self, X, y, dataset_size_for_expert: int):
+        """Groups the points into experts ON THE DEVICE (GPC:26-31: point i -> expert i % E) while they stream in; X may be
+        float32 or float64, row-major as given.  Returns the number of experts."""
+        X = np.asarray(X)
+        if X.dtype != np.float32:
+            X = np.asarray(X, dtype=np.float64)
+        X = np.ascontiguousarray(X)
+        y = np.ascontiguousarray(y, dtype=np.float64)
+        self._check(self._lib.sgp_experts_upload_grouped(self._h, N.ptr(X), int(X.dtype == np.float32), N.ptr(y), len(X),
+                                                         X.shape[1], int(dataset_size_for_expert)))
+        self._experts_d = X.shape[1]
+        return int(np.floor(len(X) / dataset_size_for_expert + 0.5))
+
     def _hyper_array(self, kernel: Kernel, nterms: int):
         hd = kernel.hyper_descriptors()
         arr = (N.Hyper * max(len(hd), 1))()
@@ -263,6 +276,19 @@ class ProjectedProcessEngine:
         K = np.empty((len(X), self.m))
         self._check(self._lib.sgp_cross_kernel(self._h, N.ptr(X), len(X), N.ptr(K)))
         return K
+
+    def kmn_sweep(self, X):
+        """fp32 K[i][j] = k(x_i, z_j) (n x m) through the tensor-core sweep kernel (one non-Eye term, d <= 32)."""
+        X = np.asarray(X)
+        if X.dtype != np.float32:
+            X = np.asarray(X, dtype=np.float64)
+        X = np.ascontiguousarray(X)
+        K = np.empty((len(X), self.m), dtype=np.float32)
+        self._check(self._lib.sgp_kmn_sweep(self._h, N.ptr(X), int(X.dtype == np.float32), len(X), N.ptr(K)))
+        return K
+
+    def kmn_sweep_device(self, x_ptr: int, x_is_f32: bool, n: int, k_ptr: int):
+        self._check(self._lib.sgp_kmn_sweep_device(self._h, C.c_void_p(x_ptr), int(x_is_f32), n, C.c_void_p(k_ptr)))
 
     def debug_i8_tile(self):
         """Arms (first call) / reads back the SGP_PREC_I8 debug dump: (T [128x64] fp32, words [128x64] uint32)."""

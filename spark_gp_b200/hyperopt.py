@@ -59,9 +59,9 @@ class BcmObjective:
 
     def __init__(self, engine: ProjectedProcessEngine, kernel_factory, X, y, dataset_size_for_expert: int):
         self.engine, self.kernel_factory = engine, kernel_factory
-        Xp, yp, off = pack_experts(X, y, dataset_size_for_expert)
-        engine.experts_upload(Xp, yp, off)
-        self.n_experts = len(off) - 1
+        # expert grouping (GPC:26-31) as a strided gather on the device while the points stream in (the host-side
+        # pack_experts below is the same permutation, kept for callers that hold expert-major data and for the tests)
+        self.n_experts = engine.experts_upload_grouped(X, y, dataset_size_for_expert)
         self._memo = {}
         self.evaluations = 0
 

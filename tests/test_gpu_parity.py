@@ -734,3 +734,44 @@ def test_bcm_large_experts_general_path(eng):
     ex100 = oracle.get_expert_labels_and_kernels(X, y, mo, 100)
     nll2, g2 = oracle.regression.bcm_objective(ex100, k.getHyperparameters())
     assert abs(nll1 - nll2) / abs(nll2) < TOL_NLL
+
+
+def test_device_side_expert_grouping_matches_host_packing(eng):
+    """sgp_experts_upload_grouped (GPC:26-31 as a strided gather on the device) must reproduce the host-side expert-major
+    packing exactly: the BCM objective is bit-identical, for fp64 and fp32 inputs, with and without a remainder (N % E)."""
+    from spark_gp_b200.hyperopt import pack_experts
+    rng = np.random.default_rng(77)
+    k = 1.3 * sg.ARDRBFKernel(np.array([1.1, 0.7, 1.9])) + sg.const(1e-2) * sg.EyeKernel()
+    for n in (1200, 1237):
+        X = rng.random((n, 3)); y = rng.standard_normal(n)
+        eng.experts_upload(*pack_experts(X, y, 100))
+        v0, g0 = eng.bcm_nll(k)
+        E = eng.experts_upload_grouped(X, y, 100)
+        assert E == int(np.floor(n / 100 + 0.5))
+        v1, g1 = eng.bcm_nll(k)
+        assert v0 == v1 and np.array_equal(g0, g1)
+        X32 = X.astype(np.float32)
+        eng.experts_upload(*pack_experts(X32.astype(np.float64), y, 100))
+        v2, g2 = eng.bcm_nll(k)
+        eng.experts_upload_grouped(X32, y, 100)
+        v3, g3 = eng.bcm_nll(k)
+        assert v2 == v3 and np.array_equal(g2, g3)
+
+
+@pytest.mark.parametrize("n,d,m", [(5000, 8, 4000), (70001, 16, 1000), (3000, 32, 200), (130, 3, 129)])
+def test_kmn_sweep_vs_fp64_cross_kernel(eng, n, d, m):
+    """K_nm sweep (fp32, tensor-core distances) against the fp64 cross kernel of the same context, which the reference's
+    RBF goldens pin (test_rbf_*): element-wise <= 1e-5 relative to the kernel scale (north-star tolerance), measured ~3e-7."""
+    rng = np.random.default_rng(n + d)
+    X = rng.random((n, d), dtype=np.float32)
+    Z = X[rng.permutation(n)[:min(m, n)]].astype(np.float64)
+    if len(Z) < m:
+        Z = np.vstack([Z, rng.random((m - len(Z), d))])
+    k = 2.5 * sg.ARDRBFKernel(np.full(d, np.sqrt(18.0 / d))) + sg.const(1) * sg.EyeKernel()
+    eng.set_precision(N.SGP_PREC_AUTO)
+    eng.begin(k, Z)
+    K32 = eng.kmn_sweep(X)
+    K64 = eng.cross_kernel(X.astype(np.float64))
+    err = float(np.abs(K32 - K64).max() / 2.5)
+    print("sweep n=%d d=%d m=%d: max |dK| / C = %.2e" % (n, d, m, err))
+    assert K32.shape == (n, m) and err < 1e-5
