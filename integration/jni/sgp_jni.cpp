@@ -6,18 +6,22 @@
 #if __has_include(<jni.h>)
 #include <jni.h>
 
+#include <string>
 #include <vector>
 
 #include "../../include/sgp.h"
 
 namespace {
+// Every failure surfaces as ONE top-level exception class with a (String) constructor,
+// org.apache.spark.ml.commons.SgpNativeException, whose message starts with "SGP<code>: ".  The Scala shim
+// (NativeProjectedProcess.rethrow) turns the code back into the reference's exception types -- NotPositiveDefiniteException
+// is an inner class of the trait ProjectedGaussianProcessHelper (PGPH:9-11) and cannot be constructed from JNI with
+// ThrowNew (no (String) constructor, needs the outer instance).
 void throw_for(JNIEnv* env, sgp_ctx* ctx, int rc) {
-  const char* cls = "java/lang/RuntimeException";
-  if (rc == SGP_E_NOT_PD) cls = "org/apache/spark/ml/commons/ProjectedGaussianProcessHelper$NotPositiveDefiniteException";
-  else if (rc == SGP_E_BADARG) cls = "java/lang/IllegalArgumentException";
-  else if (rc == SGP_E_STATE) cls = "org/apache/spark/ml/commons/kernel/TrainingVectorsNotInitializedException";
-  else if (rc == SGP_E_SINGULAR) cls = "breeze/linalg/MatrixSingularException";
-  env->ThrowNew(env->FindClass(cls), sgp_last_error(ctx));
+  std::string msg = "SGP" + std::to_string(rc) + ": " + sgp_last_error(ctx);
+  jclass cls = env->FindClass("org/apache/spark/ml/commons/SgpNativeException");
+  if (cls == nullptr) { env->ExceptionClear(); cls = env->FindClass("java/lang/RuntimeException"); }
+  env->ThrowNew(cls, msg.c_str());
 }
 }  // namespace
 
@@ -65,11 +69,13 @@ JNIEXPORT void JNICALL Java_org_apache_spark_ml_commons_NativeProjectedProcess_b
 JNIEXPORT void JNICALL Java_org_apache_spark_ml_commons_NativeProjectedProcess_accumulate(
     JNIEnv* env, jclass, jlong h, jdoubleArray X, jdoubleArray y, jlong n) {
   sgp_ctx* ctx = reinterpret_cast<sgp_ctx*>(h);
-  jdouble* x = static_cast<jdouble*>(env->GetPrimitiveArrayCritical(X, nullptr));
-  jdouble* yy = static_cast<jdouble*>(env->GetPrimitiveArrayCritical(y, nullptr));
+  // NOT Get/ReleasePrimitiveArrayCritical: sgp_stats_accumulate allocates device memory, synchronises streams and does
+  // blocking host->device copies -- none of which is allowed inside a JNI critical region (it can stall GC for the JVM)
+  jdouble* x = env->GetDoubleArrayElements(X, nullptr);
+  jdouble* yy = env->GetDoubleArrayElements(y, nullptr);
   const int rc = sgp_stats_accumulate(ctx, x, /*x_is_f32=*/0, yy, n);   // returns after the last H2D copy
-  env->ReleasePrimitiveArrayCritical(y, yy, JNI_ABORT);
-  env->ReleasePrimitiveArrayCritical(X, x, JNI_ABORT);
+  env->ReleaseDoubleArrayElements(y, yy, JNI_ABORT);
+  env->ReleaseDoubleArrayElements(X, x, JNI_ABORT);
   if (rc != SGP_OK) throw_for(env, ctx, rc);
 }
 

@@ -6,6 +6,11 @@ import org.apache.spark.ml.linalg.Vector
 import org.apache.spark.rdd.RDD
 
 /** JNI binding of libsgp.so (include/sgp.h).  One native context per executor task; device = partitionId % nGPUs. */
+/** What the JNI glue throws for every non-zero status of the C-ABI: message = "SGP<code>: <sgp_last_error>". */
+class SgpNativeException(message: String) extends RuntimeException(message) {
+  def code: Int = message.drop(3).takeWhile(_.isDigit).toInt
+}
+
 private[ml] object NativeProjectedProcess {
   System.loadLibrary("sgp_jni")
   @native def create(device: Int): Long
@@ -70,6 +75,19 @@ private[ml] object NativeProjectedProcess {
 /** Drop-in for ProjectedGaussianProcessHelper (commons/ProjectedGaussianProcessHelper.scala): same two methods,
   * same return types; mix this trait into GaussianProcessCommons instead of the original. */
 private[ml] trait NativeProjectedGaussianProcessHelper extends ProjectedGaussianProcessHelper {
+  /** Status codes of include/sgp.h back to the reference's exception types (the inner class NotPositiveDefiniteException,
+    * PGPH:9-11, needs this trait instance as its outer object, which is why the mapping lives here and not in the JNI). */
+  protected def rethrow[T](body: => T): T =
+    try body catch {
+      case e: SgpNativeException => e.code match {
+        case 3 => throw new NotPositiveDefiniteException                                           // SGP_E_NOT_PD
+        case 1 => throw new IllegalArgumentException(e.getMessage)                                  // SGP_E_BADARG
+        case 5 => throw new org.apache.spark.ml.commons.kernel.TrainingVectorsNotInitializedException  // SGP_E_STATE
+        case 6 => throw new breeze.linalg.MatrixSingularException(e.getMessage)                     // SGP_E_SINGULAR
+        case _ => throw e
+      }
+    }
+
   import NativeProjectedProcess._
 
   def nGPUs: Int = 8
@@ -110,7 +128,7 @@ private[ml] trait NativeProjectedGaussianProcessHelper extends ProjectedGaussian
       begin(ctx, terms.map(_._1).toArray, terms.map(_._2).toArray, terms.map(_._3).toArray,
         terms.flatMap(_._4).toArray, activeSet.flatMap(_.toArray), m, d)
       val mv = new Array[Double](m); val mm = new Array[Double](m * m)
-      magic(ctx, matrixKmnKnm.toArray, vectorKmny.toArray, mv, mm)   // throws NotPositiveDefiniteException like PGPH:62-65
+      rethrow(magic(ctx, matrixKmnKnm.toArray, vectorKmny.toArray, mv, mm))   // NotPositiveDefiniteException like PGPH:62-65
       (new BDV(mv), new BDM(m, m, mm))
     } finally destroy(ctx)
   }
