@@ -185,20 +185,9 @@ static int launch_stats(Ctx* c, const void* dX, int x_is_f32, const double* dy, 
   }
   if (use_i8) {
     for (int i = 0; i < n_plan; ++i) {
-      cudaError_t le = launch_gram_i8_ring(c->dI8Xt, c->dI8Ys, c->dI8Zt, n, c->d, c->m_pad, plan[i], c->dGpart, c->dBpart,
-                                           c->kf.scale[0], static_cast<uint8_t*>(c->i8_share.p), c->dbgT, c->dbgW, c->dbgClk,
-                                           c->i8_pm_dev, c->stream);
-      if (le == cudaErrorCooperativeLaunchTooLarge && plan[i].shared) {
-        // the helper CTA needs every SM of a B200; if some are unavailable fall back to column mode (tiles only)
-        (void)cudaGetLastError();
-        plan[i].shared = 0;
-        plan[i].n_slices = c->num_sms / plan[i].tiles > 0 ? c->num_sms / plan[i].tiles : 1;
-        if (plan[i].n_slices > (n + 63) / 64) plan[i].n_slices = static_cast<int>((n + 63) / 64);
-        le = launch_gram_i8_ring(c->dI8Xt, c->dI8Ys, c->dI8Zt, n, c->d, c->m_pad, plan[i], c->dGpart, c->dBpart,
+      SGP_CUDA(c, launch_gram_i8_ring(c->dI8Xt, c->dI8Ys, c->dI8Zt, n, c->d, c->m_pad, plan[i], c->dGpart, c->dBpart,
                                  c->kf.scale[0], static_cast<uint8_t*>(c->i8_share.p), c->dbgT, c->dbgW, c->dbgClk,
-                                 c->i8_pm_dev, c->stream);
-      }
-      SGP_CUDA(c, le);
+                                 c->i8_pm_dev, c->stream));
       c->launches += 1;
     }
     SGP_CUDA(c, cudaEventRecord(e1, c->stream));

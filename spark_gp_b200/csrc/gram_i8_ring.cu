@@ -91,7 +91,7 @@ constexpr int NPJ_MAX = 5;              // panel-J ring depth (off-diagonal CTAs
 // publisher -> (PUB_LAG stores in flight) -> ready counter -> consumer's copy lands -> consumed counter -> publisher's
 // back-pressure poll, every hop of which is ~1 unit period: with 16 slots the loop lag (6 + 1 + 2 + 5 + polls) was the
 // ring depth itself and the whole column throttled to 3500 clk per unit (profiles/r02_i8_tuning_log.md).
-constexpr int RING_D = 64;
+constexpr int RING_D = 32;
 constexpr int FLAG_STRIDE = 32;         // every counter owns a 128-byte line: 28 publishers + 112 pollers on ONE line (all the
                                         // `ready` words of m = 1000 fit in 128 bytes) serialised at that L2 bank
 constexpr int PUB_LAG = 4;              // bulk stores the publisher keeps in flight before it publishes a unit
@@ -263,33 +263,30 @@ struct I8Params {
   long long n_units;
   int nchunks;          // 64-column K chunks of the distance contraction (1 or 2)
   int xstages;          // operand ring depth
-  int npj;              // panel-B ring depth (<= NPJ_MAX)
+  int npj;              // panel-J ring depth (<= NPJ_MAX)
   int ksteps_last;      // 16-column k-steps used in the last chunk
   int m_pad, nt, n_slices;
-  int col_lo;           // first tile column of this launch (tiles (I,J), I >= J >= col_lo, whole columns)
-  int shared;           // 1: single launch, shared publishing + one helper CTA per slice (blockIdx.x == n_tiles); 0: column mode
-  int n_tiles;          // tile CTAs per slice in this launch
+  int col_lo;           // first tile column of this launch (whole columns per launch: tiles (I,J), I >= J >= col_lo)
   int flush_units;      // fold int32 accumulators into fp64 every this many units (<= 400)
   double* Gpart;        // [n_slices][m_pad*m_pad]
   double* bpart;        // [n_slices][m_pad]
   double gscale;        // C^2 / (4 C0^2)
   double bscale;        // C
-  uint8_t* ring;        // [n_slices][nt][RING_D][SLOT_BYTES]  published digit planes of every panel (L2 resident)
-  unsigned* ready;      // [n_slices][nt][RING_D] x FLAG_STRIDE: slot s of panel P holds unit ready-1 (0: nothing yet)
-  unsigned* consumed;   // [n_slices][nt][nt] x FLAG_STRIDE: units of panel P the CTA with A-panel a has copied out, at [P][a]
-  float* dbg_T;         // optional [128*64] : T of the first distance tile of CTA 0
+  uint8_t* ring;        // [n_slices][nt][RING_D][SLOT_BYTES]  published digit planes (L2 resident)
+  unsigned* ready;      // [n_slices][nt]       units published by the diagonal CTA of column J
+  unsigned* consumed;   // [n_slices][nt][nt]   units consumer (I,J) has finished copying out of the ring, at [J][I]
+  float* dbg_T;         // optional [128*64] : T of the first distance tile of CTA (0,0)
   uint32_t* dbg_w;      // optional [128*64] : fixed-point words of the same tile
   I8PostMortem* pm;     // host-mapped post-mortem record (first stuck wait), or null
-  int tl_slice;         // point slice whose CTAs tl_cta0 / tl_cta1 record the timeline
-  int tl_cta0, tl_cta1;
+  int tl_slice;         // point slice whose CTAs (0,0) and (1,0) record the timeline
   long long tl_u0;      // first unit of the timeline window
-  long long* dbg_clk;   // optional [2 CTAs][5 roles][32 units][8 events] clock64, then [148][32] progress marks
+  long long* dbg_clk;   // optional [2 CTAs: (0,0) publisher, (1,0) consumer][5 roles][32 units: 64..95][8 events] clock64
 };
 
 // in-kernel timeline (debug instantiation only): role 0 distance issuer, 1 Gram issuer, 2/3 epilogue group 0/1, 4 sharing warp
 #define SGP_TL(role, unit, ev)                                                                              \
   do {                                                                                                      \
-    if (DBG && tl_cta >= 0 && (unit) >= p.tl_u0 && (unit) < p.tl_u0 + 32 && tl_lane)                        \
+    if (DBG && tl_cta >= 0 && (unit) >= p.tl_u0 && (unit) < p.tl_u0 + 32 && lane == 0)                      \
       p.dbg_clk[(((tl_cta * 5) + (role)) * 32 + static_cast<int>((unit) - p.tl_u0)) * 8 + (ev)] = clock64(); \
   } while (0)
 
@@ -303,6 +300,14 @@ __device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
   asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ void st_relaxed_u32(unsigned* p, unsigned v) {
   asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -312,39 +317,23 @@ __device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void bulk_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
-template <int N>
-__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 // Bounded global spin (a protocol bug must not hang the box): post-mortem + trap after ~1 s without progress.
-__device__ __forceinline__ void spin_guard(long long t0, unsigned& it, I8PostMortem* pm, int code, long long unit, unsigned a,
+__device__ __forceinline__ void spin_guard(long long& t0, unsigned& it, I8PostMortem* pm, int code, long long unit, unsigned a,
                                            unsigned b) {
   if ((++it & 0x3FFu) == 0 && clock64() - t0 > 2000000000LL) i8_die(pm, code, unit, a, b);
 }
 
-// Who builds, who publishes, who receives.  The CTA of tile (I, J), I >= J, always builds panel I (A operand, tensor memory)
-// and receives panel J.
-//   column mode : the diagonal CTA (J,J) publishes panel J itself, every unit, and uses its own smem copy as B operand.  Its
-//                 epilogue (exp + digits + y-path + smem copy + proxy fence) then paces the whole column: ~3090 clk per tile
-//                 against ~1980 for the consumers (profiles/r02_i8_tuning_log.md, variant 26).
-//   shared mode : panel P >= 1 is built by P+1 CTAs -- (P,0) .. (P,P-1) and the diagonal (P,P) -- which take turns publishing it
-//                 (unit u by the CTA of rank u mod (P+1); rank of (P,J) is J); the diagonal CTA receives the other holders'
-//                 units through the ring like everybody else and uses its own smem copy only for the units it published.
-//                 Panel 0 has no second builder: ONE extra CTA per slice, the helper (blockIdx.x == n_tiles), builds and
-//                 publishes it and does nothing else (no Gram MMAs), so (0,0) is a plain consumer too.  Dependencies are
-//                 acyclic (a holder of panel P depends on panels < P only; the helper on nobody) -- the cyclic variant
-//                 (balanced orientation, variant 27) was latency-bound at 3500 clk per unit.
 template <bool DBG>
 __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_ring_kernel(const I8Params p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* sm = smem_raw + (base - raw);
-  // carve-up (all operand tiles 1024-byte aligned).  max(4, npj + 2) plane slots: a CTA that receives panel b keeps it in
-  // slots [0, npj) and, if it is one of the holders publishing panel a, stages its own planes in slots [npj, npj + 2); a
-  // self-mode diagonal CTA (no ring copy) keeps its own panel in slots [0, 4).  (s_own is set below, once the mode is known.)
-  const uint32_t s_slot = base;
-  const uint32_t own_extra = p.shared ? 2u : 0u;
-  const uint32_t n_slots = static_cast<uint32_t>(p.npj + own_extra > NPI_PUB ? p.npj + own_extra : NPI_PUB);
-  const uint32_t s_zt = s_slot + n_slots * SLOT_BYTES;                    // [nchunks][16384]          active tile a, fp16
+  // carve-up (all operand tiles 1024-byte aligned)
+  const uint32_t s_slot = base;                                           // [NSLOTS][3 planes][8192]  int8 digit planes
+  // (slots: a diagonal CTA keeps its own panel I here -- 4 slots, B operand + publishing; an off-diagonal CTA keeps panel J
+  //  here -- npj slots; panel I of an off-diagonal CTA lives only in tensor memory)
+  const uint32_t s_zt = s_slot + (p.npj > NPI_PUB ? p.npj : NPI_PUB) * SLOT_BYTES;   // [nchunks][16384]  active tile I, fp16
   const uint32_t s_xs = s_zt + p.nchunks * ZPANEL_BYTES;                  // [xstages][nchunks][8192]  point images, fp16
   const uint32_t s_ys = s_xs + p.xstages * p.nchunks * XIMG_BYTES;        // [YSTAGES][64] float
   const uint32_t s_bred = s_ys + YSTAGES * UP * 4;                        // [4][128] double
@@ -359,37 +348,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_ring_kernel(const I8P
   volatile uint32_t* sm_tmem = reinterpret_cast<volatile uint32_t*>(sm + (s_tmem - base));
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int nt = p.nt;
 
-  // ---- which tile, which sharing duties --------------------------------------------------------------------------------
-  const bool helper = p.shared && static_cast<int>(blockIdx.x) == p.n_tiles;
-  int ti = 0, tj = 0;
-  if (!helper) {
+  int ti, tj;
+  {
     int t = blockIdx.x;
     tj = p.col_lo;
-    while (t >= nt - tj) { t -= nt - tj; ++tj; }
+    while (t >= p.nt - tj) { t -= p.nt - tj; ++tj; }
     ti = tj + t;
   }
-  const bool diag = !helper && (ti == tj);
-  const int pa = ti;                      // panel built here (A operand; the helper builds panel 0)
-  const int pb = tj;                      // panel used as B operand
-  // pub_mode 0: we do not publish.  1 (self, column mode): diagonal CTA -- publishes every unit (if anybody reads it) and uses
-  // its own smem copy as the B operand.  2 (shared): holder of panel pa >= 1 -- publishes units u = rank mod (pa + 1); the
-  // diagonal holder uses its own copy as B for exactly those units.  3: helper -- publishes every unit of panel 0, no Gram.
-  const int pub_mode = helper ? 3 : (p.shared ? (pa >= 1 ? 2 : 0) : (diag ? 1 : 0));
-  const int pub_h = (pub_mode == 2) ? pa + 1 : 1, pub_r = (pub_mode == 2) ? pb : 0;
-  const bool own_b_units = (pub_mode == 2) && diag;         // B operand of our own published units = our smem copy
-  const bool b_from_ring = !helper && !(pub_mode == 1);
-  const int npi = (pub_mode == 1 || pub_mode == 3) ? NPI_PUB : 2;
-  const uint32_t s_own = (pub_mode == 1 || pub_mode == 3) ? s_slot : s_slot + static_cast<uint32_t>(p.npj) * SLOT_BYTES;
-  // consumers of panel pa (CTAs whose B operand it is), identified by THEIR A panel a: tiles (a, pa), a > pa, and -- in
-  // shared mode -- the diagonal CTA (pa, pa) itself
-  const int cons_lo = p.shared ? pa : pa + 1;
-  const int n_cons = pub_mode ? nt - cons_lo : 0;
-  const bool publishes = pub_mode != 0 && n_cons > 0;
-  const int tl_cta = (DBG && p.dbg_clk != nullptr && static_cast<int>(blockIdx.y) == p.tl_slice && p.col_lo == 0)
-                         ? (static_cast<int>(blockIdx.x) == p.tl_cta0 ? 0 : (static_cast<int>(blockIdx.x) == p.tl_cta1 ? 1 : -1)) : -1;
-  const bool tl_lane = lane == 0;
+  const int tl_cta = (DBG && p.dbg_clk != nullptr && static_cast<int>(blockIdx.y) == p.tl_slice && blockIdx.x < 2 && p.col_lo == 0) ? static_cast<int>(blockIdx.x) : -1;
+  const bool diag = (ti == tj);
+  const int n_cons = diag ? (p.nt - 1 - tj) : 0;     // CTAs (I, tj), I > tj, of this slice that read the panel we publish
+  const bool publisher = n_cons > 0;
+  const int npi = NPI_PUB;                        // panel-I smem slots (diagonal CTAs only)
 
   const long long ups = (p.n_units + p.n_slices - 1) / p.n_slices;
   const long long u_lo = ups * blockIdx.y;
@@ -399,20 +370,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_ring_kernel(const I8P
 
   double* Gp = p.Gpart + static_cast<size_t>(blockIdx.y) * p.m_pad * p.m_pad;
   double* bp = p.bpart + static_cast<size_t>(blockIdx.y) * p.m_pad;
-  // The partial tile D[r][c] = G[pa*128 + r][pb*128 + c] always lands in the UPPER block triangle of the partial matrix
-  // (gram_reduce_upper reads that).  pa >= pb: stored transposed, at [pb*128 + c][pa*128 + r] -- a thread owns one row r of the
-  // TMEM tile, so for a fixed column the 32 lanes write 32 consecutive doubles (two full lines per instruction).  pa < pb
-  // (balanced mode only): stored as is, at [pa*128 + r][pb*128 + c].
-  const bool out_t = true;                 // pa >= pb always (kept general: the fold below handles both layouts)
-  const size_t out_lane_stride = out_t ? 1 : static_cast<size_t>(p.m_pad);
-  const size_t out_col_stride = out_t ? static_cast<size_t>(p.m_pad) : 1;
-  double* const out_base = out_t ? Gp + static_cast<size_t>(pb * kTile) * p.m_pad + pa * kTile
-                                 : Gp + static_cast<size_t>(pa * kTile) * p.m_pad + pb * kTile;
 
   if (nu == 0) {   // empty slice (every CTA of the slice sees it): the partial tile must still be defined
-    if (helper) return;
-    for (int e = tid; e < kTile * kTile; e += NTHREADS)
-      out_base[static_cast<size_t>(e / kTile) * p.m_pad + (e % kTile)] = 0.0;
+    for (int e = tid; e < kTile * kTile; e += NTHREADS)      // (transposed storage, see the fold)
+      Gp[static_cast<size_t>(tj * kTile + e / kTile) * p.m_pad + ti * kTile + (e % kTile)] = 0.0;
     if (diag && tid < kTile) bp[ti * kTile + tid] = 0.0;
     return;
   }
@@ -423,9 +384,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_ring_kernel(const I8P
     for (int i = 0; i < 2; ++i) { mbar_init(b_qfull + 8 * i, 1); mbar_init(b_qempty + 8 * i, EPI_WARPS / 2); }
     for (int i = 0; i < NPI_PUB; ++i) {
       mbar_init(b_pifull + 8 * i, EPI_WARPS / 2);
-      // slot free again: self mode = Gram MMAs drained (+ the bulk store that ships it, if anybody reads it);
-      // shared mode = the bulk store has read it
-      mbar_init(b_piempty + 8 * i, ((pub_mode == 1 && publishes) || own_b_units) ? 2 : 1);
+      mbar_init(b_piempty + 8 * i, publisher ? 2 : 1);      // Gram MMAs drained (+ the bulk store that ships the slot)
     }
     for (int i = 0; i < NPJ_MAX; ++i) { mbar_init(b_pjfull + 8 * i, 1); mbar_init(b_pjempty + 8 * i, 1); }
     mbar_init(b_accfull, 1); mbar_init(b_accempty, EPI_WARPS); mbar_init(b_zfull, 1);
@@ -445,7 +404,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_ring_kernel(const I8P
     // ================= producer: bulk copies of the fp16 operand images =================================
     if (lane == 0) {
       mbar_expect_tx(b_zfull, static_cast<uint32_t>(p.nchunks * ZPANEL_BYTES));
-      bulk_g2s(s_zt, p.Zt + static_cast<size_t>(pa) * p.nchunks * ZPANEL_BYTES,
+      bulk_g2s(s_zt, p.Zt + static_cast<size_t>(ti) * p.nchunks * ZPANEL_BYTES,
                static_cast<uint32_t>(p.nchunks * ZPANEL_BYTES), b_zfull);
       const uint32_t xbytes = static_cast<uint32_t>(p.nchunks * XIMG_BYTES);
       uint32_t s = 0, e_phase = 1;      // parity of the x_empty completion to wait for (first lap: none)
@@ -463,8 +422,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_ring_kernel(const I8P
         if (++s == static_cast<uint32_t>(p.xstages)) { s = 0; e_phase ^= 1; }
       }
     }
-  } else if (warp == 1 || (warp == 2 && !helper)) {
-    // ================= MMA issuers: warp 1 = distance tiles, warp 2 = Gram blocks (not on the helper CTA) =================
+  } else if (warp == 1 || warp == 2) {
+    // ================= MMA issuers: warp 1 = distance tiles, warp 2 = Gram blocks ==========================
     // A whole warp runs each role (warp-uniform control flow keeps the 64-bit UMMA descriptors in uniform registers);
     // one elected lane issues the tcgen05 instructions (round-1 measurements: a divergent single thread is issue-bound at
     // 155 clk per MMA; one warp issuing both streams serialises the CTA).
@@ -478,7 +437,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_ring_kernel(const I8P
     auto lo_of = [](uint32_t addr) { return ((addr & 0x3FFFFu) >> 4) | (1u << 16); };
 
     if (warp == 1) {
-      // ---------------- distance tile of panel a: T[128 active x 64 points] per unit ---------------------------------
+      // ---------------- distance tile of panel I: T[128 active x 64 points] per unit ---------------------------------
       auto D = [](uint32_t lo) { return (static_cast<uint64_t>(DESC_HI128) << 32) | lo; };
       constexpr uint32_t SL = ZPANEL_BYTES >> 4;
       const uint32_t zt_lo = lo_of(s_zt), xs_lo = lo_of(s_xs);
@@ -517,11 +476,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_ring_kernel(const I8P
       }
     } else {
       // ---------------- Gram blocks: 12 kind::i8 MMAs per unit into the three int32 accumulators ----------------------
-      // A = panel a's digit planes in tensor memory, B = panel b's planes in shared memory (ring copy; own copy in self mode)
       auto D = [](uint32_t lo) { return (static_cast<uint64_t>(DESC_HI64) << 32) | lo; };
       constexpr uint32_t PL = PLANE_BYTES >> 4;                        // descriptor units between digit planes
       constexpr uint32_t SLD = SLOT_BYTES >> 4;
-      const uint32_t slot_lo = lo_of(s_slot), own_lo = lo_of(s_own);
+      const uint32_t slot_lo = lo_of(s_slot);
       uint32_t flush_idx = 0;
       int until_flush = p.flush_units;
       bool fresh_acc = true;
@@ -533,25 +491,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_ring_kernel(const I8P
         const uint32_t up = static_cast<uint32_t>(j & 1), a_phase = static_cast<uint32_t>((j >> 1) & 1);
         const uint32_t fresh = fresh_acc ? 0u : 1u;
         fresh_acc = false;
-        // B operand of this unit: the ring copy, or our own smem copy (self mode: always; diagonal holder in shared mode: for
-        // the units it published itself -- publish sequence number q = j / pub_h, slot q % 2)
-        const bool own_b = !b_from_ring || (own_b_units && (static_cast<uint32_t>(j % pub_h) == static_cast<uint32_t>(pub_r)));
-        uint32_t so = si, so_phase = pi_phase;
-        if (own_b_units) { const uint32_t q = static_cast<uint32_t>(j / pub_h); so = q & 1u; so_phase = (q >> 1) & 1u; }
-        const uint32_t pbd = own_b ? own_lo + so * SLD : slot_lo + sj * SLD;
+        const uint32_t pb = diag ? slot_lo + si * SLD : slot_lo + sj * SLD;
 #pragma unroll
         for (uint32_t ks = 0; ks < 2; ++ks) {
           MBAR_WAIT(b_afull + 8 * (2 * ks + up), a_phase, 5, j);           // A planes of this k-step are in TMEM
           if (ks == 0) {
             SGP_TL(1, j, 1);
-            if (own_b) MBAR_WAIT(b_pifull + 8 * so, so_phase, 14, j);           // B = our own planes in smem
-            else MBAR_WAIT(b_pjfull + 8 * sj, pj_phase, 6, j);                 // B = panel b's planes from the ring
+            if (diag) MBAR_WAIT(b_pifull + 8 * si, pi_phase, 14, j);        // B = our own planes in smem
+            else MBAR_WAIT(b_pjfull + 8 * sj, pj_phase, 6, j);             // B = panel J's planes from the ring
             SGP_TL(1, j, 2);
           }
           tc_fence_after();
           if (elected) {
             const uint32_t a0 = tmem + TM_A0 + ks * A_KS_COLS, a1 = a0 + 8, a2 = a0 + 16;   // planes P0, P1, P2
-            const uint32_t b0 = pbd + 2 * ks, b1 = b0 + PL, b2 = b0 + 2 * PL;
+            const uint32_t b0 = pb + 2 * ks, b1 = b0 + PL, b2 = b0 + 2 * PL;
             const uint32_t f = ks == 0 ? fresh : 1u;
             mma_i8_ts(tmem + TM_ACC4, a2, D(b2), ID_UU, f);                // weight 2^32 : P2'P2
             mma_i8_ts(tmem + TM_ACC3, a2, D(b1), ID_US, f);                // weight 2^24 : P2'P1 + P1'P2
@@ -561,14 +514,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_ring_kernel(const I8P
             mma_i8_ts(tmem + TM_ACC2, a1, D(b1), ID_SS, 1u);
             tc_commit(b_aempty + 8 * (2 * ks + up));                       // this k-step's A columns may be rewritten
             if (ks == 1) {
-              if (own_b) tc_commit(b_piempty + 8 * so);
+              if (diag) tc_commit(b_piempty + 8 * si);
               else tc_commit(b_pjempty + 8 * sj);
             }
           }
         }
         SGP_TL(1, j, 3);
-        if (++si == NPI_PUB) { si = 0; pi_phase ^= 1; }                                   // (self mode: slot = unit % 4)
-        if (!own_b && ++sj == static_cast<uint32_t>(p.npj)) { sj = 0; pj_phase ^= 1; }     // ring slots advance with ring units
+        if (++si == static_cast<uint32_t>(npi)) { si = 0; pi_phase ^= 1; }
+        if (++sj == static_cast<uint32_t>(p.npj)) { sj = 0; pj_phase ^= 1; }
         if (--until_flush == 0 || j == nu - 1) {
           until_flush = p.flush_units;
           fresh_acc = true;
@@ -582,131 +535,116 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_ring_kernel(const I8P
       }
     }
   } else if (warp == 3) {
-    // ================= panel sharing through L2: lane 0 publishes panel a, lane 1 copies panel b ===================
-    const size_t sl = static_cast<size_t>(blockIdx.y) * nt;
-    if (lane == 0 && publishes) {
-      // ---- ship the finished planes of our share of panel a's units to its ring, then set the slot's ready word ------
-      uint8_t* ring = p.ring + (sl + pa) * RING_D * SLOT_BYTES;
-      unsigned* ready = p.ready + (sl + pa) * (RING_D + 1) * FLAG_STRIDE;
-      const unsigned* cons = p.consumed + (sl + pa) * nt * FLAG_STRIDE;
-      unsigned min_cons = 0;                               // units every consumer has copied out (cached lower bound)
-      // our stores whose ready word is not set yet (oldest first).  Self mode keeps up to 3 in flight (consecutive units, a
-      // 24 KB store takes a few thousand clk to be acknowledged).  A holder in shared mode publishes only every h-th unit and
-      // has nothing else to do in between: it waits for each store and publishes it at once -- tying the publication of unit
-      // u to the holder's NEXT own unit u + h deadlocks (everybody's next unit needs somebody else's unit u).
-      long long pend[4] = {-1, -1, -1, -1};
-      const bool in_order_pub = (pub_mode == 1 || pub_mode == 3);      // sole publisher of the panel: units in order
-      const int lag = in_order_pub ? 3 : 0;
-      int n_pend = 0;
-      uint32_t q = 0;                                      // publish sequence number: slot q % npi
-      for (long long u = pub_r; u < nu; u += pub_h, ++q) {
-        const uint32_t si = q % static_cast<uint32_t>(npi);
+    // ================= panel sharing through L2 ===============================================================
+    const size_t col = static_cast<size_t>(blockIdx.y) * p.nt + tj;          // (slice, tile column)
+    uint8_t* ring = p.ring + col * RING_D * SLOT_BYTES;
+    unsigned* ready = p.ready + col * FLAG_STRIDE;
+    if (publisher) {
+      // ---- diagonal CTA: ship the finished planes of every unit to the ring, then release the ready counter --------
+      const unsigned* cons = p.consumed + (col * p.nt + (tj + 1)) * FLAG_STRIDE;   // [n_cons] counters of CTAs (tj+1.., tj)
+      unsigned min_cons = 0;                                                   // units every consumer has copied out
+      uint32_t si = 0, pi_phase = 0;
+      for (long long u = 0; u < nu; ++u) {
         SGP_TL(4, u, 0);
-        MBAR_WAIT(b_pifull + 8 * si, (q / static_cast<uint32_t>(npi)) & 1, 8, u);   // planes complete + fenced to the async proxy
+        MBAR_WAIT(b_pifull + 8 * si, pi_phase, 8, u);          // planes of unit u complete and visible to the async proxy
         SGP_TL(4, u, 1);
         if (u >= RING_D && min_cons < static_cast<unsigned>(u - RING_D + 1)) {   // back-pressure: ring slot still unread
           const long long t0 = clock64();
           unsigned it = 0;
           for (;;) {
             unsigned v = 0xFFFFFFFFu;
-            for (int a = cons_lo; a < nt; ++a) { const unsigned c = ld_relaxed_u32(cons + a * FLAG_STRIDE); v = c < v ? c : v; }
+            for (int k = lane; k < n_cons; k += 32) { const unsigned c = ld_relaxed_u32(cons + k * FLAG_STRIDE); v = c < v ? c : v; }
+            v = __reduce_min_sync(0xffffffffu, v);
             if (v >= static_cast<unsigned>(u - RING_D + 1)) { min_cons = v; break; }
             __nanosleep(64);
-            spin_guard(t0, it, p.pm, 12, u, v, static_cast<unsigned>(u - RING_D + 1));
+            long long tt = t0;
+            spin_guard(tt, it, p.pm, 12, u, v, static_cast<unsigned>(u - RING_D + 1));
           }
         }
         SGP_TL(4, u, 2);
-        // (the epilogue warps fenced their generic-proxy plane writes to the async proxy before arriving on pi_full)
-        bulk_s2g(ring + static_cast<size_t>(u % RING_D) * SLOT_BYTES, s_own + si * SLOT_BYTES, SLOT_BYTES);
-        bulk_commit();
-        SGP_TL(4, u, 3);
-        if (lag == 0) {
-          bulk_wait_read<0>();                              // the store has READ its smem slot: the epilogue may overwrite it
-          mbar_arrive(b_piempty + 8 * si);
-        } else if (q > 0) {
-          bulk_wait_read<1>();                              // ... of our previous unit
-          mbar_arrive(b_piempty + 8 * ((q - 1) % static_cast<uint32_t>(npi)));
-        }
-        SGP_TL(4, u, 4);
-        pend[n_pend++] = u;
-        // Ready words.  The planes of a store are in L2 (its bulk group has COMPLETED = the writes were acknowledged) before
-        // the word is written with a relaxed gpu-scope store -- L2 is the coherence point of the consumers' polls and bulk
-        // copies.  (A release here, i.e. a gpu-scope fence, stalls ~3300 clk on this SM's in-flight bulk stores; fences on
-        // this path cost 2.4x of the kernel in the first ring version.)
-        if (n_pend > lag) {
-          if (lag == 3) bulk_wait<3>(); else bulk_wait<0>();
-          st_relaxed_u32(ready + (pend[0] % RING_D) * FLAG_STRIDE, static_cast<unsigned>(pend[0] + 1));
-          if (in_order_pub) st_relaxed_u32(ready + RING_D * FLAG_STRIDE, static_cast<unsigned>(pend[0] + 1));   // units 0..pend[0]
-          pend[0] = pend[1]; pend[1] = pend[2]; pend[2] = pend[3]; pend[3] = -1;
-          --n_pend;
-        }
-        SGP_TL(4, u, 5);
-      }
-      bulk_wait<0>();
-      for (int k = 0; k < n_pend; ++k) st_relaxed_u32(ready + (pend[k] % RING_D) * FLAG_STRIDE, static_cast<unsigned>(pend[k] + 1));
-      if (in_order_pub && n_pend > 0) st_relaxed_u32(ready + RING_D * FLAG_STRIDE, static_cast<unsigned>(pend[n_pend - 1] + 1));
-    } else if (lane == 1 && b_from_ring) {
-      // ---- copy panel b's planes out of its ring into the B-operand slots -------------------------------------------
-      // One thread, two duties, neither may block the other: (a) issue the copy of unit `ni` as soon as its smem slot has
-      // drained (Gram MMAs of unit ni - npj), the landing of its previous occupant has been REPORTED (keeps pj_full at most
-      // one phase ahead of the parity tested below) and the slot's ready word covers it; (b) report every copy that has
-      // landed -- its ring slot may be recycled by the publishers.
-      const uint8_t* ring = p.ring + (sl + pb) * RING_D * SLOT_BYTES;
-      const unsigned* ready = p.ready + (sl + pb) * (RING_D + 1) * FLAG_STRIDE;
-      const bool in_order = !p.shared || pb == 0;   // sole publisher of panel b (diagonal / helper): cumulative count too
-      unsigned seen = 0;
-      unsigned* mine = p.consumed + ((sl + pb) * nt + pa) * FLAG_STRIDE;
-      const uint32_t npj = static_cast<uint32_t>(p.npj);
-      long long ni = 0, nr = 0;                // next unit to issue / next unit whose landing is unreported
-      uint32_t sj = 0, pj_phase = 0;           // slot / pj_full parity of unit ni
-      uint32_t sr = 0, pr_phase = 0;           // slot / pj_full parity of unit nr
-      long long t0 = clock64();
-      unsigned it = 0;
-      while (nr < nu) {
-        bool progressed = false;
-        // units we published ourselves (diagonal holder) are not copied: they pass both pointers without touching a slot
-        if (nr < ni && own_b_units && static_cast<uint32_t>(nr % pub_h) == static_cast<uint32_t>(pub_r)) {
-          ++nr;
-          st_relaxed_u32(mine, static_cast<unsigned>(nr));
-          progressed = true;
-        } else if (nr < ni && mbar_test(b_pjfull + 8 * sr, pr_phase)) {
-          ++nr;
-          st_relaxed_u32(mine, static_cast<unsigned>(nr));
-          if (++sr == npj) { sr = 0; pr_phase ^= 1; }
-          progressed = true;
-        }
-        if (ni < nu && own_b_units && static_cast<uint32_t>(ni % pub_h) == static_cast<uint32_t>(pub_r)) {
-          ++ni;
-          progressed = true;
-        } else if (ni < nu && ni < nr + npj) {
-          // (the planes were acknowledged by L2 before the ready word was written and the copy is issued after the word
-          //  was read, also from L2: program order + the control dependency replace an acquire fence)
-          bool avail;
-          if (in_order) {                      // one poll of the cumulative count usually covers several units
-            if (seen < static_cast<unsigned>(ni + 1)) seen = ld_relaxed_u32(ready + RING_D * FLAG_STRIDE);
-            avail = seen >= static_cast<unsigned>(ni + 1);
-          } else {
-            avail = ld_relaxed_u32(ready + (ni % RING_D) * FLAG_STRIDE) == static_cast<unsigned>(ni + 1);
+        if (lane == 0) {
+          // (the epilogue warps fenced their generic-proxy plane writes to the async proxy before arriving on pi_full,
+          //  exactly as for the tensor core's reads: no further proxy fence is needed before the bulk store)
+          bulk_s2g(ring + static_cast<size_t>(u % RING_D) * SLOT_BYTES, s_slot + si * SLOT_BYTES, SLOT_BYTES);
+          bulk_commit();
+          SGP_TL(4, u, 3);
+          if (u > 0) {
+            // the store of unit u-1 has READ its smem slot: the epilogue may overwrite it (the write side completes later)
+            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            mbar_arrive(b_piempty + 8 * ((si + NPI_PUB - 1) % NPI_PUB));
           }
-          if (avail && (ni < npj || mbar_test(b_pjempty + 8 * sj, pj_phase ^ 1))) {
-            mbar_expect_tx(b_pjfull + 8 * sj, SLOT_BYTES);
-            bulk_g2s(s_slot + sj * SLOT_BYTES, ring + static_cast<size_t>(ni % RING_D) * SLOT_BYTES, SLOT_BYTES,
-                     b_pjfull + 8 * sj);
-            ++ni;
-            if (++sj == npj) { sj = 0; pj_phase ^= 1; }
+          SGP_TL(4, u, 4);
+          // Up to PUB_LAG stores stay in flight (a 24 KB store takes microseconds to be acknowledged), and the ready
+          // counter is released for two units at a time: every gpu-scope fence costs ~1000 clk on this thread (measured:
+          // three fences per unit serialised the whole tile column at 5300 clk per unit, profiles/r02_i8_tuning_log.md).
+          if (u >= PUB_LAG) {
+            bulk_wait<PUB_LAG>();                        // stores of units <= u - PUB_LAG have completed (writes performed)
+            SGP_TL(4, u, 5);
+            // The planes are in L2 (the bulk group has completed = its writes were acknowledged) BEFORE this store is
+            // issued, and L2 is the coherence point of the consumers' polls and bulk copies: a relaxed gpu-scope store
+            // publishes them.  A release here (= gpu-scope fence) stalls ~3300 clk on this SM's in-flight bulk stores.
+            st_relaxed_u32(ready, static_cast<unsigned>(u - PUB_LAG + 1));
+            SGP_TL(4, u, 6);
+          }
+        }
+        __syncwarp();
+        if (++si == NPI_PUB) { si = 0; pi_phase ^= 1; }
+      }
+      if (lane == 0) {
+        bulk_wait<0>();
+        st_relaxed_u32(ready, static_cast<unsigned>(nu));
+      }
+    } else if (!diag) {
+      // ---- off-diagonal CTA: copy panel J's planes out of the ring into the B-operand ring ------------------------
+      unsigned* mine = p.consumed + (col * p.nt + ti) * FLAG_STRIDE;
+      if (lane == 0) {
+        // One thread, two duties, neither may block the other: (a) issue the copy of unit `ni` as soon as its smem slot
+        // has drained (Gram MMAs of unit ni - npj) and the publisher's counter covers it; (b) report every copy that has
+        // LANDED (its ring slot may be recycled) -- reporting only when the MMAs had drained added npj units of lag to the
+        // publisher's back-pressure loop.
+        const uint32_t npj = static_cast<uint32_t>(p.npj);
+        long long ni = 0, nr = 0;                // next unit to issue / next unit whose landing is unreported
+        uint32_t sj = 0, pj_phase = 0;           // slot / pj_full parity of unit ni
+        uint32_t sr = 0, pr_phase = 0;           // slot / pj_full parity of unit nr
+        unsigned seen = 0;
+        long long t0 = clock64();
+        unsigned it = 0;
+        while (nr < nu) {
+          bool progressed = false;
+          if (nr < ni && mbar_test(b_pjfull + 8 * sr, pr_phase)) {
+            SGP_TL(4, nr, 4);
+            ++nr;
+            st_relaxed_u32(mine, static_cast<unsigned>(nr));
+            if (++sr == npj) { sr = 0; pr_phase ^= 1; }
             progressed = true;
           }
+          if (ni < nu && ni < nr + npj) {      // slot reuse only after the previous occupant's landing has been REPORTED:
+                                               // keeps pj_full at most one phase ahead of the parity tested above
+            if (seen < static_cast<unsigned>(ni + 1)) { SGP_TL(4, ni, 0); seen = ld_relaxed_u32(ready); SGP_TL(4, ni, 1); }
+            if (seen >= static_cast<unsigned>(ni + 1) && (ni < npj || mbar_test(b_pjempty + 8 * sj, pj_phase ^ 1))) {
+              // (the planes were acknowledged by L2 before the counter was written and this copy is issued after the
+              //  counter was read, also from L2: program order + the control dependency replace an acquire fence)
+              SGP_TL(4, ni, 2);
+              mbar_expect_tx(b_pjfull + 8 * sj, SLOT_BYTES);
+              bulk_g2s(s_slot + sj * SLOT_BYTES, ring + static_cast<size_t>(ni % RING_D) * SLOT_BYTES, SLOT_BYTES,
+                       b_pjfull + 8 * sj);
+              SGP_TL(4, ni, 3);
+              ++ni;
+              if (++sj == npj) { sj = 0; pj_phase ^= 1; }
+              progressed = true;
+            }
+          }
+          if (progressed) t0 = clock64();
+          else { __nanosleep(20); spin_guard(t0, it, p.pm, 13, ni, seen, static_cast<unsigned>(nr)); }
         }
-        if (progressed) t0 = clock64();
-        else { __nanosleep(20); spin_guard(t0, it, p.pm, 13, ni, static_cast<unsigned>(nr), static_cast<unsigned>(pb)); }
       }
     }
   } else {
     // ================= epilogue warps ===================================================================
     const int ew = warp - 4;
-    const int grp = ew >> 3;            // epilogue group == parity of the units it owns
+    const int grp = ew >> 3;            // epilogue group == parity of the units it owns == TMEM distance buffer
     const int lq = ew & 3;              // TMEM lane quarter of this warp (== warp % 4)
-    const int ch = (ew >> 2) & 1;       // which 32 of the 64 columns (points) of a distance tile == k-step
+    const int ch = (ew >> 2) & 1;       // which 32 of the 64 columns (points) of a distance tile
     const int cq = ew >> 2;             // 0..3: which 32 of the 128 accumulator columns in a flush
     const int L = lq * 32 + lane;       // TMEM lane == active-set row inside the tile
     const uint32_t lane_bits = static_cast<uint32_t>(lq * 32) << 16;
@@ -716,8 +654,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_ring_kernel(const I8P
     uint32_t flush_idx = 0, q_phase = 0;
     int until_flush = p.flush_units;
     bool first_flush = true;
+    // barrier polls are software-pipelined: a try_wait on an already-complete phase still costs 150-250 clk of latency,
+    // so q_full of this group's NEXT tile is tested during this tile's store phase and pi_empty in the middle of the
+    // exp block
     bool q_ready = false;
     const bool dbg = DBG && (p.dbg_T != nullptr) && blockIdx.x == 0 && blockIdx.y == 0;
+    const int npi_shift = 2;                                                     // npi == 4
     for (long long i = 0; i < nu; ++i) {
       if ((i & 1) == grp) {
         // ---- one distance tile (128 active rows x 64 points) -> three int8 digit planes of unit i ---------------
@@ -771,19 +713,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_ring_kernel(const I8P
           const uint32_t u01 = prmt(w0, w1, 0x0062), u23 = prmt(w2, w3, 0x0062);
           d2[g] = prmt(u01, u23, 0x5410);                   // P2 = s2 = byte2 (0..255, unsigned operand)
         }
-        const bool pub_this = publishes && (pub_h == 1 || (i % pub_h) == pub_r);
-        const bool sts_this = pub_this || pub_mode == 1;    // (self mode: the smem copy is also our own B operand)
-        // (shared mode, diagonal holder: pub_this units are exactly the ones whose B operand is our own copy)
-        if (sts_this) {
-          // smem copy of the planes (K-major SWIZZLE_64B image): published to the ring and, in self mode, our B operand.
-          // Written BEFORE the wait for the A columns; the proxy fence (400-600 clk of this warp) is absorbed by that wait.
-          // Slot = publish sequence number % npi; before overwriting it the bulk store that shipped its previous occupant
-          // (and, in self mode, the Gram MMAs that read it) must have drained: completion (q / npi - 1) of pi_empty[slot]
-          const uint32_t q = static_cast<uint32_t>(i / pub_h);
-          const uint32_t si = q % static_cast<uint32_t>(npi);
-          if (q >= static_cast<uint32_t>(npi))
-            MBAR_WAIT(b_piempty + 8 * si, ((q / static_cast<uint32_t>(npi)) - 1) & 1, 15, i);
-          uint8_t* const slot = sm + (s_own - base) + si * SLOT_BYTES;
+        if (diag) {
+          // the diagonal tile also needs its panel as the B operand (and publishes it): K-major SWIZZLE_64B image in smem,
+          // written BEFORE the wait for the A columns so that pi_full (B side, publisher) is never behind a_full.
+          // unit i lives in slot i % 4; before overwriting it the Gram MMAs of unit i - 4 (and, on a publishing CTA,
+          // the bulk store that shipped it) must have drained: completion (i / 4 - 1) of pi_empty[slot]
+          const uint32_t si = static_cast<uint32_t>(i) & static_cast<uint32_t>(npi - 1);
+          if (i >= npi) MBAR_WAIT(b_piempty + 8 * si, static_cast<uint32_t>(((i >> npi_shift) - 1) & 1), 15, i);
+          uint8_t* const slot = sm + si * SLOT_BYTES;
 #pragma unroll
           for (int g16 = 0; g16 < 2; ++g16) {
             uint8_t* dst = slot + sw64_off(L, ch * 2 + g16);
@@ -791,34 +728,39 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_ring_kernel(const I8P
             *reinterpret_cast<uint4*>(dst + 1 * PLANE_BYTES) = make_uint4(d1[4 * g16], d1[4 * g16 + 1], d1[4 * g16 + 2], d1[4 * g16 + 3]);
             *reinterpret_cast<uint4*>(dst + 2 * PLANE_BYTES) = make_uint4(d2[4 * g16], d2[4 * g16 + 1], d2[4 * g16 + 2], d2[4 * g16 + 3]);
           }
-          fence_proxy_async();           // generic-proxy plane writes -> visible to the tensor core / bulk copy (async proxy)
+          // generic-proxy plane writes -> visible to the tensor core / bulk copy (async proxy).  The fence costs 400-600 clk
+          // of this warp; it sits BEFORE the wait for the A columns, which would idle anyway (tried: after the A store
+          // 1600 clk per unit, deferred into the next tile's TMEM load 2130 -- the Gram issuer then waits for pi_full)
+          fence_proxy_async();
           __syncwarp();
           if (lane == 0) mbar_arrive(b_pifull + 8 * si);
         }
         if (tle) SGP_TL(2 + grp, i, 4);
-        if (!helper) {
-          // A operand: straight into tensor memory once the Gram MMAs of the previous unit's k-step `ch` have drained
-          // (barriers are split by unit parity so that a group, which sees only every other unit, never lags a phase)
-          if (i >= 1) MBAR_WAIT(b_aempty + 8 * (2 * ch + (grp ^ 1)), static_cast<uint32_t>(((i - 1) >> 1) & 1), 10, i);
-          tc_fence_after();
-          tmem_st8(a_taddr + 0, d0);
-          tmem_st8(a_taddr + 8, d1);
-          tmem_st8(a_taddr + 16, d2);
-          tmem_wait_st();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(b_afull + 8 * (2 * ch + grp));
-        }
+        // A operand: straight into tensor memory once the Gram MMAs of the previous unit's k-step `ch` have drained
+        // (barriers are split by unit parity so that a group, which sees only every other unit, never lags a phase)
+        if (i >= 1) MBAR_WAIT(b_aempty + 8 * (2 * ch + (grp ^ 1)), static_cast<uint32_t>(((i - 1) >> 1) & 1), 10, i);
+        tc_fence_after();
+        tmem_st8(a_taddr + 0, d0);
+        tmem_st8(a_taddr + 8, d1);
+        tmem_st8(a_taddr + 16, d2);
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(b_afull + 8 * (2 * ch + grp));
         q_ready = mbar_test(b_qfull + 8 * grp, q_phase);     // next tile of this group
         if (tle) SGP_TL(2 + grp, i, 5);
       }
 
-      if (!helper && (--until_flush == 0 || i == nu - 1)) {
+      if (--until_flush == 0 || i == nu - 1) {
         until_flush = p.flush_units;
         // ---- fold the exact int32 accumulators into the fp64 partial tile (all 16 warps) -----------------
         MBAR_WAIT(b_accfull, flush_idx & 1, 11, i);
         tc_fence_after();
-        double* gl = out_base + static_cast<size_t>(L) * out_lane_stride;
+        // The partial tile is stored TRANSPOSED, i.e. at the mirror position (tile (tj,ti) of the upper block triangle):
+        // a thread owns one ROW of the TMEM tile, so for a fixed column the 32 lanes of a warp write 32 consecutive
+        // doubles of the transposed image -- two full 128-byte lines per instruction instead of 32 half-used sectors 8 KB
+        // apart (the row-major fold cost 30k clk, 7 % of the kernel).  gram_reduce reads the upper triangle.
+        double* gcol = Gp + static_cast<size_t>(tj * kTile) * p.m_pad + ti * kTile + L;
         for (int cg = 0; cg < 2; ++cg) {
           const int col0 = cq * 32 + cg * 16;
           uint32_t a4[16], a3[16], a2[16];
@@ -832,7 +774,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_ring_kernel(const I8P
                        16777216.0 * static_cast<double>(static_cast<int>(a3[k])) +
                        65536.0 * static_cast<double>(static_cast<int>(a2[k]));
             v *= p.gscale;
-            double* dst = gl + static_cast<size_t>(col0 + k) * out_col_stride;
+            double* dst = gcol + static_cast<size_t>(col0 + k) * p.m_pad;
             if (first_flush) *dst = v;
             else *dst += v;
           }
@@ -871,29 +813,12 @@ size_t i8_share_bytes(int m_pad, int n_slices) {
 }
 size_t i8_share_flag_bytes(int m_pad, int n_slices) {
   const size_t nt = m_pad / kTile;
-  return (static_cast<size_t>(n_slices) * nt * (RING_D + 1) + static_cast<size_t>(n_slices) * nt * nt) * FLAG_STRIDE * sizeof(unsigned);
+  return (static_cast<size_t>(n_slices) * nt + static_cast<size_t>(n_slices) * nt * nt) * FLAG_STRIDE * sizeof(unsigned);
 }
 
-// Launch plan.  If every tile fits in ONE cooperative launch (nt (nt+1) / 2 <= num_sms: m <= 2048 on a B200) the launch is
-// "balanced" (col_hi = -1 marks it): tile orientations alternate and the holders of a panel share its publishing.  Otherwise
-// whole tile columns per launch, at most `num_sms` CTAs each, the diagonal CTA of a column publishes its panel.
+// Launch plan: whole tile columns per launch, at most `num_sms` CTAs each (every CTA of a launch must be resident).
 int i8_plan(int m_pad, int num_sms, long long n_units, I8Launch* out, int max_out) {
   const int nt = m_pad / kTile;
-  const int all = nt * (nt + 1) / 2;
-  if (all <= num_sms && max_out >= 1) {
-    int slices = num_sms / all;
-    if (slices > n_units) slices = static_cast<int>(n_units > 0 ? n_units : 1);
-    if (slices < 1) slices = 1;
-    out[0].col_lo = 0; out[0].col_hi = nt; out[0].tiles = all; out[0].n_slices = slices; out[0].shared = 0;
-    // shared publishing needs one helper CTA per slice on top of the tiles, all co-resident
-    if (nt >= 2 && all + 1 <= num_sms) {
-      int sl = num_sms / (all + 1);
-      if (sl > n_units) sl = static_cast<int>(n_units > 0 ? n_units : 1);
-      if (sl >= 1 && sl >= slices) { out[0].shared = 1; out[0].n_slices = sl; }
-    }
-    if (const char* e = getenv("SGP_I8_MODE")) { if (std::string(e) == "column") out[0].shared = 0; }
-    return 1;
-  }
   int n = 0, col = 0;
   while (col < nt) {
     int tiles = 0, c = col;
@@ -903,23 +828,25 @@ int i8_plan(int m_pad, int num_sms, long long n_units, I8Launch* out, int max_ou
     int slices = num_sms / tiles;
     if (slices < 1) slices = 1;
     if (slices > n_units) slices = static_cast<int>(n_units > 0 ? n_units : 1);
-    out[n].col_lo = col; out[n].col_hi = c; out[n].tiles = tiles; out[n].n_slices = slices; out[n].shared = 0;
+    out[n].col_lo = col; out[n].col_hi = c; out[n].tiles = tiles; out[n].n_slices = slices;
     ++n;
     col = c;
   }
   return n;
 }
 
+
+
 cudaError_t launch_gram_i8_ring(const uint8_t* Xt, const float* ys, const uint8_t* Zt, long long n, int d, int m_pad,
-                                const I8Launch& plan, double* Gpart, double* bpart, double C, uint8_t* share, float* dbg_T,
-                                uint32_t* dbg_w, long long* dbg_clk, void* post_mortem, cudaStream_t s) {
+                           const I8Launch& plan, double* Gpart, double* bpart, double C, uint8_t* share, float* dbg_T,
+                           uint32_t* dbg_w, long long* dbg_clk, void* post_mortem, cudaStream_t s) {
   I8Params p{};
   const int dp = (d + 15) / 16 * 16;
   p.Xt = Xt; p.ys = ys; p.Zt = Zt;
   p.n_units = (n + UP - 1) / UP;
   p.nchunks = i8_nchunks(d);
   p.ksteps_last = (3 * dp + 16) / 16 - 4 * (p.nchunks - 1);
-  p.m_pad = m_pad; p.nt = m_pad / kTile; p.n_slices = plan.n_slices; p.col_lo = plan.col_lo; p.shared = plan.shared; p.n_tiles = plan.tiles;
+  p.m_pad = m_pad; p.nt = m_pad / kTile; p.n_slices = plan.n_slices; p.col_lo = plan.col_lo;
   // fold every 400 units = 25600 points: guaranteed bounds |ACC4| <= 255^2 n = 1.66e9, |ACC3| <= 2*255*128 n = 1.67e9,
   // |ACC2| <= (2*255*128 + 128^2) n = 2.09e9, all < 2^31 = 2.147e9
   p.flush_units = 400;
@@ -929,28 +856,23 @@ cudaError_t launch_gram_i8_ring(const uint8_t* Xt, const float* ys, const uint8_
   p.tl_u0 = 64; p.tl_slice = 0;
   if (const char* e = getenv("SGP_I8_TL_U0")) p.tl_u0 = atoll(e);
   if (const char* e = getenv("SGP_I8_TL_SLICE")) p.tl_slice = atoi(e);
-  p.tl_cta0 = 0; p.tl_cta1 = 1;
-  if (const char* e = getenv("SGP_I8_TL_CTA0")) p.tl_cta0 = atoi(e);
-  if (const char* e = getenv("SGP_I8_TL_CTA1")) p.tl_cta1 = atoi(e);
   p.dbg_T = dbg_T; p.dbg_w = dbg_w; p.dbg_clk = dbg_clk; p.pm = static_cast<I8PostMortem*>(post_mortem);
-  // shared memory: npj ring slots (panel b) + 4 own slots (panel a when published) + Z image + X ring (227 KB limit)
-  if (plan.shared) { p.npj = (p.nchunks == 1) ? 4 : 3; p.xstages = (p.nchunks == 1) ? 6 : 4; }   // + 2 own slots
-  else { p.npj = (p.nchunks == 1) ? 5 : 3; p.xstages = (p.nchunks == 1) ? 8 : 5; }
+  p.xstages = (p.nchunks == 1) ? 8 : 5;
+  p.npj = (p.nchunks == 1) ? NPJ_MAX : 3;
   const size_t ring_bytes = static_cast<size_t>(plan.n_slices) * p.nt * RING_D * SLOT_BYTES;
   p.ring = share;
   p.ready = reinterpret_cast<unsigned*>(share + ring_bytes);
-  p.consumed = p.ready + static_cast<size_t>(plan.n_slices) * p.nt * (RING_D + 1) * FLAG_STRIDE;
+  p.consumed = p.ready + static_cast<size_t>(plan.n_slices) * p.nt * FLAG_STRIDE;
   cudaError_t e = cudaMemsetAsync(p.ready, 0, i8_share_flag_bytes(m_pad, plan.n_slices), s);
   if (e != cudaSuccess) return e;
-  const int own_extra = plan.shared ? 2 : 0;
-  const size_t smem = 1024 + (p.npj + own_extra > NPI_PUB ? p.npj + own_extra : NPI_PUB) * SLOT_BYTES + p.nchunks * ZPANEL_BYTES + p.xstages * p.nchunks * XIMG_BYTES +
+  const size_t smem = 1024 + (p.npj > NPI_PUB ? p.npj : NPI_PUB) * SLOT_BYTES + p.nchunks * ZPANEL_BYTES + p.xstages * p.nchunks * XIMG_BYTES +
                       YSTAGES * UP * 4 + 4 * 128 * 8 + 512;
   const void* fn = dbg_T ? reinterpret_cast<const void*>(kmn_gram_i8_ring_kernel<true>)
                          : reinterpret_cast<const void*>(kmn_gram_i8_ring_kernel<false>);
   // per-device attribute: set on every launch (contexts on several GPUs may live in one process)
   e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) return e;
-  dim3 grid(plan.tiles + (plan.shared ? 1 : 0), plan.n_slices);
+  dim3 grid(plan.tiles, plan.n_slices);
   void* args[] = {&p};
   // cooperative launch: the runtime refuses (instead of deadlocking) if the grid cannot be co-resident
   return cudaLaunchCooperativeKernel(fn, grid, dim3(NTHREADS), args, smem, s);

@@ -177,7 +177,6 @@ cudaError_t launch_i8_prep_points(uint8_t* Xt, float* ys, const void* dX, int x_
 // One cooperative launch of the int8 Gram kernel: whole tile columns [col_lo, col_hi) x n_slices point slices.
 struct I8Launch {
   int col_lo, col_hi, tiles, n_slices;
-  int shared;        // 1: all tiles in this launch + one helper CTA per slice, holders share the publishing; 0: column mode
 };
 int i8_plan(int m_pad, int num_sms, long long n_units, I8Launch* out, int max_out);
 size_t i8_share_bytes(int m_pad, int n_slices);

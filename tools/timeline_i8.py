@@ -57,7 +57,7 @@ P = eng.i8_progress if hasattr(eng, "i8_progress") else None
 if P is not None:
     g0 = P[P > 0].min()
     print("per-CTA progress: clk/unit between marks (every 128 units), CTA = slice*36 + tile")
-    for cta in list(range(0, 37)) + [37, 74, 111, 147]:
+    for cta in list(range(0, 10)) + [35, 36, 37, 72, 108, 143]:
         t = P[cta]
         k = int((t > 0).sum())
         if k < 2:
