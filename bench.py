@@ -257,7 +257,8 @@ def run_ours(args):
         sampler.start()
     prim = primary_workload(world)
 
-    def measure(name: str, with_e2e: bool, steps: int, warmup: int):
+    def measure(name: str, with_e2e: bool, steps: int, warmup: int, precision=None):
+        eng.set_precision(sg._native.SGP_PREC_AUTO if precision is None else precision)
         w = WORKLOADS[name]
         n, d, m = w["n_per_gpu"], w["d"], w["m"]
         Xh, yh = make_shard(name, rank)
@@ -369,7 +370,8 @@ def run_ours(args):
         e = {"workload": WORKLOADS[r["name"]]["label"], "n_per_gpu": r["n"], "d": r["d"], "m": r["m"],
              "value": n_total / (ms / 1e3), "unit": UNIT, "ms_per_step": ms, "tail_ms": r["tail_ms"],
              "stats_plus_tail": n_total / ((ms + r["tail_ms"]) / 1e3),
-             "kernel_path": {0: "f64", 1: "f64_strict", 2: "i8"}.get(r["path"], str(r["path"]))}
+             "kernel_path": {0: "f64", 1: "f64_strict", 2: "i8", 4: "i8_direct"}.get(r["path"], str(r["path"])),
+             "gram_kernel_ms": r["kern_ms"] / max(r["kern_n"], 1)}
         if r["e2e_ms"]:
             e["e2e"] = n_total * steps / (r["e2e_ms"] / 1e3)
         return e
@@ -378,6 +380,10 @@ def run_ours(args):
     rp = measure(prim, True, args.steps, args.warmup)
     ro = measure(other, False, max(2, min(args.steps, 3)), 3)
     clocks = sampler.stop(*rp["t_wall"]) if rank == 0 else None
+    rd = None
+    if world == 1 and args.direct:      # same shard, exponents from direct fp32 distances (what AUTO picks for large norms)
+        rd = measure("configs1", False, 3, 3, precision=sg._native.SGP_PREC_I8_DIRECT)
+        eng.set_precision(sg._native.SGP_PREC_AUTO)
 
     if rank == 0:
         n_total = rp["n"] * world
@@ -412,6 +418,8 @@ def run_ours(args):
                                    "ms_per_step": ms_step + rp["tail_ms"]},
                "series": {prim: series_entry(rp, args.steps), other: series_entry(ro, max(2, min(args.steps, 3)))},
                "wall_ms_timed_region": 1e3 * (rp["t_wall"][1] - rp["t_wall"][0])}
+        if rd is not None:
+            out["series"]["configs1_i8_direct"] = series_entry(rd, 3)
         if "allreduce_check" in rp:
             out["allreduce_check"] = rp["allreduce_check"]
         if world == 1 and args.fit:
@@ -488,6 +496,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fit", dest="fit", action="store_false", help="skip the whole-fit number (N=1 only)")
     ap.add_argument("--no-sweep", dest="sweep", action="store_false", help="skip the K_nm sweep number (N=1 only)")
+    ap.add_argument("--no-direct", dest="direct", action="store_false",
+                    help="skip the direct-distance int8 series entry (N=1 only)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -39,7 +39,8 @@ enum {
   SGP_E_STATE = 5,    /* call order violated (e.g. accumulate before begin) ~ TrainingVectorsNotInitializedException */
   SGP_E_SINGULAR = 6, /* MatrixSingularException (commons/util/logDetAndInv.scala:27-28), LU info > 0 */
   SGP_E_NOMEM = 7,
-  SGP_E_RANGE = 8     /* SGP_PREC_I8 only: scaled coordinates outside the fp16 operand range; rerun in SGP_PREC_F64 */
+  SGP_E_RANGE = 8     /* int8 modes only: scaled coordinates outside the fp16 operand range / above the magnitude budget
+                         (SGP_PREC_I8), or scaled squared norms above 2048 (SGP_PREC_I8_DIRECT); rerun in SGP_PREC_F64 */
 };
 
 /* Flattened kernel DSL (the files under commons/kernel/).  A kernel is a sum of terms  sum_t scale_t * k_t:
@@ -72,9 +73,15 @@ enum {
   SGP_PREC_F64_STRICT = 1, /* elements in fp64 as well (verification mode, ~1e-13 on G,b)               */
   SGP_PREC_I8 = 2,         /* tcgen05 path: distance contraction on fp16 hi/lo splits (fp32 in TMEM), kernel elements
                               as 23-bit fixed point in three balanced int8 digits, Gram = six kind::i8 products with
-                              EXACT int32 accumulation, folded into fp64.  Kernels with one non-Eye term, d <= 32. */
-  SGP_PREC_AUTO = 3        /* default: SGP_PREC_I8 when the kernel/shape qualifies AND the shard has >= 262144 points,
-                              else SGP_PREC_F64 ('precision')                                     */
+                              EXACT int32 accumulation, folded into fp64.  Kernels with one non-Eye term, d <= 32; other
+                              qualifying shapes are served by SGP_PREC_I8_DIRECT (sgp_last_path tells which ran).       */
+  SGP_PREC_AUTO = 3,       /* default: SGP_PREC_I8 when the kernel/shape qualifies AND the shard has >= 262144 points,
+                              else SGP_PREC_I8_DIRECT when THAT qualifies, else SGP_PREC_F64 ('precision')    */
+  SGP_PREC_I8_DIRECT = 4   /* same exact int8 Gram as SGP_PREC_I8, but the exponents come from fp32 DIRECT-FORM distances on
+                              the CUDA cores (no cancellation; coordinates are centred on the active-set mean in fp64
+                              first) and the kernel may be a sum of up to 4 non-Eye terms (kernel/SumOfKernels.scala:57-58)
+                              with n_terms * roundup(d, 4) <= 72.  Scaled squared norms up to 2048.  AUTO picks it for large
+                              shards that SGP_PREC_I8 cannot take (several terms, 32 < d <= 72, norms above its budget). */
 };
 
 /* ---- context ------------------------------------------------------------------------------ */
@@ -182,7 +189,8 @@ int sgp_gram_kernel_time(sgp_ctx* ctx, double* total_ms, int64_t* launches);
  * stream).  slot in [0, 8): sgp_event_record enqueues an event; sgp_event_elapsed_ms waits for both. */
 int sgp_event_record(sgp_ctx* ctx, int slot);
 int sgp_event_elapsed_ms(sgp_ctx* ctx, int slot_start, int slot_stop, double* ms);
-/* Which kernel the last statistics launch used: SGP_PREC_F64, SGP_PREC_F64_STRICT or SGP_PREC_I8 (-1: none yet). */
+/* Which kernel the last statistics launch used: SGP_PREC_F64, SGP_PREC_F64_STRICT, SGP_PREC_I8 or SGP_PREC_I8_DIRECT
+ * (-1: none yet). */
 int sgp_last_path(const sgp_ctx* ctx);
 /* Which path the last sgp_magic took: 1 = Cholesky for both A and K_mm (success of dpotrf IS the reference's positive-
  * definiteness check PGPH:62-65), 0 = the reference's literal sequence (dsyevd eigenvalue check, LU solves) because a

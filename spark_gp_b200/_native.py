@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(HERE, "libsgp.so")
 
 SGP_OK, SGP_E_BADARG, SGP_E_CUDA, SGP_E_NOT_PD, SGP_E_NCCL, SGP_E_STATE, SGP_E_SINGULAR, SGP_E_NOMEM, SGP_E_RANGE = range(9)
 SGP_TERM_ARD, SGP_TERM_RBF, SGP_TERM_EYE = 0, 1, 2
-SGP_PREC_F64, SGP_PREC_F64_STRICT, SGP_PREC_I8, SGP_PREC_AUTO = 0, 1, 2, 3
+SGP_PREC_F64, SGP_PREC_F64_STRICT, SGP_PREC_I8, SGP_PREC_AUTO, SGP_PREC_I8_DIRECT = 0, 1, 2, 3, 4
 SGP_UNIQUE_ID_BYTES = 128
 
 # every symbol include/sgp.h declares (tests/test_abi.py checks the .so exports each of them)

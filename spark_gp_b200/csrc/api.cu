@@ -60,6 +60,7 @@ static void free_active_set(Ctx* c) {
   cudaFree(c->dZ); cudaFree(c->dZs); cudaFree(c->dBeta); cudaFree(c->dGb);
   cudaFree(c->dMagicVec); cudaFree(c->dMagicMat);
   cudaFree(c->dI8Scale); cudaFree(c->dI8Centre); cudaFree(c->dI8Flags); cudaFree(c->dI8Zt); cudaFree(c->dI8NormSum);
+  cudaFree(c->dI8Zd); cudaFree(c->dI8DScale); c->dI8Zd = nullptr; c->dI8DScale = nullptr; c->i8_direct_ok = false;
   c->dI8NormSum = nullptr;
   c->dZ = c->dZs = c->dBeta = c->dGb = c->dMagicVec = c->dMagicMat = nullptr;
   c->dI8Scale = c->dI8Centre = nullptr; c->dI8Flags = nullptr; c->dI8Zt = nullptr; c->i8_ok = false;
@@ -97,7 +98,7 @@ static int launch_stats(Ctx* c, const void* dX, int x_is_f32, const double* dy, 
   // int8 kernel: cooperative launches of whole tile columns (all CTAs of a launch are co-resident)
   I8Launch plan[64];
   int n_plan = 0, plan_slices = 1;
-  if (c->i8_ok && c->i8_impl == 1) {
+  if ((c->i8_ok || c->i8_direct_ok) && c->i8_impl == 1) {
     n_plan = i8_plan(c->m_pad, c->num_sms, (n + 63) / 64, plan, 64);
     for (int i = 0; i < n_plan; ++i) plan_slices = plan[i].n_slices > plan_slices ? plan[i].n_slices : plan_slices;
   }
@@ -117,31 +118,46 @@ static int launch_stats(Ctx* c, const void* dX, int x_is_f32, const double* dy, 
   // mean within 1.1e-6 .. 2.4e-6 of the all-fp64 kernel for N = 250k .. 4M, profiles/r01_i8_scaling.txt; the limit
   // is the two dropped low-order digit products, tools/i8_error_model.py) and small scaled norms (gate below).
   // Smaller shards stay on the fp64 DMMA kernel (2e-7), which is fast enough at that size.
-  bool use_i8 = c->i8_ok && (c->precision == SGP_PREC_I8 || (c->precision == SGP_PREC_AUTO && n_call >= 262144));
-  if (c->precision == SGP_PREC_AUTO && !first_of_call) use_i8 = use_i8 && c->call_i8;
-  if (c->precision == SGP_PREC_I8 && !c->i8_ok)
-    return fail(c, SGP_E_BADARG, "SGP_PREC_I8 needs a kernel with exactly one non-Eye term and d <= 32");
+  // Path of this launch: 0 = fp64 DMMA kernel, 1 = int8 Gram with tensor-core distances (one term, d <= 32, benign norms),
+  // 2 = int8 Gram with direct fp32 distances (up to 4 terms, any norms).
+  const bool tensor_ok = c->i8_ok, direct_ok = c->i8_direct_ok && c->i8_impl == 1 && n_plan > 0;
+  int path = 0;
+  if (c->precision == SGP_PREC_I8) {
+    if (tensor_ok) path = 1;
+    else if (direct_ok) path = 2;
+    else return fail(c, SGP_E_BADARG, "SGP_PREC_I8 needs a kernel with 1..4 non-Eye terms and n_terms * d <= 72 "
+                                      "(tensor-core distances: exactly one term and d <= 32)");
+  } else if (c->precision == SGP_PREC_I8_DIRECT) {
+    if (!direct_ok) return fail(c, SGP_E_BADARG, "SGP_PREC_I8_DIRECT needs a kernel with 1..4 non-Eye terms and n_terms * d <= 72");
+    path = 2;
+  } else if (c->precision == SGP_PREC_AUTO && n_call >= 262144) {
+    path = tensor_ok ? 1 : (direct_ok ? 2 : 0);
+    if (!first_of_call) path = c->call_path;
+  }
+  bool use_i8 = (path == 1);
   if (use_i8 && c->i8_impl == 1 && n_plan <= 0) {
     if (c->precision == SGP_PREC_I8) return fail(c, SGP_E_BADARG, "active set too large for the int8 kernel's launch plan");
-    use_i8 = false;
+    use_i8 = false; path = 0;
   }
-  if (use_i8) {
-    const int nch = i8_nchunks(c->d);
-    const size_t xb = i8_points_scratch_bytes(n, nch);
+  if (path != 0) {
     const size_t yb = static_cast<size_t>((n + 63) / 64) * 64 * sizeof(float);
-    if (xb > c->i8_xt_bytes) {
-      cudaFree(c->dI8Xt); c->dI8Xt = nullptr; c->i8_xt_bytes = 0;
-      SGP_CUDA(c, cudaMalloc(&c->dI8Xt, xb));
-      c->i8_xt_bytes = xb;
+    if (yb > c->i8_ys_bytes) {
+      cudaFree(c->dI8Ys); c->dI8Ys = nullptr; c->i8_ys_bytes = 0;
+      SGP_CUDA(c, cudaMalloc(&c->dI8Ys, yb));
+      c->i8_ys_bytes = yb;
     }
     if (c->i8_impl == 1) {
       rc = ctx_scratch(c, c->i8_share, i8_share_bytes(c->m_pad, plan_slices));
       if (rc != SGP_OK) return rc;
     }
-    if (yb > c->i8_ys_bytes) {
-      cudaFree(c->dI8Ys); c->dI8Ys = nullptr; c->i8_ys_bytes = 0;
-      SGP_CUDA(c, cudaMalloc(&c->dI8Ys, yb));
-      c->i8_ys_bytes = yb;
+  }
+  if (use_i8) {
+    const int nch = i8_nchunks(c->d);
+    const size_t xb = i8_points_scratch_bytes(n, nch);
+    if (xb > c->i8_xt_bytes) {
+      cudaFree(c->dI8Xt); c->dI8Xt = nullptr; c->i8_xt_bytes = 0;
+      SGP_CUDA(c, cudaMalloc(&c->dI8Xt, xb));
+      c->i8_xt_bytes = xb;
     }
     const bool gate = (c->precision == SGP_PREC_AUTO) && first_of_call;
     // the scaled squared norms of EVERY chunk are summed on the device (dI8NormSum[0]: whole begin..finish window,
@@ -159,12 +175,36 @@ static int launch_stats(Ctx* c, const void* dX, int x_is_f32, const double* dy, 
       double xsum = 0.0;
       SGP_CUDA(c, cudaMemcpyAsync(&xsum, c->dI8NormSum + 1, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
       SGP_CUDA(c, cudaStreamSynchronize(c->stream));
-      if (xsum / static_cast<double>(n) + c->i8_z_norm_mean > c->i8_norm_budget) use_i8 = false;
+      if (xsum / static_cast<double>(n) + c->i8_z_norm_mean > c->i8_norm_budget) {
+        use_i8 = false;
+        path = direct_ok ? 2 : 0;      // large norms: exponents from direct-form fp32 distances instead (no cancellation)
+      }
     }
   }
-  if (first_of_call) c->call_i8 = use_i8;
+  I8Direct direct;
+  if (path == 2) {
+    const size_t xb = static_cast<size_t>((n + 63) / 64) * c->kf.n_terms * 64 * c->i8_dpad4 * sizeof(float);
+    if (xb > c->i8_xt_bytes) {
+      cudaFree(c->dI8Xt); c->dI8Xt = nullptr; c->i8_xt_bytes = 0;
+      SGP_CUDA(c, cudaMalloc(&c->dI8Xt, xb));
+      c->i8_xt_bytes = xb;
+    }
+    SGP_CUDA(c, launch_i8_prep_points_direct(reinterpret_cast<float*>(c->dI8Xt), c->dI8Ys, dX, x_is_f32, dy, n, c->d,
+                                             c->i8_dpad4, c->kf.n_terms, c->dI8DScale,
+                                             c->dI8DScale + static_cast<size_t>(kMaxTerms) * c->i8_dpad4, c->dI8Flags,
+                                             c->i8_direct_r2max, c->stream));
+    c->launches += 1;
+    direct.on = 1; direct.n_terms = c->kf.n_terms; direct.dpad4 = c->i8_dpad4;
+    double csum = 0.0;
+    for (int t = 0; t < c->kf.n_terms; ++t) csum += c->kf.scale[t];
+    for (int t = 0; t < c->kf.n_terms; ++t) direct.w[t] = static_cast<float>(c->kf.scale[t] / csum);
+    direct.csum = csum;
+    c->i8_direct_used = true;
+  }
+  if (first_of_call) c->call_path = path;
   if (use_i8) { c->i8_used = true; c->i8_points += n; }
-  c->last_path = use_i8 ? SGP_PREC_I8 : (c->precision == SGP_PREC_F64_STRICT ? SGP_PREC_F64_STRICT : SGP_PREC_F64);
+  c->last_path = (path == 1) ? SGP_PREC_I8 : (path == 2) ? SGP_PREC_I8_DIRECT
+                 : (c->precision == SGP_PREC_F64_STRICT ? SGP_PREC_F64_STRICT : SGP_PREC_F64);
   if (c->gram_events_used == c->gram_events.size()) {          // grow the event pool (steady state: no creation)
     cudaEvent_t a, b;
     SGP_CUDA(c, cudaEventCreate(&a));
@@ -183,9 +223,10 @@ static int launch_stats(Ctx* c, const void* dX, int x_is_f32, const double* dy, 
     c->launches += 2;
     return SGP_OK;
   }
-  if (use_i8) {
+  if (use_i8 || path == 2) {
+    const uint8_t* zop = (path == 2) ? reinterpret_cast<const uint8_t*>(c->dI8Zd) : c->dI8Zt;
     for (int i = 0; i < n_plan; ++i) {
-      SGP_CUDA(c, launch_gram_i8_ring(c->dI8Xt, c->dI8Ys, c->dI8Zt, n, c->d, c->m_pad, plan[i], c->dGpart, c->dBpart,
+      SGP_CUDA(c, launch_gram_i8_ring(c->dI8Xt, c->dI8Ys, zop, n, c->d, c->m_pad, plan[i], direct, c->dGpart, c->dBpart,
                                  c->kf.scale[0], static_cast<uint8_t*>(c->i8_share.p), c->dbgT, c->dbgW, c->dbgClk,
                                  c->i8_pm_dev, c->stream));
       c->launches += 1;
@@ -302,7 +343,7 @@ const char* sgp_last_error(const sgp_ctx* h) {
 int sgp_set_precision(sgp_ctx* h, int mode) {
   Ctx* c = reinterpret_cast<Ctx*>(h);
   if (!c) return SGP_E_BADARG;
-  if (mode < SGP_PREC_F64 || mode > SGP_PREC_AUTO) return fail(c, SGP_E_BADARG, "unknown precision mode");
+  if (mode < SGP_PREC_F64 || mode > SGP_PREC_I8_DIRECT) return fail(c, SGP_E_BADARG, "unknown precision mode");
   c->precision = mode;
   return SGP_OK;
 }
@@ -389,6 +430,12 @@ int sgp_stats_begin(sgp_ctx* h, const sgp_kernel_desc* k, const double* Z, int32
   }
   // ---- tcgen05 int8 path: qualifies for one non-Eye term and d <= 32 (two 64-column K chunks) -------------
   c->i8_ok = (kf.n_terms == 1 && d <= 32);
+  if (!c->dI8Flags) {
+    SGP_CUDA(c, cudaMalloc(&c->dI8Flags, sizeof(int)));
+    SGP_CUDA(c, cudaMalloc(&c->dI8NormSum, 2 * sizeof(double)));
+  }
+  SGP_CUDA(c, cudaMemsetAsync(c->dI8Flags, 0, sizeof(int), c->stream));
+  SGP_CUDA(c, cudaMemsetAsync(c->dI8NormSum, 0, 2 * sizeof(double), c->stream));
   if (c->i8_ok) {
     const int dp16 = (d + 15) / 16 * 16;
     std::vector<double> sc(dp16, 0.0), ctr(dp16, 0.0);
@@ -402,8 +449,6 @@ int sgp_stats_begin(sgp_ctx* h, const sgp_kernel_desc* k, const double* Z, int32
     if (!c->dI8Scale) {
       SGP_CUDA(c, cudaMalloc(&c->dI8Scale, dp16 * 8));
       SGP_CUDA(c, cudaMalloc(&c->dI8Centre, dp16 * 8));
-      SGP_CUDA(c, cudaMalloc(&c->dI8Flags, sizeof(int)));
-      SGP_CUDA(c, cudaMalloc(&c->dI8NormSum, 2 * sizeof(double)));
       SGP_CUDA(c, cudaMalloc(&c->dI8Zt, i8_active_scratch_bytes(c->m_pad, i8_nchunks(d))));
     }
     {
@@ -418,13 +463,42 @@ int sgp_stats_begin(sgp_ctx* h, const sgp_kernel_desc* k, const double* Z, int32
     }
     SGP_CUDA(c, cudaMemcpyAsync(c->dI8Scale, sc.data(), dp16 * 8, cudaMemcpyHostToDevice, c->stream));
     SGP_CUDA(c, cudaMemcpyAsync(c->dI8Centre, ctr.data(), dp16 * 8, cudaMemcpyHostToDevice, c->stream));
-    SGP_CUDA(c, cudaMemsetAsync(c->dI8Flags, 0, sizeof(int), c->stream));
-    SGP_CUDA(c, cudaMemsetAsync(c->dI8NormSum, 0, 2 * sizeof(double), c->stream));
     SGP_CUDA(c, launch_i8_prep_active(c->dI8Zt, c->dZ, m, c->m_pad, d, c->dI8Scale, c->dI8Centre, c->dI8Flags,
                                       c->stream));
     c->launches += 1;
     SGP_CUDA(c, cudaStreamSynchronize(c->stream));               // sc / ctr are locals
   }
+  // ---- direct-distance mode of the int8 Gram: 1..4 non-Eye terms, n_terms * dpad4 <= 72 (smem), any norms ------------
+  {
+    const int dpad4 = (d + 3) & ~3;
+    c->i8_direct_ok = kf.n_terms >= 1 && kf.n_terms * dpad4 <= 72;
+    if (c->i8_direct_ok) {
+      c->i8_dpad4 = dpad4;
+      if (const char* e = getenv("SGP_I8_DIRECT_R2MAX")) c->i8_direct_r2max = static_cast<float>(atof(e));
+      std::vector<double> sc(static_cast<size_t>(kMaxTerms + 1) * dpad4, 0.0);      // [term][k] scales, then the centre
+      const double s2 = std::sqrt(1.4426950408889634074);
+      for (int t = 0; t < kf.n_terms; ++t)
+        for (int j = 0; j < d; ++j) sc[static_cast<size_t>(t) * dpad4 + j] = s2 * beta[static_cast<size_t>(t) * dpad + j];
+      for (int j = 0; j < d; ++j) {
+        double acc = 0.0;
+        for (int i = 0; i < m; ++i) acc += Z[static_cast<size_t>(i) * d + j];
+        sc[static_cast<size_t>(kMaxTerms) * dpad4 + j] = acc / m;
+      }
+      const size_t zd_bytes = static_cast<size_t>(c->m_pad / kTile) * kf.n_terms * kTile * dpad4 * sizeof(float);
+      if (!same_shape || !c->dI8Zd) {
+        cudaFree(c->dI8Zd); cudaFree(c->dI8DScale); c->dI8Zd = nullptr; c->dI8DScale = nullptr;
+        SGP_CUDA(c, cudaMalloc(&c->dI8Zd, zd_bytes));
+        SGP_CUDA(c, cudaMalloc(&c->dI8DScale, sc.size() * 8));
+      }
+      SGP_CUDA(c, cudaMemcpyAsync(c->dI8DScale, sc.data(), sc.size() * 8, cudaMemcpyHostToDevice, c->stream));
+      SGP_CUDA(c, launch_i8_prep_active_direct(c->dI8Zd, c->dZ, m, c->m_pad, d, dpad4, kf.n_terms, c->dI8DScale,
+                                               c->dI8DScale + static_cast<size_t>(kMaxTerms) * dpad4, c->dI8Flags,
+                                               c->i8_direct_r2max, c->stream));
+      c->launches += 1;
+      SGP_CUDA(c, cudaStreamSynchronize(c->stream));             // sc is a local
+    }
+  }
+  c->i8_direct_used = false;
   SGP_CUDA(c, cudaStreamSynchronize(c->stream));   // Z / beta are host temporaries of the caller
   c->gram_events_used = 0;
   c->i8_points = 0;
@@ -505,9 +579,10 @@ int sgp_stats_finish(sgp_ctx* h, double* G_out, double* b_out) {
     // buffer: every rank sees the same sum and takes the same return decision AFTER the collective -- a rank that
     // bailed out before it would leave its peers blocked in ncclAllReduce.
     const bool i8 = c->i8_ok && c->i8_used && c->dI8Flags;
+    const bool i8d = c->i8_direct_used && c->dI8Flags;          // direct mode: bit 2 = scaled squared norm above its limit
     const bool budget = i8 && c->precision == SGP_PREC_AUTO;
     const double limit = (c->i8_norm_budget - c->i8_z_norm_mean) * static_cast<double>(c->i8_points) * 1.25;
-    SGP_CUDA(c, launch_status_to_double(c->dGb + mm + c->m, i8 ? c->dI8Flags : nullptr, 1,
+    SGP_CUDA(c, launch_status_to_double(c->dGb + mm + c->m, (i8 || i8d) ? c->dI8Flags : nullptr, (i8 ? 1 : 0) | (i8d ? 4 : 0),
                                         budget ? c->dI8NormSum : nullptr, limit, c->stream));
     c->launches += 1;
     if (c->comm && c->nranks > 1) {
@@ -524,9 +599,10 @@ int sgp_stats_finish(sgp_ctx* h, double* G_out, double* b_out) {
     SGP_CUDA(c, cudaMemcpyAsync(b_out, c->dGb + mm, static_cast<size_t>(c->m) * 8, cudaMemcpyDeviceToHost, c->stream));
   SGP_CUDA(c, cudaStreamSynchronize(c->stream));
   if (status != 0.0)
-    return fail(c, SGP_E_RANGE, "SGP_PREC_I8 cannot represent this shard on some rank (scaled coordinates outside the "
-                                "fp16 operand range, or scaled squared norms above AUTO's magnitude budget); "
-                                "rerun the statistics with sgp_set_precision(SGP_PREC_F64)");
+    return fail(c, SGP_E_RANGE, "the int8 path cannot represent this shard on some rank (scaled coordinates outside the "
+                                "fp16 operand range, scaled squared norms above AUTO's magnitude budget for tensor-core "
+                                "distances, or above the fp32 direct-distance limit); rerun the statistics with "
+                                "sgp_set_precision(SGP_PREC_I8_DIRECT) or sgp_set_precision(SGP_PREC_F64)");
   return SGP_OK;
 }
 

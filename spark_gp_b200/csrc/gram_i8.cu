@@ -314,6 +314,64 @@ __global__ void prep_active_kernel(uint8_t* __restrict__ Zt, const double* __res
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Operand preparation for the DIRECT-distance mode of the ring kernel (gram_i8_ring.cu): fp32 coordinate tiles, centred
+// on the active-set mean and pre-scaled per kernel term by sqrt(log2 e) * beta_tk, so that the epilogue's direct-form
+// sum_k (x~_k - z~_k)^2 is the base-2 exponent.  Points: [unit][term][dpad4][64]; active set: [tile][term][dpad4][128 rows,
+// permuted], stored NEGATED (the inner loop adds).  Padding points carry +inf on coordinate 0: their kernel values are 0.
+// ---------------------------------------------------------------------------------------------------
+__global__ void prep_points_direct_kernel(float* __restrict__ Xd, float* __restrict__ ys, const void* __restrict__ X,
+                                          int x_is_f32, const double* __restrict__ y, long long n, long long n_units, int d,
+                                          int dpad4, int n_terms, const double* __restrict__ scale /*[n_terms][dpad4]*/,
+                                          const double* __restrict__ centre /*[dpad4]*/, int* __restrict__ flags,
+                                          float r2max) {
+  const long long pt = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (pt >= n_units * UP) return;
+  const bool valid = pt < n;
+  const long long unit = pt / UP;
+  const int pp = static_cast<int>(pt % UP);
+  float r2[kMaxTerms] = {0.f, 0.f, 0.f, 0.f};
+  for (int k = 0; k < dpad4; ++k) {
+    double x = 0.0;
+    if (valid && k < d) {
+      const size_t off = static_cast<size_t>(pt) * d + k;
+      x = (x_is_f32 ? static_cast<double>(reinterpret_cast<const float*>(X)[off]) : reinterpret_cast<const double*>(X)[off]) -
+          centre[k];
+    }
+    for (int t = 0; t < n_terms; ++t) {
+      float v = static_cast<float>(x * scale[t * dpad4 + k]);
+      r2[t] = fmaf(v, v, r2[t]);
+      if (!valid) v = (k == 0) ? __int_as_float(0x7f800000) : 0.f;     // +inf: kernel value exactly 0 against any active row
+      Xd[((static_cast<size_t>(unit) * n_terms + t) * dpad4 + k) * UP + pp] = v;
+    }
+  }
+  // fp32 coordinates: the exponent's rounding error grows like 2^-24 * sqrt(q) * (|x~| + |z~|)
+  if (valid && !(fmaxf(fmaxf(r2[0], r2[1]), fmaxf(r2[2], r2[3])) <= r2max)) atomicOr(flags, 4);
+  if (ys) ys[pt] = (valid && y) ? static_cast<float>(y[pt]) : 0.f;
+}
+
+__global__ void prep_active_direct_kernel(float* __restrict__ Zd, const double* __restrict__ Z, int m, int m_pad, int d,
+                                          int dpad4, int n_terms, const double* __restrict__ scale,
+                                          const double* __restrict__ centre, int* __restrict__ flags, float r2max) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= m_pad) return;
+  const bool valid = j < m;
+  const int tile = j / kTile, r = j % kTile;
+  // the kernel's register tile: a thread owns rows r0, r0+8, r0+16, r0+24 of a 32-row block -> those four are adjacent
+  const int rp = (r & ~31) + 4 * (r & 7) + ((r >> 3) & 3);
+  for (int t = 0; t < n_terms; ++t) {
+    float* col = Zd + (static_cast<size_t>(tile) * n_terms + t) * dpad4 * kTile + rp;
+    float r2 = 0.f;
+    for (int k = 0; k < dpad4; ++k) {
+      float v = 0.f;
+      if (valid && k < d) v = -static_cast<float>((Z[static_cast<size_t>(j) * d + k] - centre[k]) * scale[t * dpad4 + k]);
+      r2 = fmaf(v, v, r2);
+      col[static_cast<size_t>(k) * kTile] = v;                   // padding rows: zeros (their Gram rows are never read)
+    }
+    if (valid && !(r2 <= r2max)) atomicOr(flags, 4);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // The fused kernel
 // ---------------------------------------------------------------------------------------------------
 struct I8Params {
@@ -722,6 +780,24 @@ cudaError_t launch_i8_prep_points(uint8_t* Xt, float* ys, const void* dX, int x_
   prep_points_kernel<<<static_cast<unsigned>((threads + 127) / 128), 128, 0, s>>>(Xt, ys, dX, x_is_f32, dy, n, units, d, dp,
                                                                                 i8_nchunks(d), dScale, dCentre, dFlags,
                                                                                 dNormSum, dNormSumCall);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_i8_prep_active_direct(float* Zd, const double* dZ, int m, int m_pad, int d, int dpad4, int n_terms,
+                                         const double* dScale, const double* dCentre, int* flags, float r2max,
+                                         cudaStream_t s) {
+  prep_active_direct_kernel<<<(m_pad + 127) / 128, 128, 0, s>>>(Zd, dZ, m, m_pad, d, dpad4, n_terms, dScale, dCentre, flags,
+                                                                r2max);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_i8_prep_points_direct(float* Xd, float* ys, const void* dX, int x_is_f32, const double* dy, long long n,
+                                         int d, int dpad4, int n_terms, const double* dScale, const double* dCentre, int* flags,
+                                         float r2max, cudaStream_t s) {
+  const long long units = (n + UP - 1) / UP;
+  const long long threads = units * UP;
+  prep_points_direct_kernel<<<static_cast<unsigned>((threads + 127) / 128), 128, 0, s>>>(Xd, ys, dX, x_is_f32, dy, n, units, d,
+                                                                                       dpad4, n_terms, dScale, dCentre, flags, r2max);
   return cudaGetLastError();
 }
 

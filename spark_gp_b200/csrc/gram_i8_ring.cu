@@ -194,6 +194,11 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8])
                ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                : "memory");
 }
+// 16 lanes x 256 bits: thread t holds (row t/4, 32-bit columns 2(t%4), 2(t%4)+1) in r0, r1 and (row t/4 + 8, same columns) in r2, r3
+__device__ __forceinline__ void tmem_st_16x256b(uint32_t taddr, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3) {
+  asm volatile("tcgen05.st.sync.aligned.16x256b.x1.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(r0), "r"(r1), "r"(r2), "r"(r3)
+               : "memory");
+}
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
@@ -262,6 +267,14 @@ struct I8Params {
   const uint8_t* Zt;    // [n_tiles_1d][nchunks][16384]
   long long n_units;
   int nchunks;          // 64-column K chunks of the distance contraction (1 or 2)
+  // generic sizes of the operand staging (tensor-distance mode: fp16 images; direct mode: fp32 coordinate tiles)
+  uint32_t xbytes;      // bytes of one 64-point unit of the point operand
+  uint32_t zbytes;      // bytes of one active tile of the active-set operand
+  // direct-distance mode (template DIRECT): exponents from fp32 direct-form distances on the CUDA cores -- any norms, up to 4
+  // non-Eye terms.  Xt = [n_units][n_terms][64][dpad4] fp32, Zt = [n_tiles_1d][n_terms][128][dpad4 + 4] fp32, coordinates
+  // centred and pre-scaled by sqrt(log2 e) * beta_t
+  int n_terms, dpad4;
+  float w[4];           // term weights C_t / sum_t C_t (the fixed-point scale is the sum)
   int xstages;          // operand ring depth
   int npj;              // panel-J ring depth (<= NPJ_MAX)
   int ksteps_last;      // 16-column k-steps used in the last chunk
@@ -323,7 +336,7 @@ __device__ __forceinline__ void spin_guard(long long& t0, unsigned& it, I8PostMo
   if ((++it & 0x3FFu) == 0 && clock64() - t0 > 2000000000LL) i8_die(pm, code, unit, a, b);
 }
 
-template <bool DBG>
+template <bool DBG, bool DIRECT>
 __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_ring_kernel(const I8Params p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -334,8 +347,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_ring_kernel(const I8P
   // (slots: a diagonal CTA keeps its own panel I here -- 4 slots, B operand + publishing; an off-diagonal CTA keeps panel J
   //  here -- npj slots; panel I of an off-diagonal CTA lives only in tensor memory)
   const uint32_t s_zt = s_slot + (p.npj > NPI_PUB ? p.npj : NPI_PUB) * SLOT_BYTES;   // [nchunks][16384]  active tile I, fp16
-  const uint32_t s_xs = s_zt + p.nchunks * ZPANEL_BYTES;                  // [xstages][nchunks][8192]  point images, fp16
-  const uint32_t s_ys = s_xs + p.xstages * p.nchunks * XIMG_BYTES;        // [YSTAGES][64] float
+  const uint32_t s_xs = s_zt + p.zbytes;                                  // [xstages][xbytes]         point operand ring
+  const uint32_t s_ys = s_xs + p.xstages * p.xbytes;                      // [YSTAGES][64] float
   const uint32_t s_bred = s_ys + YSTAGES * UP * 4;                        // [4][128] double
   const uint32_t s_bar = s_bred + 4 * 128 * 8;                            // mbarriers
   const uint32_t b_xfull = s_bar, b_xempty = b_xfull + 8 * XSTAGES_MAX, b_qfull = b_xempty + 8 * XSTAGES_MAX,
@@ -380,7 +393,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_ring_kernel(const I8P
 
   // ---- one-time setup -------------------------------------------------------------------------------
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < XSTAGES_MAX; ++s) { mbar_init(b_xfull + 8 * s, 1); mbar_init(b_xempty + 8 * s, 1); }
+    // a point stage is released by the distance MMAs' commit (tensor mode) or by the 8 epilogue warps that read it (direct)
+    for (int s = 0; s < XSTAGES_MAX; ++s) { mbar_init(b_xfull + 8 * s, 1); mbar_init(b_xempty + 8 * s, DIRECT ? EPI_WARPS / 2 : 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(b_qfull + 8 * i, 1); mbar_init(b_qempty + 8 * i, EPI_WARPS / 2); }
     for (int i = 0; i < NPI_PUB; ++i) {
       mbar_init(b_pifull + 8 * i, EPI_WARPS / 2);
@@ -403,10 +417,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_ring_kernel(const I8P
   if (warp == 0) {
     // ================= producer: bulk copies of the fp16 operand images =================================
     if (lane == 0) {
-      mbar_expect_tx(b_zfull, static_cast<uint32_t>(p.nchunks * ZPANEL_BYTES));
-      bulk_g2s(s_zt, p.Zt + static_cast<size_t>(ti) * p.nchunks * ZPANEL_BYTES,
-               static_cast<uint32_t>(p.nchunks * ZPANEL_BYTES), b_zfull);
-      const uint32_t xbytes = static_cast<uint32_t>(p.nchunks * XIMG_BYTES);
+      mbar_expect_tx(b_zfull, p.zbytes);
+      bulk_g2s(s_zt, p.Zt + static_cast<size_t>(ti) * p.zbytes, p.zbytes, b_zfull);
+      const uint32_t xbytes = p.xbytes;
       uint32_t s = 0, e_phase = 1;      // parity of the x_empty completion to wait for (first lap: none)
       constexpr int PF = 24;               // units of X images kept warm in L2 ahead of the copies (HBM latency cover)
       for (long long i = 0; i < PF && i < nu; ++i)
@@ -436,7 +449,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_ring_kernel(const I8P
     constexpr uint32_t DESC_HI64 = 32u | (1u << 14) | (4u << 29);    // SBO =  512 B, version 1, SWIZZLE_64B
     auto lo_of = [](uint32_t addr) { return ((addr & 0x3FFFFu) >> 4) | (1u << 16); };
 
-    if (warp == 1) {
+    if (warp == 1 && DIRECT) {
+      // direct mode: the epilogue warps compute the exponents themselves from the fp32 tiles; no distance MMAs
+    } else if (warp == 1) {
       // ---------------- distance tile of panel I: T[128 active x 64 points] per unit ---------------------------------
       auto D = [](uint32_t lo) { return (static_cast<uint64_t>(DESC_HI128) << 32) | lo; };
       constexpr uint32_t SL = ZPANEL_BYTES >> 4;
@@ -651,6 +666,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_ring_kernel(const I8P
     const uint32_t q_taddr = tmem + lane_bits + TM_Q0 + ch * 32;
     const uint32_t a_taddr = tmem + lane_bits + TM_A0 + ch * A_KS_COLS;      // this warp's 32 points = k-step `ch`
     double bsum = 0.0;
+    [[maybe_unused]] double bs4[4] = {0.0, 0.0, 0.0, 0.0};     // direct mode: partial b of this thread's 4 rows
     uint32_t flush_idx = 0, q_phase = 0;
     int until_flush = p.flush_units;
     bool first_flush = true;
@@ -665,89 +681,204 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_ring_kernel(const I8P
         // ---- one distance tile (128 active rows x 64 points) -> three int8 digit planes of unit i ---------------
         const bool tle = (ew & 7) == 0;
         if (tle) SGP_TL(2 + grp, i, 0);
-        if (!q_ready) MBAR_WAIT(b_qfull + 8 * grp, q_phase, 9, i);
-        if (tle) SGP_TL(2 + grp, i, 1);
-        q_phase ^= 1;
-        tc_fence_after();
-        uint32_t T[32];
-        tmem_ld32(q_taddr, T);
-        tmem_wait_ld();
-        if (tle) SGP_TL(2 + grp, i, 2);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(b_qempty + 8 * grp);
-        if (DBG && dbg && i == 0) {
-          for (int k = 0; k < 32; ++k) p.dbg_T[L * UP + ch * 32 + k] = __uint_as_float(T[k]);
-        }
-        // kappa = 2^T ; fixed point: (mantissa(kappa*C0 + MAGIC) << 1) has the digit bytes (2 s0 + 128, s1 + 128, s2)
-        if (diag) {
-          const float4* yv = reinterpret_cast<const float4*>(sm_ys + static_cast<int>(i & (YSTAGES - 1)) * UP + ch * 32);
-          float b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;        // four independent chains (a single one serialised 32 FFMAs)
-#pragma unroll
+        if constexpr (!DIRECT) {
+          uint32_t T[32];
+          {
+            if (!q_ready) MBAR_WAIT(b_qfull + 8 * grp, q_phase, 9, i);
+            if (tle) SGP_TL(2 + grp, i, 1);
+            q_phase ^= 1;
+            tc_fence_after();
+            tmem_ld32(q_taddr, T);
+            tmem_wait_ld();
+            if (tle) SGP_TL(2 + grp, i, 2);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(b_qempty + 8 * grp);
+            if (DBG && dbg && i == 0) {
+              for (int k = 0; k < 32; ++k) p.dbg_T[L * UP + ch * 32 + k] = __uint_as_float(T[k]);
+            }
+            // kappa = 2^T ; fixed point: (mantissa(kappa*C0 + MAGIC) << 1) has the digit bytes (2 s0 + 128, s1 + 128, s2)
+            if (diag) {
+              const float4* yv = reinterpret_cast<const float4*>(sm_ys + static_cast<int>(i & (YSTAGES - 1)) * UP + ch * 32);
+              float b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;        // four independent chains (a single one serialised 32 FFMAs)
+  #pragma unroll
+              for (int g = 0; g < 8; ++g) {
+                const float4 y4 = yv[g];
+                const float e0 = ex2f(__uint_as_float(T[4 * g + 0])), e1 = ex2f(__uint_as_float(T[4 * g + 1])),
+                            e2 = ex2f(__uint_as_float(T[4 * g + 2])), e3 = ex2f(__uint_as_float(T[4 * g + 3]));
+                b0 = fmaf(e0, y4.x, b0); b1 = fmaf(e1, y4.y, b1);
+                b2 = fmaf(e2, y4.z, b2); b3 = fmaf(e3, y4.w, b3);
+                T[4 * g + 0] = fixed_word(e0); T[4 * g + 1] = fixed_word(e1);
+                T[4 * g + 2] = fixed_word(e2); T[4 * g + 3] = fixed_word(e3);
+              }
+              bsum += static_cast<double>((b0 + b1) + (b2 + b3));
+            } else {
+  #pragma unroll
+              for (int k = 0; k < 32; ++k) T[k] = fixed_word(ex2f(__uint_as_float(T[k])));
+            }
+          }
+          if (DBG && dbg && i == 0) {
+            for (int k = 0; k < 32; ++k) p.dbg_w[L * UP + ch * 32 + k] = T[k] >> 1;     // the fp32 word (sign bit is 0)
+          }
+          if (tle) SGP_TL(2 + grp, i, 3);
+          // byte planes: 4 consecutive points -> one word per digit, 32 points -> 8 words per digit = one k-step of A
+          uint32_t d0[8], d1[8], d2[8];
+  #pragma unroll
           for (int g = 0; g < 8; ++g) {
-            const float4 y4 = yv[g];
-            const float e0 = ex2f(__uint_as_float(T[4 * g + 0])), e1 = ex2f(__uint_as_float(T[4 * g + 1])),
-                        e2 = ex2f(__uint_as_float(T[4 * g + 2])), e3 = ex2f(__uint_as_float(T[4 * g + 3]));
-            b0 = fmaf(e0, y4.x, b0); b1 = fmaf(e1, y4.y, b1);
-            b2 = fmaf(e2, y4.z, b2); b3 = fmaf(e3, y4.w, b3);
-            T[4 * g + 0] = fixed_word(e0); T[4 * g + 1] = fixed_word(e1);
-            T[4 * g + 2] = fixed_word(e2); T[4 * g + 3] = fixed_word(e3);
+            const uint32_t w0 = T[g * 4 + 0], w1 = T[g * 4 + 1], w2 = T[g * 4 + 2], w3 = T[g * 4 + 3];
+            const uint32_t t01 = prmt(w0, w1, 0x5140), t23 = prmt(w2, w3, 0x5140);
+            d0[g] = prmt(t01, t23, 0x5410) ^ 0x80808080u;     // P0 = 2 s0 = byte0 - 128 (two's complement)
+            d1[g] = prmt(t01, t23, 0x7632) ^ 0x80808080u;     // P1 = s1 = byte1 - 128
+            const uint32_t u01 = prmt(w0, w1, 0x0062), u23 = prmt(w2, w3, 0x0062);
+            d2[g] = prmt(u01, u23, 0x5410);                   // P2 = s2 = byte2 (0..255, unsigned operand)
           }
-          bsum += static_cast<double>((b0 + b1) + (b2 + b3));
-        } else {
-#pragma unroll
-          for (int k = 0; k < 32; ++k) T[k] = fixed_word(ex2f(__uint_as_float(T[k])));
-        }
-        if (DBG && dbg && i == 0) {
-          for (int k = 0; k < 32; ++k) p.dbg_w[L * UP + ch * 32 + k] = T[k] >> 1;     // the fp32 word (sign bit is 0)
-        }
-        if (tle) SGP_TL(2 + grp, i, 3);
-        // byte planes: 4 consecutive points -> one word per digit, 32 points -> 8 words per digit = one k-step of A
-        uint32_t d0[8], d1[8], d2[8];
-#pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          const uint32_t w0 = T[g * 4 + 0], w1 = T[g * 4 + 1], w2 = T[g * 4 + 2], w3 = T[g * 4 + 3];
-          const uint32_t t01 = prmt(w0, w1, 0x5140), t23 = prmt(w2, w3, 0x5140);
-          d0[g] = prmt(t01, t23, 0x5410) ^ 0x80808080u;     // P0 = 2 s0 = byte0 - 128 (two's complement)
-          d1[g] = prmt(t01, t23, 0x7632) ^ 0x80808080u;     // P1 = s1 = byte1 - 128
-          const uint32_t u01 = prmt(w0, w1, 0x0062), u23 = prmt(w2, w3, 0x0062);
-          d2[g] = prmt(u01, u23, 0x5410);                   // P2 = s2 = byte2 (0..255, unsigned operand)
-        }
-        if (diag) {
-          // the diagonal tile also needs its panel as the B operand (and publishes it): K-major SWIZZLE_64B image in smem,
-          // written BEFORE the wait for the A columns so that pi_full (B side, publisher) is never behind a_full.
-          // unit i lives in slot i % 4; before overwriting it the Gram MMAs of unit i - 4 (and, on a publishing CTA,
-          // the bulk store that shipped it) must have drained: completion (i / 4 - 1) of pi_empty[slot]
-          const uint32_t si = static_cast<uint32_t>(i) & static_cast<uint32_t>(npi - 1);
-          if (i >= npi) MBAR_WAIT(b_piempty + 8 * si, static_cast<uint32_t>(((i >> npi_shift) - 1) & 1), 15, i);
-          uint8_t* const slot = sm + si * SLOT_BYTES;
-#pragma unroll
-          for (int g16 = 0; g16 < 2; ++g16) {
-            uint8_t* dst = slot + sw64_off(L, ch * 2 + g16);
-            *reinterpret_cast<uint4*>(dst + 0 * PLANE_BYTES) = make_uint4(d0[4 * g16], d0[4 * g16 + 1], d0[4 * g16 + 2], d0[4 * g16 + 3]);
-            *reinterpret_cast<uint4*>(dst + 1 * PLANE_BYTES) = make_uint4(d1[4 * g16], d1[4 * g16 + 1], d1[4 * g16 + 2], d1[4 * g16 + 3]);
-            *reinterpret_cast<uint4*>(dst + 2 * PLANE_BYTES) = make_uint4(d2[4 * g16], d2[4 * g16 + 1], d2[4 * g16 + 2], d2[4 * g16 + 3]);
+          if (diag) {
+            // the diagonal tile also needs its panel as the B operand (and publishes it): K-major SWIZZLE_64B image in smem,
+            // written BEFORE the wait for the A columns so that pi_full (B side, publisher) is never behind a_full.
+            // unit i lives in slot i % 4; before overwriting it the Gram MMAs of unit i - 4 (and, on a publishing CTA,
+            // the bulk store that shipped it) must have drained: completion (i / 4 - 1) of pi_empty[slot]
+            const uint32_t si = static_cast<uint32_t>(i) & static_cast<uint32_t>(npi - 1);
+            if (i >= npi) MBAR_WAIT(b_piempty + 8 * si, static_cast<uint32_t>(((i >> npi_shift) - 1) & 1), 15, i);
+            uint8_t* const slot = sm + si * SLOT_BYTES;
+  #pragma unroll
+            for (int g16 = 0; g16 < 2; ++g16) {
+              uint8_t* dst = slot + sw64_off(L, ch * 2 + g16);
+              *reinterpret_cast<uint4*>(dst + 0 * PLANE_BYTES) = make_uint4(d0[4 * g16], d0[4 * g16 + 1], d0[4 * g16 + 2], d0[4 * g16 + 3]);
+              *reinterpret_cast<uint4*>(dst + 1 * PLANE_BYTES) = make_uint4(d1[4 * g16], d1[4 * g16 + 1], d1[4 * g16 + 2], d1[4 * g16 + 3]);
+              *reinterpret_cast<uint4*>(dst + 2 * PLANE_BYTES) = make_uint4(d2[4 * g16], d2[4 * g16 + 1], d2[4 * g16 + 2], d2[4 * g16 + 3]);
+            }
+            // generic-proxy plane writes -> visible to the tensor core / bulk copy (async proxy).  The fence costs 400-600 clk
+            // of this warp; it sits BEFORE the wait for the A columns, which would idle anyway (tried: after the A store
+            // 1600 clk per unit, deferred into the next tile's TMEM load 2130 -- the Gram issuer then waits for pi_full)
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(b_pifull + 8 * si);
           }
-          // generic-proxy plane writes -> visible to the tensor core / bulk copy (async proxy).  The fence costs 400-600 clk
-          // of this warp; it sits BEFORE the wait for the A columns, which would idle anyway (tried: after the A store
-          // 1600 clk per unit, deferred into the next tile's TMEM load 2130 -- the Gram issuer then waits for pi_full)
-          fence_proxy_async();
+          if (tle) SGP_TL(2 + grp, i, 4);
+          // A operand: straight into tensor memory once the Gram MMAs of the previous unit's k-step `ch` have drained
+          // (barriers are split by unit parity so that a group, which sees only every other unit, never lags a phase)
+          if (i >= 1) MBAR_WAIT(b_aempty + 8 * (2 * ch + (grp ^ 1)), static_cast<uint32_t>(((i - 1) >> 1) & 1), 10, i);
+          tc_fence_after();
+          tmem_st8(a_taddr + 0, d0);
+          tmem_st8(a_taddr + 8, d1);
+          tmem_st8(a_taddr + 16, d2);
+          tmem_wait_st();
+          tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(b_pifull + 8 * si);
+          if (lane == 0) mbar_arrive(b_afull + 8 * (2 * ch + grp));
+          q_ready = mbar_test(b_qfull + 8 * grp, q_phase);     // next tile of this group
+        } else {
+          // ---- direct mode: kappa = sum_t w_t 2^(-|x~_t - z~_t|^2) from fp32 direct-form distances (no cancellation: any
+          // norms).  Register tile 4 rows x 8 points per thread, the fragment of tcgen05.st.16x256b: rows
+          // lq*32 + lane/4 + {0,8,16,24}, points ch*32 + 8*(lane%4) + 0..7; packed f32x2 arithmetic over point pairs with
+          // the active-set coordinate as the scalar (broadcast) operand of FADD2.  Shared-memory traffic 48 B per thread
+          // and dimension (a row-per-thread tile moved 132 B and ran at the LDS port's 128 B/clk: 4950 clk per unit) ----------
+          const int c4 = lane & 3, r8 = lane >> 2;
+          const uint32_t xs_stage = static_cast<uint32_t>(i % p.xstages);
+          MBAR_WAIT(b_xfull + 8 * xs_stage, static_cast<uint32_t>((i / p.xstages) & 1), 9, i);
+          if (tle) SGP_TL(2 + grp, i, 1);
+          const float* xs0 = reinterpret_cast<const float*>(sm + (s_xs - base) + xs_stage * p.xbytes) + ch * 32 + 8 * c4;
+          const float* zs0 = reinterpret_cast<const float*>(sm + (s_zt - base)) + lq * 32 + 4 * r8;
+          float kap[32];                                   // kap[j * 8 + pt]
+          for (int t = 0; t < p.n_terms; ++t) {
+            const float* zt = zs0 + t * p.dpad4 * kTile;   // [k][128 rows, permuted so that this thread's 4 rows are adjacent]
+            const float* xt = xs0 + t * p.dpad4 * UP;      // [k][64 points]
+            float2 q[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) q[e] = make_float2(0.f, 0.f);
+#pragma unroll 4
+            for (int k = 0; k < p.dpad4; ++k) {
+              const float4 z = *reinterpret_cast<const float4*>(zt + k * kTile);     // stored negated
+              const float4 xa = *reinterpret_cast<const float4*>(xt + k * UP), xb = *reinterpret_cast<const float4*>(xt + k * UP + 4);
+              const float2 x0 = make_float2(xa.x, xa.y), x1 = make_float2(xa.z, xa.w), x2 = make_float2(xb.x, xb.y),
+                           x3 = make_float2(xb.z, xb.w);
+              const float zj[4] = {z.x, z.y, z.z, z.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 zb = make_float2(zj[j], zj[j]);
+                const float2 e0 = __fadd2_rn(x0, zb), e1 = __fadd2_rn(x1, zb), e2 = __fadd2_rn(x2, zb), e3 = __fadd2_rn(x3, zb);
+                q[4 * j + 0] = __ffma2_rn(e0, e0, q[4 * j + 0]);
+                q[4 * j + 1] = __ffma2_rn(e1, e1, q[4 * j + 1]);
+                q[4 * j + 2] = __ffma2_rn(e2, e2, q[4 * j + 2]);
+                q[4 * j + 3] = __ffma2_rn(e3, e3, q[4 * j + 3]);
+              }
+            }
+            const float wt = p.w[t];
+            if (t == 0) {
+#pragma unroll
+              for (int e = 0; e < 16; ++e) { kap[2 * e] = wt * ex2f(-q[e].x); kap[2 * e + 1] = wt * ex2f(-q[e].y); }
+            } else {
+#pragma unroll
+              for (int e = 0; e < 16; ++e) {
+                kap[2 * e] = fmaf(wt, ex2f(-q[e].x), kap[2 * e]);
+                kap[2 * e + 1] = fmaf(wt, ex2f(-q[e].y), kap[2 * e + 1]);
+              }
+            }
+          }
+          if (tle) SGP_TL(2 + grp, i, 2);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(b_xempty + 8 * xs_stage);        // this warp is done with the point tile
+          if (diag) {
+            const float* yv = sm_ys + static_cast<int>(i & (YSTAGES - 1)) * UP + ch * 32 + 8 * c4;
+            const float4 ya = *reinterpret_cast<const float4*>(yv), yb = *reinterpret_cast<const float4*>(yv + 4);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float s0 = fmaf(kap[8 * j + 0], ya.x, kap[8 * j + 1] * ya.y), s1 = fmaf(kap[8 * j + 2], ya.z, kap[8 * j + 3] * ya.w),
+                          s2 = fmaf(kap[8 * j + 4], yb.x, kap[8 * j + 5] * yb.y), s3 = fmaf(kap[8 * j + 6], yb.z, kap[8 * j + 7] * yb.w);
+              bs4[j] += static_cast<double>((s0 + s1) + (s2 + s3));
+            }
+          }
+          if (DBG && dbg && i == 0) {
+            for (int j = 0; j < 4; ++j)
+              for (int e = 0; e < 8; ++e)
+                p.dbg_w[(lq * 32 + r8 + 8 * j) * UP + ch * 32 + 8 * c4 + e] = fixed_word(kap[8 * j + e]) >> 1;
+          }
+          if (tle) SGP_TL(2 + grp, i, 3);
+          // digit planes: word h of row j = points 4h .. 4h+3
+          uint32_t D0[4][2], D1[4][2], D2[4][2];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const uint32_t w0 = fixed_word(kap[8 * j + 4 * h + 0]), w1 = fixed_word(kap[8 * j + 4 * h + 1]),
+                             w2 = fixed_word(kap[8 * j + 4 * h + 2]), w3 = fixed_word(kap[8 * j + 4 * h + 3]);
+              const uint32_t t01 = prmt(w0, w1, 0x5140), t23 = prmt(w2, w3, 0x5140);
+              D0[j][h] = prmt(t01, t23, 0x5410) ^ 0x80808080u;
+              D1[j][h] = prmt(t01, t23, 0x7632) ^ 0x80808080u;
+              const uint32_t u01 = prmt(w0, w1, 0x0062), u23 = prmt(w2, w3, 0x0062);
+              D2[j][h] = prmt(u01, u23, 0x5410);
+            }
+          }
+          if (diag) {
+            const uint32_t si = static_cast<uint32_t>(i) & static_cast<uint32_t>(npi - 1);
+            if (i >= npi) MBAR_WAIT(b_piempty + 8 * si, static_cast<uint32_t>(((i >> npi_shift) - 1) & 1), 15, i);
+            uint8_t* const slot = sm + si * SLOT_BYTES;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint8_t* dst = slot + sw64_off(lq * 32 + r8 + 8 * j, ch * 2 + (c4 >> 1)) + (c4 & 1) * 8;
+              *reinterpret_cast<uint2*>(dst + 0 * PLANE_BYTES) = make_uint2(D0[j][0], D0[j][1]);
+              *reinterpret_cast<uint2*>(dst + 1 * PLANE_BYTES) = make_uint2(D1[j][0], D1[j][1]);
+              *reinterpret_cast<uint2*>(dst + 2 * PLANE_BYTES) = make_uint2(D2[j][0], D2[j][1]);
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(b_pifull + 8 * si);
+          }
+          if (tle) SGP_TL(2 + grp, i, 4);
+          if (i >= 1) MBAR_WAIT(b_aempty + 8 * (2 * ch + (grp ^ 1)), static_cast<uint32_t>(((i - 1) >> 1) & 1), 10, i);
+          tc_fence_after();
+          tmem_st_16x256b(a_taddr + 0, D0[0][0], D0[0][1], D0[1][0], D0[1][1]);
+          tmem_st_16x256b(a_taddr + 8, D1[0][0], D1[0][1], D1[1][0], D1[1][1]);
+          tmem_st_16x256b(a_taddr + 16, D2[0][0], D2[0][1], D2[1][0], D2[1][1]);
+          tmem_st_16x256b(a_taddr + (16u << 16) + 0, D0[2][0], D0[2][1], D0[3][0], D0[3][1]);
+          tmem_st_16x256b(a_taddr + (16u << 16) + 8, D1[2][0], D1[2][1], D1[3][0], D1[3][1]);
+          tmem_st_16x256b(a_taddr + (16u << 16) + 16, D2[2][0], D2[2][1], D2[3][0], D2[3][1]);
+          tmem_wait_st();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(b_afull + 8 * (2 * ch + grp));
+          if (tle) SGP_TL(2 + grp, i, 5);
         }
-        if (tle) SGP_TL(2 + grp, i, 4);
-        // A operand: straight into tensor memory once the Gram MMAs of the previous unit's k-step `ch` have drained
-        // (barriers are split by unit parity so that a group, which sees only every other unit, never lags a phase)
-        if (i >= 1) MBAR_WAIT(b_aempty + 8 * (2 * ch + (grp ^ 1)), static_cast<uint32_t>(((i - 1) >> 1) & 1), 10, i);
-        tc_fence_after();
-        tmem_st8(a_taddr + 0, d0);
-        tmem_st8(a_taddr + 8, d1);
-        tmem_st8(a_taddr + 16, d2);
-        tmem_wait_st();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(b_afull + 8 * (2 * ch + grp));
-        q_ready = mbar_test(b_qfull + 8 * grp, q_phase);     // next tile of this group
         if (tle) SGP_TL(2 + grp, i, 5);
       }
 
@@ -787,6 +918,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_ring_kernel(const I8P
       }
     }
     if (diag) {
+      if constexpr (DIRECT) {
+        // 4 rows x 8 points per thread: sum the four point groups (lanes differing in the low two bits), lane c4 == j owns row j
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          bs4[j] += __shfl_xor_sync(0xffffffffu, bs4[j], 1);
+          bs4[j] += __shfl_xor_sync(0xffffffffu, bs4[j], 2);
+        }
+        const int c4 = lane & 3;
+        const double mine = c4 == 0 ? bs4[0] : c4 == 1 ? bs4[1] : c4 == 2 ? bs4[2] : bs4[3];
+        sm_bred[cq * 128 + lq * 32 + (lane >> 2) + 8 * c4] = mine;
+      } else
       sm_bred[cq * 128 + L] = bsum;      // (group, column half) -> 4 partial sums per row
       asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
       if (cq == 0) bp[ti * kTile + L] = p.bscale * (sm_bred[L] + sm_bred[128 + L] + sm_bred[256 + L] + sm_bred[384 + L]);
@@ -838,8 +980,9 @@ int i8_plan(int m_pad, int num_sms, long long n_units, I8Launch* out, int max_ou
 
 
 cudaError_t launch_gram_i8_ring(const uint8_t* Xt, const float* ys, const uint8_t* Zt, long long n, int d, int m_pad,
-                           const I8Launch& plan, double* Gpart, double* bpart, double C, uint8_t* share, float* dbg_T,
-                           uint32_t* dbg_w, long long* dbg_clk, void* post_mortem, cudaStream_t s) {
+                                const I8Launch& plan, const I8Direct& direct, double* Gpart, double* bpart, double C,
+                                uint8_t* share, float* dbg_T, uint32_t* dbg_w, long long* dbg_clk, void* post_mortem,
+                                cudaStream_t s) {
   I8Params p{};
   const int dp = (d + 15) / 16 * 16;
   p.Xt = Xt; p.ys = ys; p.Zt = Zt;
@@ -858,6 +1001,23 @@ cudaError_t launch_gram_i8_ring(const uint8_t* Xt, const float* ys, const uint8_
   if (const char* e = getenv("SGP_I8_TL_SLICE")) p.tl_slice = atoi(e);
   p.dbg_T = dbg_T; p.dbg_w = dbg_w; p.dbg_clk = dbg_clk; p.pm = static_cast<I8PostMortem*>(post_mortem);
   p.xstages = (p.nchunks == 1) ? 8 : 5;
+  p.xbytes = static_cast<uint32_t>(p.nchunks * XIMG_BYTES);
+  p.zbytes = static_cast<uint32_t>(p.nchunks * ZPANEL_BYTES);
+  if (direct.on) {
+    p.n_terms = direct.n_terms; p.dpad4 = direct.dpad4;
+    for (int t = 0; t < 4; ++t) p.w[t] = direct.w[t];
+    p.xbytes = static_cast<uint32_t>(direct.n_terms * UP * direct.dpad4 * sizeof(float));
+    p.zbytes = static_cast<uint32_t>(direct.n_terms * kTile * direct.dpad4 * sizeof(float));
+    p.npj = 5;
+    const long avail = 227L * 1024 - 1024 - 5L * SLOT_BYTES - static_cast<long>(p.zbytes) - YSTAGES * UP * 4 - 4 * 128 * 8 - 512;
+    long xs = avail / static_cast<long>(p.xbytes);
+    if (xs > XSTAGES_MAX) xs = XSTAGES_MAX;
+    if (xs < 2) return cudaErrorInvalidConfiguration;
+    p.xstages = static_cast<int>(xs);
+    C = direct.csum;
+    p.gscale = C * C / (4.0 * static_cast<double>(C0) * static_cast<double>(C0));
+    p.bscale = C;
+  }
   p.npj = (p.nchunks == 1) ? NPJ_MAX : 3;
   const size_t ring_bytes = static_cast<size_t>(plan.n_slices) * p.nt * RING_D * SLOT_BYTES;
   p.ring = share;
@@ -865,10 +1025,12 @@ cudaError_t launch_gram_i8_ring(const uint8_t* Xt, const float* ys, const uint8_
   p.consumed = p.ready + static_cast<size_t>(plan.n_slices) * p.nt * FLAG_STRIDE;
   cudaError_t e = cudaMemsetAsync(p.ready, 0, i8_share_flag_bytes(m_pad, plan.n_slices), s);
   if (e != cudaSuccess) return e;
-  const size_t smem = 1024 + (p.npj > NPI_PUB ? p.npj : NPI_PUB) * SLOT_BYTES + p.nchunks * ZPANEL_BYTES + p.xstages * p.nchunks * XIMG_BYTES +
+  const size_t smem = 1024 + (p.npj > NPI_PUB ? p.npj : NPI_PUB) * SLOT_BYTES + p.zbytes + static_cast<size_t>(p.xstages) * p.xbytes +
                       YSTAGES * UP * 4 + 4 * 128 * 8 + 512;
-  const void* fn = dbg_T ? reinterpret_cast<const void*>(kmn_gram_i8_ring_kernel<true>)
-                         : reinterpret_cast<const void*>(kmn_gram_i8_ring_kernel<false>);
+  const void* fn = direct.on ? (dbg_T ? reinterpret_cast<const void*>(kmn_gram_i8_ring_kernel<true, true>)
+                                      : reinterpret_cast<const void*>(kmn_gram_i8_ring_kernel<false, true>))
+                             : (dbg_T ? reinterpret_cast<const void*>(kmn_gram_i8_ring_kernel<true, false>)
+                                      : reinterpret_cast<const void*>(kmn_gram_i8_ring_kernel<false, false>));
   // per-device attribute: set on every launch (contexts on several GPUs may live in one process)
   e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) return e;

@@ -82,9 +82,17 @@ struct Ctx {
   double* dBpart = nullptr;  size_t bpart_bytes = 0;
   int n_slices = 1;
   // tcgen05 int8 path (gram_i8.cu)
-  bool i8_ok = false;            // kernel/shape qualifies (one non-Eye term, d <= 32)
+  bool i8_ok = false;            // kernel/shape qualifies for tensor-core distances (one non-Eye term, d <= 32)
+  bool i8_direct_ok = false;     // ... for the direct-distance mode (<= 4 non-Eye terms, n_terms * (dpad4 + 4) <= 72)
+  int i8_dpad4 = 0;
+  float* dI8Zd = nullptr;        // direct mode: active-set tiles [tile][term][128][dpad4 + 4] fp32
+  double* dI8DScale = nullptr;   // [n_terms][dpad4] sqrt(log2 e) * beta_tk ; then [dpad4] centre
+  bool i8_direct_used = false;
   bool i8_used = false;          // an int8 launch contributed to the current statistics
-  bool call_i8 = false;          // AUTO's decision for the current accumulate call (taken on its first chunk)
+  float i8_direct_r2max = 2048.f;  // direct mode: largest scaled squared norm accepted (env SGP_I8_DIRECT_R2MAX); measured
+                                   // dG 6.6e-7 at ~1300 and 2.7e-6 at ~7700 on clustered data (tests: error_growth)
+  int call_path = 0;             // AUTO's decision for the current accumulate call (taken on its first chunk): 0 fp64,
+                                 // 1 int8 Gram with tensor-core distances, 2 int8 Gram with direct fp32 distances
   double* dI8Scale = nullptr;    // [dp16] sqrt(log2 e) * beta_k
   double* dI8Centre = nullptr;   // [dp16] per-feature centre (active-set mean)
   int* dI8Flags = nullptr;       // bit 0: coordinates out of fp16 operand range
@@ -174,6 +182,20 @@ cudaError_t launch_i8_prep_active(uint8_t* Zt, const double* dZ, int m, int m_pa
 cudaError_t launch_i8_prep_points(uint8_t* Xt, float* ys, const void* dX, int x_is_f32, const double* dy, long long n,
                                   int d, const double* dScale, const double* dCentre, int* dFlags, double* dNormSum,
                                   double* dNormSumCall, cudaStream_t s);
+// direct-distance mode of the ring kernel: fp32 coordinate tiles instead of fp16 operand images
+cudaError_t launch_i8_prep_active_direct(float* Zd, const double* dZ, int m, int m_pad, int d, int dpad4, int n_terms,
+                                         const double* dScale, const double* dCentre, int* flags, float r2max,
+                                         cudaStream_t s);
+cudaError_t launch_i8_prep_points_direct(float* Xd, float* ys, const void* dX, int x_is_f32, const double* dy, long long n,
+                                         int d, int dpad4, int n_terms, const double* dScale, const double* dCentre, int* flags,
+                                         float r2max, cudaStream_t s);
+struct I8Direct {
+  int on = 0;            // 1: exponents from fp32 direct-form distances on the CUDA cores (any norms, up to 4 terms)
+  int n_terms = 0, dpad4 = 0;
+  float w[4] = {0, 0, 0, 0};   // C_t / sum C
+  double csum = 0.0;     // sum of the term scales = the fixed-point scale
+};
+
 // One cooperative launch of the int8 Gram kernel: whole tile columns [col_lo, col_hi) x n_slices point slices.
 struct I8Launch {
   int col_lo, col_hi, tiles, n_slices;
@@ -182,8 +204,9 @@ int i8_plan(int m_pad, int num_sms, long long n_units, I8Launch* out, int max_ou
 size_t i8_share_bytes(int m_pad, int n_slices);
 size_t i8_share_flag_bytes(int m_pad, int n_slices);
 cudaError_t launch_gram_i8_ring(const uint8_t* Xt, const float* ys, const uint8_t* Zt, long long n, int d, int m_pad,
-                                const I8Launch& plan, double* Gpart, double* bpart, double C, uint8_t* share, float* dbg_T,
-                                uint32_t* dbg_w, long long* dbg_clk, void* post_mortem, cudaStream_t s);
+                                const I8Launch& plan, const I8Direct& direct, double* Gpart, double* bpart, double C,
+                                uint8_t* share, float* dbg_T, uint32_t* dbg_w, long long* dbg_clk, void* post_mortem,
+                                cudaStream_t s);
 // round-1 kernel (every CTA builds both panels of its tile; SGP_I8_IMPL=v1): kept as the A/B reference of the ring kernel
 cudaError_t launch_gram_i8(const uint8_t* Xt, const float* ys, const uint8_t* Zt, long long n, int d, int m_pad,
                            int n_slices, double* Gpart, double* bpart, double C, float* dbg_T, uint32_t* dbg_w,

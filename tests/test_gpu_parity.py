@@ -167,18 +167,20 @@ def test_airfoil_golden(eng, mode):
 
 
 def test_auto_magnitude_gate(eng):
-    """AUTO picks the tcgen05 int8 kernel only for large shards whose scaled squared norms are small (the fp32
-    accumulator of the distance contraction rounds in proportion to them).  Airfoil (mean scaled squared norm ~6 for
-    points and active set, maxima ~40) stays on the fp64 kernel even when the shard is large; the benchmark's unit
-    cube (mean ~2.2) runs the int8 kernel."""
+    """AUTO picks tensor-core distances for the int8 Gram only on large shards whose scaled squared norms are small (the
+    fp32 accumulator of the distance contraction rounds in proportion to them).  Airfoil (mean scaled squared norm ~6
+    for points and active set, maxima ~40) gets the int8 Gram with DIRECT fp32 distances instead (no cancellation);
+    the benchmark's unit cube (mean ~2.2) runs tensor-core distances; small shards stay on the fp64 kernel."""
     c = np.load(os.path.join(GOLD, "airfoil_case.npz"))
     kernel = (1 * sg.ARDRBFKernel(5) + sg.const(1) * sg.EyeKernel() + sg.const(float(c["sigma2"])) * sg.EyeKernel())
     kernel.setHyperparameters(c["theta"])
     reps = 200                                              # 270k points
     X, y = np.tile(c["X"], (reps, 1)), np.tile(c["y"], reps)
     G, b = run_stats(eng, kernel, X, y, c["Z"], N.SGP_PREC_AUTO)
-    assert eng.last_path() == N.SGP_PREC_F64
-    assert np.abs(np.diag(G) - reps * c["G_diag"]).max() / (reps * np.abs(c["G_diag"]).max()) < TOL_STATS
+    assert eng.last_path() == N.SGP_PREC_I8_DIRECT
+    eg = np.abs(np.diag(G) - reps * c["G_diag"]).max() / (reps * np.abs(c["G_diag"]).max())
+    print("airfoil x200, AUTO -> int8 Gram with direct distances: dG_diag=%.2e db=%.2e" % (eg, rel(b, reps * c["b"])))
+    assert eg < TOL_STATS
     assert rel(b, reps * c["b"]) < TOL_STATS
     rng = np.random.default_rng(2)
     Xu = rng.random((300000, 16), dtype=np.float32)
@@ -191,7 +193,7 @@ def test_auto_magnitude_gate(eng):
 
 # ---------------- seeded inputs vs the oracle, edge cases ---------------------------------------------
 @pytest.mark.parametrize("n,d,m", [(1, 1, 1), (15, 2, 3), (16, 4, 128), (17, 5, 129), (257, 7, 256), (1000, 33, 200),
-                                   (2048, 16, 384), (333, 70, 50)])
+                                   (2048, 16, 384), (333, 70, 50), (200, 80, 40)])
 def test_ragged_shapes_vs_oracle(eng, n, d, m):
     rng = np.random.default_rng(n * 1000 + d * 10 + m)
     X = rng.standard_normal((n, d))
@@ -205,10 +207,14 @@ def test_ragged_shapes_vs_oracle(eng, n, d, m):
     assert rel(G, G0) < TOL_STRICT and rel(b, b0) < TOL_STRICT
     G, b = run_stats(eng, k, X, y, Z, N.SGP_PREC_F64)
     assert rel(G, G0) < TOL_STATS and rel(b, b0) < TOL_STATS
-    if d <= 32:                                             # tcgen05 int8 path (one non-Eye term, d <= 32)
+    if d <= 72:                              # int8 Gram: tensor-core distances for d <= 32, direct fp32 distances up to 72
         G, b = run_stats(eng, k, X, y, Z, N.SGP_PREC_I8)
+        assert eng.last_path() == (N.SGP_PREC_I8 if d <= 32 else N.SGP_PREC_I8_DIRECT)
         assert rel(G, G0) < TOL_I8 and rel(b, b0) < TOL_I8
         assert np.array_equal(G, G.T)
+        G, b = run_stats(eng, k, X, y, Z, N.SGP_PREC_I8_DIRECT)
+        assert eng.last_path() == N.SGP_PREC_I8_DIRECT
+        assert rel(G, G0) < TOL_I8 and rel(b, b0) < TOL_I8
     else:
         with pytest.raises(ValueError):                     # explicit I8 request on a non-qualifying shape
             run_stats(eng, k, X, y, Z, N.SGP_PREC_I8)
@@ -678,8 +684,8 @@ def test_two_contexts_two_devices_two_threads():
 def test_auto_budget_checked_over_whole_window(eng):
     """AUTO chooses the kernel on the first chunk of a call; the scaled squared norms of EVERY chunk are summed on the
     device and checked at finish, so an unrepresentative first chunk cannot silently degrade the statistics: here the first
-    600k points are benign and the rest have large norms -> SGP_E_RANGE at finish, and the Estimator's helper reruns on
-    the fp64 kernel."""
+    600k points are benign and the rest have large norms -> SGP_E_RANGE at finish, and the Estimator's helper reruns with
+    direct fp32 distances (scaled squared norms up to ~1500 < its limit of 2048)."""
     rng = np.random.default_rng(17)
     d, m = 8, 128
     Xa = rng.random((600_000, d), dtype=np.float32)
@@ -694,9 +700,11 @@ def test_auto_budget_checked_over_whole_window(eng):
     with pytest.raises(sg.OperandRangeError):
         eng.finish()
     G, b = eng.statistics(k, Z, X, y)
-    assert eng.last_path() == N.SGP_PREC_F64
+    assert eng.last_path() == N.SGP_PREC_I8_DIRECT
+    Gs, bs = run_stats(eng, k, X, y, Z, N.SGP_PREC_F64)
     eng.set_precision(N.SGP_PREC_AUTO)
-    assert np.all(np.isfinite(G))
+    print("budget rerun on direct distances vs fp64 kernel: dG=%.2e db=%.2e" % (rel(G, Gs), rel(b, bs)))
+    assert rel(G, Gs) < TOL_STATS and rel(b, bs) < TOL_STATS
 
 
 def test_bcm_large_experts_general_path(eng):
@@ -775,3 +783,91 @@ def test_kmn_sweep_vs_fp64_cross_kernel(eng, n, d, m):
     err = float(np.abs(K32 - K64).max() / 2.5)
     print("sweep n=%d d=%d m=%d: max |dK| / C = %.2e" % (n, d, m, err))
     assert K32.shape == (n, m) and err < 1e-5
+
+
+# ---------------- int8 Gram with direct fp32 distances (SGP_PREC_I8_DIRECT) -------------------------------------------
+def test_i8_direct_headline_shape_vs_oracle(eng):
+    """The headline shape on the direct-distance mode against the ORACLE: same 1e-6 / 1e-5 gates as the tensor-distance
+    mode."""
+    from oracle.cpu_baseline import stats_parallel
+    n, d, m = 300_000, 16, 1000
+    X, y, Z, k, ok = _bench_workload(n, d, m)
+    G, b = run_stats(eng, k, X, y, Z, N.SGP_PREC_I8_DIRECT)
+    assert eng.last_path() == N.SGP_PREC_I8_DIRECT
+    eng.magic()
+    Xt = np.random.default_rng(99).random((1000, d))
+    mean, var = eng.predict(Xt)
+    G0, b0, _ = stats_parallel(X.astype(np.float64), y, Z, ok, ok().get_hyperparameters(), 100)
+    kernel0 = ok().set_hyperparameters(ok().get_hyperparameters()).set_training_vectors(Z)
+    mv0, mm0 = oracle.get_magic_vector(kernel0, G0, b0)
+    m0, v0 = oracle.GaussianProjectedProcessRawPredictor(mv0, mm0, kernel0).predict_many(Xt)
+    eg, eb, em, ev = rel(G, G0), rel(b, b0), rel(mean, m0), float(np.abs(var / v0 - 1).max())
+    print("int8 direct vs ORACLE, 300k x 16, m=1000: dG=%.2e db=%.2e dmean=%.2e dvar=%.2e" % (eg, eb, em, ev))
+    assert eg < TOL_STATS and eb < TOL_STATS
+    assert em < TOL_PRED and ev < TOL_PRED
+    assert np.array_equal(G, G.T)
+
+
+@pytest.mark.parametrize("case", ["two_terms", "d40", "d64", "three_terms_d12", "offset_1e3", "rbf_plus_ard"])
+def test_i8_direct_widened_shapes_vs_oracle(eng, case):
+    """What the tensor-distance mode cannot take: sums of several non-Eye terms, 32 < d <= 64, data far from the origin
+    (the active-set mean is subtracted in fp64 before the fp32 rounding).  Oracle in fp64, gate 1e-6."""
+    rng = np.random.default_rng(sum(map(ord, case)))
+    n, m = 16384 + 77, 300
+    d = {"two_terms": 8, "d40": 40, "d64": 64, "three_terms_d12": 12, "offset_1e3": 6, "rbf_plus_ard": 5}[case]
+    X = rng.random((n, d))
+    if case == "offset_1e3":
+        X += 1000.0
+    y = np.sin(X.sum(1)) + 0.1 * rng.standard_normal(n)
+    Z = X[rng.permutation(n)[:m]].copy()
+    b1 = rng.uniform(0.5, 1.5, d) * np.sqrt(6.0 / d)
+    b2 = rng.uniform(0.5, 1.5, d) * np.sqrt(20.0 / d)
+    b3 = rng.uniform(0.5, 1.5, d) * np.sqrt(2.0 / d)
+    if case in ("two_terms",):
+        mk = lambda S: 0.7 * S.ARDRBFKernel(b1) + 1.9 * S.ARDRBFKernel(b2) + S.const(1e-3) * S.EyeKernel()
+    elif case == "three_terms_d12":
+        mk = lambda S: 0.7 * S.ARDRBFKernel(b1) + 1.9 * S.ARDRBFKernel(b2) + 0.2 * S.ARDRBFKernel(b3) + S.const(1e-3) * S.EyeKernel()
+    elif case == "rbf_plus_ard":
+        mk = lambda S: 1.1 * S.RBFKernel(0.6) + 0.4 * S.ARDRBFKernel(b2) + S.const(1e-3) * S.EyeKernel()
+    else:
+        mk = lambda S: 1.3 * S.ARDRBFKernel(b1) + S.const(1e-3) * S.EyeKernel()
+    k, ok = mk(sg), (lambda: mk(oracle))
+    G0, b0 = _oracle_stats_chunked(ok, X, y, Z)
+    G, b = run_stats(eng, k, X, y, Z, N.SGP_PREC_I8_DIRECT)
+    assert eng.last_path() == N.SGP_PREC_I8_DIRECT
+    eg, eb = rel(G, G0), rel(b, b0)
+    print("int8 direct vs oracle [%s] n=%d d=%d m=%d: dG=%.2e db=%.2e" % (case, n, d, m, eg, eb))
+    assert eg < TOL_STATS and eb < TOL_STATS
+    assert np.array_equal(G, G.T)
+
+
+def test_i8_direct_norm_limit_and_error_growth(eng):
+    """The direct mode rounds centred, scaled coordinates to fp32: the exponent error grows like 2^-24 sqrt(q) (|x|+|z|),
+    and the rounding of an active point is common to all its kernel values (it does not average out over the shard).
+    Adversarial layout: clusters far apart, unit-scale structure inside each.  Measured dG 1.2e-7 / 6.6e-7 / 2.7e-6 at
+    scaled squared norms ~10 / ~1300 / ~7700: norms above 2048 are refused (SGP_E_RANGE at finish), below the limit the
+    statistics stay inside 1e-6."""
+    rng = np.random.default_rng(23)
+    n, d, m = 65536, 8, 256
+    base = rng.random((n, d))
+    errs = []
+    for spread in (1.0, 10.0, 25.0, 400.0):
+        # clusters `spread` apart, unit-scale structure inside each: norms grow, neighbour distances do not
+        X = base + spread * rng.integers(0, 3, (n, 1)) * np.ones((1, d))
+        y = np.sin(base.sum(1))
+        Z = X[rng.permutation(n)[:m]].copy()
+        beta = np.full(d, 1.0)
+        k = 1 * sg.ARDRBFKernel(beta) + sg.const(1e-3) * sg.EyeKernel()
+        ok = lambda: 1 * oracle.ARDRBFKernel(beta) + oracle.const(1e-3) * oracle.EyeKernel()
+        eng.set_precision(N.SGP_PREC_I8_DIRECT)
+        eng.begin(k, Z)
+        eng.accumulate(X, y)
+        if spread >= 25.0:                   # scaled squared norm ~ 8 * (25 * 1.2)^2 = 7200 > 2048
+            with pytest.raises(sg.OperandRangeError):
+                eng.finish()
+            continue
+        G, b = eng.finish()
+        G0, b0 = _oracle_stats_chunked(ok, X, y, Z)
+        errs.append((spread, rel(G, G0), rel(b, b0)))
+    print("int8 direct, error vs cluster spread:", ", ".join("%g: dG=%.1e db=%.1e" % e for e in errs))
+    assert all(e[1] < TOL_STATS and e[2] < TOL_STATS for e in errs)
