@@ -1,12 +1,12 @@
 """One int8 statistics pass (device-resident shard) -- the target of ncu captures.
-    python tools/prof_i8.py [i8|f64] [n] [d] [m]"""
+    python tools/prof_i8.py [i8|i8d|f64] [n] [d] [m]"""
 import sys
 sys.path.insert(0, ".")
 import numpy as np
 import torch
 import spark_gp_b200 as sg
 from spark_gp_b200 import _native as N
-mode = {"i8": N.SGP_PREC_I8, "f64": N.SGP_PREC_F64}[sys.argv[1] if len(sys.argv) > 1 else "i8"]
+mode = {"i8": N.SGP_PREC_I8, "f64": N.SGP_PREC_F64, "i8d": N.SGP_PREC_I8_DIRECT}[sys.argv[1] if len(sys.argv) > 1 else "i8"]
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 1_000_000
 d = int(sys.argv[3]) if len(sys.argv) > 3 else 16
 m = int(sys.argv[4]) if len(sys.argv) > 4 else 1000
