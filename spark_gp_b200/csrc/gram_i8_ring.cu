@@ -336,6 +336,15 @@ __device__ __forceinline__ void spin_guard(long long& t0, unsigned& it, I8PostMo
   if ((++it & 0x3FFu) == 0 && clock64() - t0 > 2000000000LL) i8_die(pm, code, unit, a, b);
 }
 
+// Where the generic -> async proxy fence for the diagonal CTA's smem copy of its planes sits: false = in the 256 writer threads
+// (epilogue, before their arrive on pi_full), true = in the two reader threads (Gram issuer, publisher) after their wait.
+constexpr bool CONSUMER_SIDE_PROXY_FENCE = true;
+// pi_empty / a_empty polled early with test_wait (true) or only where they are needed with try_wait (false)
+#ifndef SGP_EARLY_POLLS
+#define SGP_EARLY_POLLS 0
+#endif
+constexpr bool EARLY_POLLS = SGP_EARLY_POLLS != 0;
+
 template <bool DBG, bool DIRECT>
 __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_ring_kernel(const I8Params p) {
   extern __shared__ uint8_t smem_raw[];
@@ -512,7 +521,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_ring_kernel(const I8P
           MBAR_WAIT(b_afull + 8 * (2 * ks + up), a_phase, 5, j);           // A planes of this k-step are in TMEM
           if (ks == 0) {
             SGP_TL(1, j, 1);
-            if (diag) MBAR_WAIT(b_pifull + 8 * si, pi_phase, 14, j);        // B = our own planes in smem
+            if (diag) {
+              MBAR_WAIT(b_pifull + 8 * si, pi_phase, 14, j);                // B = our own planes in smem
+              // the planes were written through the generic proxy by the epilogue warps; release (their arrive) ->
+              // acquire (this wait) -> proxy fence HERE orders them before this thread's tensor-core reads.  The fence
+              // costs 400-600 clk on a thread with stores in flight; the writers no longer pay it once per tile
+              if constexpr (CONSUMER_SIDE_PROXY_FENCE) fence_proxy_async();
+            }
             else MBAR_WAIT(b_pjfull + 8 * sj, pj_phase, 6, j);             // B = panel J's planes from the ring
             SGP_TL(1, j, 2);
           }
@@ -580,6 +595,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_ring_kernel(const I8P
         if (lane == 0) {
           // (the epilogue warps fenced their generic-proxy plane writes to the async proxy before arriving on pi_full,
           //  exactly as for the tensor core's reads: no further proxy fence is needed before the bulk store)
+          if constexpr (CONSUMER_SIDE_PROXY_FENCE) fence_proxy_async();
           bulk_s2g(ring + static_cast<size_t>(u % RING_D) * SLOT_BYTES, s_slot + si * SLOT_BYTES, SLOT_BYTES);
           bulk_commit();
           SGP_TL(4, u, 3);
@@ -674,8 +690,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_ring_kernel(const I8P
     // so q_full of this group's NEXT tile is tested during this tile's store phase and pi_empty in the middle of the
     // exp block
     bool q_ready = false;
+    [[maybe_unused]] bool pe_ready = false;
     const bool dbg = DBG && (p.dbg_T != nullptr) && blockIdx.x == 0 && blockIdx.y == 0;
     const int npi_shift = 2;                                                     // npi == 4
+    // (a loop over the group's OWN units only -- i += 2, folds counted per group -- measured slower on the tensor-distance
+    //  path: 3.08 vs 3.02 ms, 17.0 vs 16.25 ms at d = 32 / m = 2000; code layout)
     for (long long i = 0; i < nu; ++i) {
       if ((i & 1) == grp) {
         // ---- one distance tile (128 active rows x 64 points) -> three int8 digit planes of unit i ---------------
@@ -694,6 +713,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_ring_kernel(const I8P
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(b_qempty + 8 * grp);
+            // polls issued early, consumed later: a try_wait costs 150-250 clk even when the phase is complete
+            pe_ready = !diag || i < npi ||
+                       (EARLY_POLLS && mbar_test(b_piempty + 8 * (static_cast<uint32_t>(i) & static_cast<uint32_t>(npi - 1)),
+                                                 static_cast<uint32_t>(((i >> npi_shift) - 1) & 1)));
             if (DBG && dbg && i == 0) {
               for (int k = 0; k < 32; ++k) p.dbg_T[L * UP + ch * 32 + k] = __uint_as_float(T[k]);
             }
@@ -721,6 +744,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_ring_kernel(const I8P
             for (int k = 0; k < 32; ++k) p.dbg_w[L * UP + ch * 32 + k] = T[k] >> 1;     // the fp32 word (sign bit is 0)
           }
           if (tle) SGP_TL(2 + grp, i, 3);
+          const bool a_ready = i < 1 || (EARLY_POLLS && mbar_test(b_aempty + 8 * (2 * ch + (grp ^ 1)),
+                                                                  static_cast<uint32_t>(((i - 1) >> 1) & 1)));
           // byte planes: 4 consecutive points -> one word per digit, 32 points -> 8 words per digit = one k-step of A
           uint32_t d0[8], d1[8], d2[8];
   #pragma unroll
@@ -738,7 +763,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_ring_kernel(const I8P
             // unit i lives in slot i % 4; before overwriting it the Gram MMAs of unit i - 4 (and, on a publishing CTA,
             // the bulk store that shipped it) must have drained: completion (i / 4 - 1) of pi_empty[slot]
             const uint32_t si = static_cast<uint32_t>(i) & static_cast<uint32_t>(npi - 1);
-            if (i >= npi) MBAR_WAIT(b_piempty + 8 * si, static_cast<uint32_t>(((i >> npi_shift) - 1) & 1), 15, i);
+            if (!pe_ready) MBAR_WAIT(b_piempty + 8 * si, static_cast<uint32_t>(((i >> npi_shift) - 1) & 1), 15, i);
             uint8_t* const slot = sm + si * SLOT_BYTES;
   #pragma unroll
             for (int g16 = 0; g16 < 2; ++g16) {
@@ -750,14 +775,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_ring_kernel(const I8P
             // generic-proxy plane writes -> visible to the tensor core / bulk copy (async proxy).  The fence costs 400-600 clk
             // of this warp; it sits BEFORE the wait for the A columns, which would idle anyway (tried: after the A store
             // 1600 clk per unit, deferred into the next tile's TMEM load 2130 -- the Gram issuer then waits for pi_full)
-            fence_proxy_async();
+            if constexpr (!CONSUMER_SIDE_PROXY_FENCE) fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(b_pifull + 8 * si);
           }
           if (tle) SGP_TL(2 + grp, i, 4);
           // A operand: straight into tensor memory once the Gram MMAs of the previous unit's k-step `ch` have drained
           // (barriers are split by unit parity so that a group, which sees only every other unit, never lags a phase)
-          if (i >= 1) MBAR_WAIT(b_aempty + 8 * (2 * ch + (grp ^ 1)), static_cast<uint32_t>(((i - 1) >> 1) & 1), 10, i);
+          if (!a_ready) MBAR_WAIT(b_aempty + 8 * (2 * ch + (grp ^ 1)), static_cast<uint32_t>(((i - 1) >> 1) & 1), 10, i);
           tc_fence_after();
           tmem_st8(a_taddr + 0, d0);
           tmem_st8(a_taddr + 8, d1);
@@ -860,7 +885,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) kmn_gram_i8_ring_kernel(const I8P
               *reinterpret_cast<uint2*>(dst + 1 * PLANE_BYTES) = make_uint2(D1[j][0], D1[j][1]);
               *reinterpret_cast<uint2*>(dst + 2 * PLANE_BYTES) = make_uint2(D2[j][0], D2[j][1]);
             }
-            fence_proxy_async();
+            if constexpr (!CONSUMER_SIDE_PROXY_FENCE) fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(b_pifull + 8 * si);
           }

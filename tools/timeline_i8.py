@@ -27,7 +27,7 @@ for _ in range(2):
 print("gram kernel ms (debug build):", eng.gram_kernel_time())
 tl = eng.debug_i8_timeline()              # [cta][role][unit][event]
 names = {0: ["wait_x", "x_ok", "q_ok", "issued"], 1: ["wait_pi", "pi_ok", "pj_ok", "issued"],
-         2: ["q_wait", "q_ok", "ld", "exp", "pe_ok", "stored"], 3: ["q_wait", "q_ok", "ld", "exp", "pe_ok", "stored"],
+         2: ["q_wait", "q_ok", "ld", "exp", "pe_ok", "stored", "next_top"], 3: ["q_wait", "q_ok", "ld", "exp", "pe_ok", "stored", "next_top"],
          4: ["start", "a", "b", "c", "d", "e", "f"]}
 roles = ["dist", "gram", "epi0", "epi1", "share"]
 for cta, cname in enumerate(["publisher (0,0)", "consumer (1,0)"]):
