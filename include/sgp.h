@@ -206,6 +206,18 @@ int sgp_debug_i8_tile(sgp_ctx* ctx, float* T_out /* 128*64 */, uint32_t* w_out /
  * issuer, epilogue group 0, group 1, sharing warp][32 units: 64..95][8 events] of the last SGP_PREC_I8 launch made while
  * armed (see sgp_debug_i8_tile). */
 int sgp_debug_i8_timeline(sgp_ctx* ctx, long long* out /* 2560 + 148*32: timeline, then per-CTA progress marks */);
+/* GreedilyOptimizingActiveSetProvider (commons/ActiveSetProvider.scala:58-139) with rank-1 updates: selects m_target points
+ * of the shard X (n x d fp64, host) by the reference's forward selection and returns their row indices.  The reference
+ * recomputes the statistics, two m x m inverses and three quadratic forms per candidate in every round (ASP:83-137); here
+ * the cross kernel stays on the device and grows by one row per round, the inverses and the per-point p_i, q_i, mu_i
+ * (ASP:109-113) are updated through the bordered-matrix identities: O(n m) per round.  Selection semantics are the
+ * reference's (point i belongs to expert i % n_experts, per-expert fold with later-wins ties and NaN poisoning, first
+ * expert with the maximal score, sigma2 = the kernel's whiteNoiseVar, ASP:76, 108-135).  first_index replaces
+ * takeSample(1, seed) (ASP:70).  Needs 8 n (m_target + d + 8) bytes of device memory: SGP_E_NOMEM otherwise.
+ * Errors: SGP_E_NOT_PD as assertSymPositiveDefinite (PGPH:62-65), SGP_E_BADARG "empty.max" when every expert is poisoned. */
+int sgp_greedy_active_set(sgp_ctx* ctx, const sgp_kernel_desc* kernel, const double* X, const double* y, int64_t n,
+                          int32_t d, int64_t n_experts, int64_t first_index, int32_t m_target, int64_t* indices_out);
+
 /* Evaluate K(X_test, Z) (n x m row-major fp64 out) with the current kernel -- the `crossKernel`
  * contract of kernel/Kernel.scala:69-74 (used by the golden-vector tests). */
 int sgp_cross_kernel(sgp_ctx* ctx, const double* X, int64_t n, double* K_out);

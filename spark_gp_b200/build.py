@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsgp.so")
-SOURCES = ["api.cu", "bcm_nll.cu", "gram_f64.cu", "gram_i8.cu", "gram_i8_ring.cu", "kmn_sweep.cu", "laplace.cu", "misc_kernels.cu", "tail.cu"]
+SOURCES = ["api.cu", "bcm_nll.cu", "gram_f64.cu", "gram_i8.cu", "gram_i8_ring.cu", "greedy.cu", "kmn_sweep.cu", "laplace.cu", "misc_kernels.cu", "tail.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-Xptxas", "-v"]
 LINK = ["-lcusolver", "-lcublas", "-ldl", "-Xlinker", "-rpath=/usr/local/cuda/lib64"]

@@ -322,7 +322,7 @@ int sgp_ctx_destroy(sgp_ctx* h) {
   }
   if (c->comm && nccl().ok) nccl().CommDestroy(c->comm);
   if (c->i8_pm_host) cudaFreeHost(c->i8_pm_host);
-  cudaFree(c->sweep_ws.p); cudaFree(c->bcm_ws.p); cudaFree(c->tail_ws.p); cudaFree(c->tail_ws2.p); cudaFree(c->predict_ws.p); cudaFree(c->cross_ws.p);
+  cudaFree(c->greedy_ws.p); cudaFree(c->sweep_ws.p); cudaFree(c->bcm_ws.p); cudaFree(c->tail_ws.p); cudaFree(c->tail_ws2.p); cudaFree(c->predict_ws.p); cudaFree(c->cross_ws.p);
   if (c->tail_fork) cudaEventDestroy(c->tail_fork);
   if (c->tail_join) cudaEventDestroy(c->tail_join);
   if (c->tail_stream) cudaStreamDestroy(c->tail_stream);
@@ -1074,6 +1074,40 @@ int sgp_kmn_sweep(sgp_ctx* h, const void* X, int32_t x_is_f32, int64_t n, float*
     return fail(c, SGP_E_RANGE, "scaled coordinates exceed the fp16 operand range of the tensor-core distance contraction; "
                                 "use sgp_cross_kernel");
   return SGP_OK;
+}
+
+int sgp_greedy_active_set(sgp_ctx* h, const sgp_kernel_desc* k, const double* X, const double* y, int64_t n, int32_t d,
+                          int64_t n_experts, int64_t first_index, int32_t m_target, int64_t* indices_out) {
+  Ctx* c = reinterpret_cast<Ctx*>(h);
+  if (!c) return SGP_E_BADARG;
+  if (!k || !X || !y || !indices_out || n <= 0 || d <= 0 || m_target <= 0 || k->n_terms <= 0 || !k->terms)
+    return fail(c, SGP_E_BADARG, "sgp_greedy_active_set: null or empty argument");
+  if (n_experts <= 0) return fail(c, SGP_E_BADARG, "numberOfExperts == 0 (N < datasetSizeForExpert / 2)");
+  if (first_index < 0 || first_index >= n) return fail(c, SGP_E_BADARG, "first_index out of range");
+  if (n > 2147483647LL) return fail(c, SGP_E_BADARG, "sgp_greedy_active_set: n too large for one device");
+  SGP_CUDA(c, cudaSetDevice(c->device));
+  KernelFlat kf;
+  std::vector<double> beta(static_cast<size_t>(kMaxTerms) * d, 0.0);
+  for (int t = 0; t < k->n_terms; ++t) {
+    const sgp_kernel_term& term = k->terms[t];
+    if (!(term.scale >= 0.0)) return fail(c, SGP_E_BADARG, "requirement failed: C should be positive");
+    kf.self_kernel += term.scale;
+    if (term.type == SGP_TERM_EYE) { kf.eye_sum += term.scale; continue; }
+    if (kf.n_terms == kMaxTerms) return fail(c, SGP_E_BADARG, "too many non-Eye kernel terms (max 4)");
+    double* bt = beta.data() + static_cast<size_t>(kf.n_terms) * d;
+    if (term.type == SGP_TERM_ARD) {
+      if (!term.beta) return fail(c, SGP_E_BADARG, "ARD term without beta");
+      for (int j = 0; j < d; ++j) bt[j] = term.beta[j];
+    } else if (term.type == SGP_TERM_RBF) {
+      if (!(term.sigma > 0.0)) return fail(c, SGP_E_BADARG, "RBF sigma must be > 0");
+      for (int j = 0; j < d; ++j) bt[j] = 1.0 / (std::sqrt(2.0) * term.sigma);
+    } else {
+      return fail(c, SGP_E_BADARG, "unknown kernel term type");
+    }
+    kf.scale[kf.n_terms++] = term.scale;
+  }
+  static_assert(sizeof(long long) == sizeof(int64_t), "index type");
+  return run_greedy(c, kf, beta, X, y, n, d, n_experts, first_index, m_target, reinterpret_cast<long long*>(indices_out));
 }
 
 int sgp_cross_kernel(sgp_ctx* h, const double* X, int64_t n, double* K_out) {

@@ -62,7 +62,7 @@ struct Ctx {
   cusolverDnHandle_t solver2 = nullptr;   // bound to tail_stream
   cublasHandle_t blas = nullptr;
   cudaEvent_t tail_fork = nullptr, tail_join = nullptr;
-  DevScratch tail_ws, tail_ws2, predict_ws, cross_ws, bcm_ws, sweep_ws;
+  DevScratch tail_ws, tail_ws2, predict_ws, cross_ws, bcm_ws, sweep_ws, greedy_ws;
   bool has_magic_run = false;
   bool tail_fast = false;              // last sgp_magic took the Cholesky path for both matrices
   ncclComm_t comm = nullptr;
@@ -240,6 +240,9 @@ cudaError_t launch_laplace(const double* dX, const double* dy, double* df, const
                            double* dPerExpert, double* dTotal, int* dFlags, cudaStream_t s);
 
 int ctx_scratch(Ctx* c, DevScratch& s, size_t bytes);
+// csrc/greedy.cu: forward selection with rank-1 updates (ActiveSetProvider.scala:58-139); beta_flat = [n_terms][d]
+int run_greedy(Ctx* c, const KernelFlat& kf, const std::vector<double>& beta_flat, const double* X, const double* y,
+               long long n, int d, long long n_experts, long long first_index, int m_target, long long* indices_out);
 int run_tail(Ctx* c, double* magic_vector, double* magic_matrix);
 int run_predict(Ctx* c, const double* X, long long n, double* mean_out, double* var_out);
 

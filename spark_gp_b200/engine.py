@@ -286,6 +286,18 @@ class ProjectedProcessEngine:
         self._check(self._lib.sgp_cross_kernel(self._h, N.ptr(X), len(X), N.ptr(K)))
         return K
 
+    def greedy_active_set(self, kernel: Kernel, X, y, n_experts: int, first_index: int, m_target: int):
+        """Row indices of the points GreedilyOptimizingActiveSetProvider selects (ActiveSetProvider.scala:58-139), computed
+        with rank-1 updates on the device (`sgp_greedy_active_set`): O(n m) per round instead of a statistics pass."""
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        y = np.ascontiguousarray(y, dtype=np.float64)
+        desc, keep = _make_desc(kernel, X.shape[1])
+        idx = np.empty(int(m_target), dtype=np.int64)
+        self._check(self._lib.sgp_greedy_active_set(self._h, C.byref(desc), N.ptr(X), N.ptr(y), len(X), X.shape[1],
+                                                    int(n_experts), int(first_index), int(m_target), N.ptr(idx)))
+        del keep
+        return idx
+
     def kmn_sweep(self, X):
         """fp32 K[i][j] = k(x_i, z_j) (n x m) through the tensor-core sweep kernel (one non-Eye term, d <= 32)."""
         X = np.asarray(X)

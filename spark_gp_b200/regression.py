@@ -70,11 +70,17 @@ class GreedilyOptimizingActiveSetProvider(ActiveSetProvider):
     Reference semantics kept: `s2` is the kernel's whiteNoiseVar (ASP:76); candidates are folded per expert (point i
     belongs to expert i % E) with later-wins ties and NaN poisoning, NaN experts are dropped (ASP:108-131), the first
     expert with the best score wins; points already selected are not excluded.  The first point is `takeSample(1,
-    seed)` in the reference (Spark's RNG stream is unpinned): `first_index` fixes it, else a seeded NumPy draw."""
+    seed)` in the reference (Spark's RNG stream is unpinned): `first_index` fixes it, else a seeded NumPy draw.
 
-    def __init__(self, first_index=None, precision=None):
+    `incremental=True` (default) runs the whole selection in `sgp_greedy_active_set`: the N x m cross kernel stays on the
+    device and p_i, q_i, mu_i and the two inverses follow from rank-1 (bordered-matrix) updates -- O(N m) per round, all
+    in fp64; `incremental=False` is the round-by-round form above (kept as the cross-check: both must select the points
+    the CPU restatement selects)."""
+
+    def __init__(self, first_index=None, precision=None, incremental=True):
         self.first_index = first_index
         self.precision = precision            # None: SGP_PREC_F64 (fp64 DMMA kernel); tests use SGP_PREC_F64_STRICT
+        self.incremental = incremental
 
     def __call__(self, activeSetSize, X, y, kernel_factory, optimalHyperparameter, seed, gp=None):
         X64 = np.ascontiguousarray(X, dtype=np.float64)
@@ -90,6 +96,9 @@ class GreedilyOptimizingActiveSetProvider(ActiveSetProvider):
         eng = ProjectedProcessEngine(gp._device if gp is not None else 0)
         eng.set_precision(N.SGP_PREC_F64 if self.precision is None else self.precision)
         try:
+            if self.incremental:
+                kernel = kernel_factory().setHyperparameters(theta)
+                return X64[eng.greedy_active_set(kernel, X64, y, E, first, activeSetSize)]
             while len(active) < activeSetSize:
                 kernel = kernel_factory().setHyperparameters(theta)
                 active = np.vstack([active, self._get_next(eng, kernel, X64, y, active, E)])

@@ -546,9 +546,12 @@ def test_greedy_active_set_provider_matches_oracle():
     gp = (sg.GaussianProcessRegression().setKernel(lambda: 1.3 * sg.ARDRBFKernel(beta) + sg.const(1) * sg.EyeKernel())
           .setSigma2(1e-2).setDatasetSizeForExpert(n_e).setActiveSetSize(m).setMaxIter(0)
           .setActiveSetProvider(sg.GreedilyOptimizingActiveSetProvider(first_index=5, precision=N.SGP_PREC_F64_STRICT)))
-    got = gp._activeSetProvider(m, X, y, gp.getKernel, theta, 13, gp=gp)
+    got = gp._activeSetProvider(m, X, y, gp.getKernel, theta, 13, gp=gp)          # rank-1 updates on the device (default)
     assert got.shape == want.shape
-    assert np.array_equal(got, want), "greedy selection differs from the restatement"
+    assert np.array_equal(got, want), "greedy selection (rank-1 updates) differs from the restatement"
+    slow = sg.GreedilyOptimizingActiveSetProvider(first_index=5, precision=N.SGP_PREC_F64_STRICT, incremental=False)
+    got2 = slow(m, X, y, gp.getKernel, theta, 13, gp=gp)                          # a statistics pass per round
+    assert np.array_equal(got2, want), "greedy selection (round-by-round form) differs from the restatement"
     # and through fit(): the model is the projected process on that active set
     model = gp.fit(X, y, hyperparameters=theta)
     k0 = ofac().set_hyperparameters(theta)
@@ -871,3 +874,58 @@ def test_i8_direct_norm_limit_and_error_growth(eng):
         errs.append((spread, rel(G, G0), rel(b, b0)))
     print("int8 direct, error vs cluster spread:", ", ".join("%g: dG=%.1e db=%.1e" % e for e in errs))
     assert all(e[1] < TOL_STATS and e[2] < TOL_STATS for e in errs)
+
+
+def test_greedy_rank1_larger_cases():
+    """The rank-1 form (sgp_greedy_active_set) on a case with 64 rounds and all-distinct selections against the CPU
+    restatement AND the round-by-round GPU form; a sum of two ARD terms with repeated selections (the reference does not
+    exclude selected points: nearly singular bordered steps -> the Cholesky refresh path) against the round-by-round form;
+    and the time per round at 200k points (the reference's form costs a statistics pass + two predictions per round)."""
+    import time
+    from oracle.active_set import greedy_active_set
+    rng = np.random.default_rng(77)
+    n, d, m, n_e = 3000, 4, 64, 100
+    X = rng.random((n, d)); y = np.sin(4 * X.sum(1)) + 0.1 * rng.standard_normal(n)
+    beta = np.full(d, 3.0)
+    ofac = oracle.get_kernel(lambda: 1.0 * oracle.ARDRBFKernel(beta) + oracle.const(1) * oracle.EyeKernel(), 1e-1)
+    theta = ofac().get_hyperparameters()
+    experts = oracle.get_expert_labels_and_kernels(X, y, ofac, n_e)
+    for _, k in experts:
+        k.set_hyperparameters(theta)
+    want = greedy_active_set(m, experts, ofac, theta, X[5])
+    gp = (sg.GaussianProcessRegression().setKernel(lambda: 1.0 * sg.ARDRBFKernel(beta) + sg.const(1) * sg.EyeKernel())
+          .setSigma2(1e-1).setDatasetSizeForExpert(n_e).setActiveSetSize(m).setMaxIter(0))
+    fast = sg.GreedilyOptimizingActiveSetProvider(first_index=5)
+    slow = sg.GreedilyOptimizingActiveSetProvider(first_index=5, precision=N.SGP_PREC_F64_STRICT, incremental=False)
+    a = fast(m, X, y, gp.getKernel, theta, 1, gp=gp)
+    b = slow(m, X, y, gp.getKernel, theta, 1, gp=gp)
+    print("greedy 3000 x 4 -> 64 points: %d distinct (oracle %d)" % (len(np.unique(a, axis=0)), len(np.unique(want, axis=0))))
+    assert np.array_equal(a, want), "rank-1 selection differs from the restatement"
+    assert np.array_equal(b, want), "round-by-round selection differs from the restatement"
+    # repeated selections, two terms, ragged last expert
+    n, d, m = 20011, 5, 48
+    X = rng.random((n, d)); y = np.sin(2 * X.sum(1)) + 0.1 * rng.standard_normal(n)
+    b1, b2 = rng.uniform(0.8, 2.5, d), rng.uniform(2.0, 5.0, d)
+    gp = (sg.GaussianProcessRegression().setKernel(lambda: 0.8 * sg.ARDRBFKernel(b1) + 0.5 * sg.ARDRBFKernel(b2))
+          .setSigma2(1e-2).setDatasetSizeForExpert(n_e).setActiveSetSize(m).setMaxIter(0))
+    theta = gp.getKernel().getHyperparameters()
+    fast = sg.GreedilyOptimizingActiveSetProvider(first_index=123)
+    slow = sg.GreedilyOptimizingActiveSetProvider(first_index=123, precision=N.SGP_PREC_F64_STRICT, incremental=False)
+    t0 = time.perf_counter(); a = fast(m, X, y, gp.getKernel, theta, 1, gp=gp); t1 = time.perf_counter()
+    b = slow(m, X, y, gp.getKernel, theta, 1, gp=gp); t2 = time.perf_counter()
+    print("greedy 20011 x 5 -> 48 points (%d distinct): rank-1 %.3f s, round-by-round %.3f s" % (
+        len(np.unique(a, axis=0)), t1 - t0, t2 - t1))
+    assert np.array_equal(a, b)
+    # scale: 200k points, 256 selected -- O(N m) per round
+    n2, d2, m2 = 200_000, 8, 256
+    X2 = rng.random((n2, d2)); y2 = np.sin(2 * X2.sum(1)) + 0.1 * rng.standard_normal(n2)
+    bb = np.full(d2, 3.0)
+    gp2 = (sg.GaussianProcessRegression().setKernel(lambda: 1 * sg.ARDRBFKernel(bb) + sg.const(1) * sg.EyeKernel())
+           .setSigma2(1e-1).setActiveSetSize(m2).setMaxIter(0))
+    fast = sg.GreedilyOptimizingActiveSetProvider(first_index=7)
+    t0 = time.perf_counter()
+    a2 = fast(m2, X2, y2, gp2.getKernel, gp2.getKernel().getHyperparameters(), 1, gp=gp2)
+    t1 = time.perf_counter()
+    print("greedy 200000 x 8 -> 256 points (%d distinct): rank-1 %.3f s = %.2f ms per round" % (
+        len(np.unique(a2, axis=0)), t1 - t0, 1e3 * (t1 - t0) / m2))
+    assert a2.shape == (m2, d2) and np.all(np.isfinite(a2))
