@@ -394,7 +394,7 @@ def run_ours(args):
         flops = algorithmic_flops_per_point(rp["m"], rp["d"]) * rp["n"] * args.steps / max(rp["kern_n"], 1)
         achieved_tf = flops / (launch_ms / 1e3) / 1e12
         traffic, traffic_src = ncu_traffic(prim)
-        roof = {"bound": "tensor", "kernel": "kmn_gram_i8_kernel", "achieved": achieved_tf, "peak": peak_tf,
+        roof = {"bound": "tensor", "kernel": "kmn_gram_i8_ring_kernel", "achieved": achieved_tf, "peak": peak_tf,
                 "unit": "TFLOP/s", "frac": achieved_tf / peak_tf, "peak_source": peak_src,
                 "traffic": traffic, "traffic_source": traffic_src, "launch_ms": launch_ms,
                 "launches_timed": rp["kern_n"], "algorithmic_flops_per_launch": flops,

@@ -534,6 +534,17 @@ int sgp_stats_accumulate(sgp_ctx* h, const void* X, int32_t x_is_f32, const doub
     chunk = ((n + nchunks - 1) / nchunks + 63) / 64 * 64;
   }
   if (chunk > n) chunk = n;
+  // The first chunk's copy is the only one the kernels cannot hide: make it a quarter of the others
+  long long first = chunk;
+  if (n > chunk) {
+    first = (chunk / 4 + 63) / 64 * 64;
+    if (first < 65536) first = 65536;
+    if (first > chunk) first = chunk;
+    const long long rest = n - first;
+    const long long nchunks = (rest + chunk - 1) / chunk;
+    chunk = ((rest + nchunks - 1) / nchunks + 63) / 64 * 64;
+    if (chunk < first) chunk = first;
+  }
   if (chunk > c->stage_points || row * chunk > c->stage_bytes) {
     SGP_CUDA(c, cudaStreamSynchronize(c->stream));
     SGP_CUDA(c, cudaStreamSynchronize(c->copy_stream));
@@ -548,8 +559,8 @@ int sgp_stats_accumulate(sgp_ctx* h, const void* X, int32_t x_is_f32, const doub
   }
   const char* Xb = static_cast<const char*>(X);
   int buf = 0;
-  for (long long p0 = 0; p0 < n; p0 += chunk, buf ^= 1) {
-    const long long cn = (n - p0 < chunk) ? (n - p0) : chunk;
+  for (long long p0 = 0, step = first; p0 < n; p0 += step, step = chunk, buf ^= 1) {
+    const long long cn = (n - p0 < step) ? (n - p0) : step;
     SGP_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->stage_free[buf], 0));
     SGP_CUDA(c, cudaMemcpyAsync(c->stageX[buf], Xb + static_cast<size_t>(p0) * row, row * cn, cudaMemcpyHostToDevice,
                                 c->copy_stream));

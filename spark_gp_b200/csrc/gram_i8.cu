@@ -249,8 +249,15 @@ __global__ void prep_points_kernel(uint8_t* __restrict__ Xt, float* __restrict__
                                    int d, int dp, int nchunks, const double* __restrict__ scale /*[dp]*/,
                                    const double* __restrict__ centre /*[dp]*/, int* __restrict__ flags,
                                    double* __restrict__ norm_sum, double* __restrict__ norm_sum_call) {
+  // 128 threads = two 64-point units.  A thread builds the operand row of its point into shared memory; the block then
+  // copies the rows out with 16-byte chunks of one 128-byte image row on consecutive threads (full-line stores).  Writing
+  // the rows straight from the owning thread put the 32 stores of a warp instruction into 32 different lines: 167 us per
+  // 1M x 16 points, 5 % of the statistics step.
+  extern __shared__ __align__(16) uint8_t prep_smem[];
+  __shared__ double warp_norm[4];
+  const int row_bytes = nchunks * 128 + 16;                        // +16: the row-owner stores spread over the banks
   const long long pt = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-  if (pt >= n_units * UP) return;
+  const bool in_grid = pt < n_units * UP;
   const bool valid = pt < n;
   double v[32];
   for (int k = 0; k < dp; ++k) {
@@ -269,22 +276,35 @@ __global__ void prep_points_kernel(uint8_t* __restrict__ Xt, float* __restrict__
   if (norm_sum) {                                                // sum of scaled squared norms (AUTO's magnitude gate)
     double v2 = valid ? norm2 : 0.0;
     for (int o = 16; o > 0; o >>= 1) v2 += __shfl_xor_sync(0xffffffffu, v2, o);
-    if ((threadIdx.x & 31) == 0 && v2 > 0.0) {
-      atomicAdd(norm_sum, v2);
-      if (norm_sum_call) atomicAdd(norm_sum_call, v2);
-    }
+    if ((threadIdx.x & 31) == 0) warp_norm[threadIdx.x >> 5] = v2;     // one atomic per block (same-address atomics serialise)
   }
-  ys[pt] = (valid && y) ? static_cast<float>(y[pt]) : 0.f;
-  const long long unit = pt / UP;
-  const int r = static_cast<int>(pt % UP);
+  if (in_grid) ys[pt] = (valid && y) ? static_cast<float>(y[pt]) : 0.f;
+  uint8_t* myrow = prep_smem + threadIdx.x * row_bytes;
   for (int c = 0; c < nchunks; ++c) {
-    uint8_t* img = Xt + (static_cast<size_t>(unit) * nchunks + c) * XIMG_BYTES;
     for (int c16 = 0; c16 < 8; ++c16) {
       __align__(16) __half h[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) h[e] = operand_col<true>(s, dp, c * 64 + c16 * 8 + e, valid);
-      *reinterpret_cast<uint4*>(img + sw128_off(r, c16)) = *reinterpret_cast<const uint4*>(h);
+      *reinterpret_cast<uint4*>(myrow + c * 128 + c16 * 16) = *reinterpret_cast<const uint4*>(h);
     }
+  }
+  __syncthreads();
+  if (norm_sum && threadIdx.x == 0) {
+    const double v2 = (warp_norm[0] + warp_norm[1]) + (warp_norm[2] + warp_norm[3]);
+    if (v2 > 0.0) {
+      atomicAdd(norm_sum, v2);
+      if (norm_sum_call) atomicAdd(norm_sum_call, v2);
+    }
+  }
+  const long long unit0 = static_cast<long long>(blockIdx.x) * 2;
+  const int per_unit = nchunks * 512;                              // 16-byte chunks per unit: [chunk][64 rows][8]
+  for (int q = threadIdx.x; q < 2 * per_unit; q += blockDim.x) {
+    const int u = q / per_unit, rem = q % per_unit;
+    const int c = rem >> 9, r = (rem >> 3) & 63, c16 = rem & 7;
+    if (unit0 + u >= n_units) break;
+    const uint4 val = *reinterpret_cast<const uint4*>(prep_smem + (u * 64 + r) * row_bytes + c * 128 + c16 * 16);
+    uint8_t* img = Xt + (static_cast<size_t>(unit0 + u) * nchunks + c) * XIMG_BYTES;
+    *reinterpret_cast<uint4*>(img + sw128_off(r, c16)) = val;
   }
 }
 
@@ -777,9 +797,9 @@ cudaError_t launch_i8_prep_points(uint8_t* Xt, float* ys, const void* dX, int x_
   const int dp = (d + 15) / 16 * 16;
   const long long units = (n + UP - 1) / UP;
   const long long threads = units * UP;
-  prep_points_kernel<<<static_cast<unsigned>((threads + 127) / 128), 128, 0, s>>>(Xt, ys, dX, x_is_f32, dy, n, units, d, dp,
-                                                                                i8_nchunks(d), dScale, dCentre, dFlags,
-                                                                                dNormSum, dNormSumCall);
+  const int nch = i8_nchunks(d);
+  prep_points_kernel<<<static_cast<unsigned>((threads + 127) / 128), 128, 128 * (nch * 128 + 16), s>>>(
+      Xt, ys, dX, x_is_f32, dy, n, units, d, dp, nch, dScale, dCentre, dFlags, dNormSum, dNormSumCall);
   return cudaGetLastError();
 }
 
