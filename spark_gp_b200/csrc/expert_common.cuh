@@ -41,6 +41,7 @@ HyperView make_hyper_view(int d, const KernelFlat& kf, const double* dBeta, int 
 // total[c] = sum_e per_expert[e][c], deterministic
 cudaError_t launch_rows_reduce(double* dTotal, const double* dPerExpert, long long E, int width, cudaStream_t s);
 
+template <int NW = EX_WARPS>
 __device__ __forceinline__ double ex_block_sum(double v, double* red) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
@@ -48,7 +49,7 @@ __device__ __forceinline__ double ex_block_sum(double v, double* red) {
   if (l == 0) red[w] = v;
   __syncthreads();
   double s = 0.0;
-  for (int i = 0; i < EX_WARPS; ++i) s += red[i];
+  for (int i = 0; i < NW; ++i) s += red[i];
   return s;
 }
 
@@ -163,6 +164,59 @@ __device__ __forceinline__ void ex_ltl_inplace(double* M, int n, int ld, double*
   }
 }
 
+// Tail of a gradient sweep: block-reduce the per-thread sums (fixed order: deterministic) and turn them into the
+// hyper-parameters this sweep owns.  S, Q: per term (sweep 0 only); D: the DCH dimensions k0 .. k0+kn-1 of term ts.
+template <int NW = EX_WARPS>
+__device__ __forceinline__ void ex_gradient_emit(const HyperView& hv, int sw, int ts, int k0, int kn,
+                                                 const double (&S)[kMaxTerms], const double (&Q)[kMaxTerms],
+                                                 const double (&D)[DCH], double trW, double factor, double* out,
+                                                 double* sums, double* red) {
+  const int tid = threadIdx.x;
+  double* sS = sums;                          // [kMaxTerms]
+  double* sQ = sums + kMaxTerms;              // [kMaxTerms]
+  double* sTr = sums + 2 * kMaxTerms;         // [1]
+  double* sD = sTr + 1;                       // [DCH]  per-dimension sums of this sweep's (term, dimension chunk)
+    if (sw == 0) {
+#pragma unroll
+    for (int t = 0; t < kMaxTerms; ++t) {
+      if (t < hv.n_terms) {
+        const double s_ = ex_block_sum<NW>(S[t], red), q_ = ex_block_sum<NW>(Q[t], red);
+        if (tid == 0) { sS[t] = s_; sQ[t] = q_; }
+      }
+    }
+    const double v = ex_block_sum<NW>(trW, red);
+    if (tid == 0) sTr[0] = v;
+  }
+#pragma unroll
+  for (int k = 0; k < DCH; ++k) {
+    if (k < kn) {
+      const double v = ex_block_sum<NW>(D[k], red);
+      if (tid == 0) sD[k] = v;
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < hv.n_hypers; i += EX_THREADS) {
+    const int kind = hv.h_kind[i];
+    double g = 0.0;
+    bool mine = (sw == 0);
+    if (kind == 0) {                                                 // trainable scalar above a sub-tree
+      const double* cf = hv.h_coef + static_cast<size_t>(i) * (kMaxTerms + 1);
+      g = cf[kMaxTerms] * sTr[0];
+      for (int t = 0; t < hv.n_terms; ++t) g = fma(cf[t], sS[t], g);
+    } else if (kind == 1) {                                          // ARD beta_k
+      const int t = hv.h_term[i], k = hv.h_dim[i];
+      mine = (t == ts && k >= k0 && k < k0 + kn);
+      if (mine) g = hv.scale[t] * (-2.0 * hv.h_value[i]) * sD[k - k0];
+    } else {                                                         // RBF sigma
+      const int t = hv.h_term[i];
+      const double sg = hv.h_value[i];
+      g = hv.scale[t] * sQ[t] / (sg * sg * sg);
+    }
+    if (mine) out[i] = factor * g;
+  }
+  __syncthreads();
+}
+
 // out[i] = factor * sum_ab dK_i[a,b] W_ab for every hyper-parameter;  wf(a, b), b <= a, returns the symmetric W_ab.
 // sums: EX_SUMS doubles of shared memory; red: 8 doubles.  All threads of the CTA must call it.
 template <class WF>
@@ -171,10 +225,6 @@ __device__ __forceinline__ void ex_descriptor_gradient(const HyperView& hv, cons
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int chunks = (hv.d + DCH - 1) / DCH;
   const int n_sweeps = hv.any_ard ? hv.n_terms * chunks : 1;
-  double* sS = sums;                          // [kMaxTerms]
-  double* sQ = sums + kMaxTerms;              // [kMaxTerms]
-  double* sTr = sums + 2 * kMaxTerms;         // [1]
-  double* sD = sTr + 1;                       // [DCH]  per-dimension sums of this sweep's (term, dimension chunk)
   for (int sw = 0; sw < n_sweeps; ++sw) {
     const int ts = hv.any_ard ? sw / chunks : -1;
     const int k0 = hv.any_ard ? (sw % chunks) * DCH : 0;
@@ -214,46 +264,7 @@ __device__ __forceinline__ void ex_descriptor_gradient(const HyperView& hv, cons
         }
       }
     }
-    // block-reduce into shared memory (fixed order: deterministic)
-    if (sw == 0) {
-#pragma unroll
-      for (int t = 0; t < kMaxTerms; ++t) {
-        if (t < hv.n_terms) {
-          const double s_ = ex_block_sum(S[t], red), q_ = ex_block_sum(Q[t], red);
-          if (tid == 0) { sS[t] = s_; sQ[t] = q_; }
-        }
-      }
-      const double v = ex_block_sum(trW, red);
-      if (tid == 0) sTr[0] = v;
-    }
-#pragma unroll
-    for (int k = 0; k < DCH; ++k) {
-      if (k < kn) {
-        const double v = ex_block_sum(D[k], red);
-        if (tid == 0) sD[k] = v;
-      }
-    }
-    __syncthreads();
-    for (int i = tid; i < hv.n_hypers; i += EX_THREADS) {
-      const int kind = hv.h_kind[i];
-      double g = 0.0;
-      bool mine = (sw == 0);
-      if (kind == 0) {                                                 // trainable scalar above a sub-tree
-        const double* cf = hv.h_coef + static_cast<size_t>(i) * (kMaxTerms + 1);
-        g = cf[kMaxTerms] * sTr[0];
-        for (int t = 0; t < hv.n_terms; ++t) g = fma(cf[t], sS[t], g);
-      } else if (kind == 1) {                                          // ARD beta_k
-        const int t = hv.h_term[i], k = hv.h_dim[i];
-        mine = (t == ts && k >= k0 && k < k0 + kn);
-        if (mine) g = hv.scale[t] * (-2.0 * hv.h_value[i]) * sD[k - k0];
-      } else {                                                         // RBF sigma
-        const int t = hv.h_term[i];
-        const double sg = hv.h_value[i];
-        g = hv.scale[t] * sQ[t] / (sg * sg * sg);
-      }
-      if (mine) out[i] = factor * g;
-    }
-    __syncthreads();
+    ex_gradient_emit(hv, sw, ts, k0, kn, S, Q, D, trW, factor, out, sums, red);
   }
 }
 
