@@ -49,7 +49,7 @@ class GaussianProcessClassifier(GaussianProcessParams):
         y = np.asarray(y, dtype=np.float64)
         if not np.all((y == 0.0) | (y == 1.0)):                     # assertLabelsAre01, GPCls:68-72
             raise RuntimeError("Only 0 and 1 labels are supported.")
-        eng = ProjectedProcessEngine(self._device)
+        eng = ProjectedProcessEngine.acquire(self._device)
         groups = group_for_experts(len(X), self._datasetSizeForExpert)
         order = np.concatenate(groups)
         eng.experts_upload_grouped(X, y, self._datasetSizeForExpert)  # grouping on the device; f = zeros per expert (GPCls:53-55)

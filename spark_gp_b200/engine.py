@@ -61,6 +61,32 @@ class ProjectedProcessEngine:
         if rc != N.SGP_OK:
             raise SgpError("sgp_ctx_create failed (%d): %s" % (rc, self._lib.sgp_last_error(None).decode()))
         self.m = self.d = 0
+        self._device = device
+        self._has_comm = False
+
+    # ---- a small per-device pool: creating a context costs ~20 ms (streams, cuBLAS, cuSOLVER) and a fresh context
+    #      re-allocates every grow-only workspace; an estimator that fits repeatedly gets its contexts back from here ----
+    _idle = {}
+    _IDLE_MAX = 4
+
+    @classmethod
+    def acquire(cls, device: int = 0):
+        pool = cls._idle.get(device)
+        if pool:
+            eng = pool.pop()
+            eng.set_precision(N.SGP_PREC_AUTO)
+            return eng
+        return cls(device)
+
+    def release(self):
+        """Hand the context back to the pool (or destroy it when the pool is full or it carries a communicator)."""
+        if not self._h:
+            return
+        pool = ProjectedProcessEngine._idle.setdefault(self._device, [])
+        if self._has_comm or len(pool) >= ProjectedProcessEngine._IDLE_MAX:
+            self.close()
+        else:
+            pool.append(self)
 
     def close(self):
         if self._h:
@@ -104,6 +130,7 @@ class ProjectedProcessEngine:
     def comm_init(self, unique_id: bytes, rank: int, nranks: int):
         buf = C.create_string_buffer(unique_id, N.SGP_UNIQUE_ID_BYTES)
         self._check(self._lib.sgp_comm_init(self._h, buf, rank, nranks))
+        self._has_comm = True
 
     # ---- getMatrixKmnKnmAndVectorKmny ---------------------------------------------------------------
     def begin(self, kernel: Kernel, active_set):

@@ -77,7 +77,7 @@ class BcmObjective:
 def optimize_hypers(gp, X, y, engine: ProjectedProcessEngine | None = None):
     """Returns the optimal hyper-parameter vector (layout of Kernel.getHyperparameters)."""
     own = engine is None
-    engine = engine or ProjectedProcessEngine(gp._device)
+    engine = engine or ProjectedProcessEngine.acquire(gp._device)
     try:
         obj = BcmObjective(engine, gp.getKernel, X, y, gp._datasetSizeForExpert)
         k0 = gp.getKernel()
@@ -91,4 +91,4 @@ def optimize_hypers(gp, X, y, engine: ProjectedProcessEngine | None = None):
         return np.asarray(res.x, dtype=np.float64)
     finally:
         if own:
-            engine.close()
+            engine.release()

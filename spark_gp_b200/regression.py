@@ -28,7 +28,7 @@ class _RandomActiveSetProvider(ActiveSetProvider):
     def __call__(self, activeSetSize, X, y, kernel_factory, optimalHyperparameter, seed, gp=None):
         rng = np.random.default_rng(seed)
         idx = rng.choice(len(X), size=min(activeSetSize, len(X)), replace=False)
-        return np.asarray(X, dtype=np.float64)[idx]
+        return np.asarray(np.asarray(X)[idx], dtype=np.float64)     # index first: no fp64 copy of the whole shard
 
 
 RandomActiveSetProvider = _RandomActiveSetProvider()
@@ -93,7 +93,7 @@ class GreedilyOptimizingActiveSetProvider(ActiveSetProvider):
         first = self.first_index if self.first_index is not None else int(np.random.default_rng(seed).integers(n))
         active = X64[[first]].copy()
         theta = np.asarray(optimalHyperparameter, dtype=np.float64)
-        eng = ProjectedProcessEngine(gp._device if gp is not None else 0)
+        eng = ProjectedProcessEngine.acquire(gp._device if gp is not None else 0)
         eng.set_precision(N.SGP_PREC_F64 if self.precision is None else self.precision)
         try:
             if self.incremental:
@@ -103,7 +103,7 @@ class GreedilyOptimizingActiveSetProvider(ActiveSetProvider):
                 kernel = kernel_factory().setHyperparameters(theta)
                 active = np.vstack([active, self._get_next(eng, kernel, X64, y, active, E)])
         finally:
-            eng.close()
+            eng.release()
         return active
 
     @staticmethod
@@ -189,6 +189,12 @@ class GaussianProjectedProcessRawPredictor:
         self._engine = engine
         self.magicVector, self.magicMatrix, self.kernel, self.activeSet = magicVector, magicMatrix, kernel, activeSet
 
+    def __del__(self):                          # the context goes back to the per-device pool
+        try:
+            self._engine.release()
+        except Exception:
+            pass
+
     def predict(self, features):
         """(mean, variance) for one vector or a block of vectors."""
         f = np.asarray(features, dtype=np.float64)
@@ -240,7 +246,7 @@ class GaussianProcessRegression(GaussianProcessParams):
         """produceModel -> projectedProcess  (commons/GaussianProcessCommons.scala:40-59, 102-110)."""
         active_set = self._activeSetProvider(self._activeSetSize, X, y, self.getKernel, theta, self._seed, gp=self)
         kernel = self.getKernel().setHyperparameters(theta)
-        eng = ProjectedProcessEngine(self._device)
+        eng = ProjectedProcessEngine.acquire(self._device)
 
         G, b = eng.statistics(kernel, active_set, X, y, self._shard_points)   # PGPH:20-36 (+ fp64-kernel fallback)
         mv, mm = eng.magic()                                            # PGPH:49-60
