@@ -192,18 +192,21 @@ __global__ void __launch_bounds__(REG_THREADS, 1) bcm_nll_reg_kernel(const NllPa
 #pragma unroll
       for (int c = 0; c < RBC; ++c) cj[c] = cb[tx + 16 * c] * pinv;
       const bool rowk = (ty == ky), colk = (tx == kx);
+      // the generic rank-1 update everywhere, then the pivot row / column are overwritten by their owners (selecting per
+      // element cost 70 of the 140 instructions of a sweep)
 #pragma unroll
       for (int r = 0; r < RBR; ++r)
 #pragma unroll
-        for (int c = 0; c < RBC; ++c) {
-          if (r == rk || c == ck) {
-            const bool ik = (r == rk) && rowk, jk = (c == ck) && colk;
-            const double upd = fma(-ci[r], cj[c], A[r][c]);
-            A[r][c] = ik ? (jk ? -pinv : cj[c]) : (jk ? ci[r] * pinv : upd);
-          } else {
-            A[r][c] = fma(-ci[r], cj[c], A[r][c]);
-          }
-        }
+        for (int c = 0; c < RBC; ++c) A[r][c] = fma(-ci[r], cj[c], A[r][c]);
+      if (colk) {                             // column k: A_ik / p
+#pragma unroll
+        for (int r = 0; r < RBR; ++r) A[r][ck] = ci[r] * pinv;
+      }
+      if (rowk) {                             // row k: A_kj / p, and -1/p on the diagonal
+#pragma unroll
+        for (int c = 0; c < RBC; ++c) A[rk][c] = cj[c];
+        if (colk) A[rk][ck] = -pinv;
+      }
     }
   }
   if (bad && tid == 0) atomicOr(p.flags, 1);
