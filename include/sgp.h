@@ -75,7 +75,7 @@ enum {
                               as 23-bit fixed point in three balanced int8 digits, Gram = six kind::i8 products with
                               EXACT int32 accumulation, folded into fp64.  Kernels with one non-Eye term, d <= 32; other
                               qualifying shapes are served by SGP_PREC_I8_DIRECT (sgp_last_path tells which ran).       */
-  SGP_PREC_AUTO = 3,       /* default: SGP_PREC_I8 when the kernel/shape qualifies AND the shard has >= 262144 points,
+  SGP_PREC_AUTO = 3,       /* default: SGP_PREC_I8 when the kernel/shape qualifies AND the accumulate call brings >= 32768 points,
                               else SGP_PREC_I8_DIRECT when THAT qualifies, else SGP_PREC_F64 ('precision')    */
   SGP_PREC_I8_DIRECT = 4   /* same exact int8 Gram as SGP_PREC_I8, but the exponents come from fp32 DIRECT-FORM distances on
                               the CUDA cores (no cancellation; coordinates are centred on the active-set mean in fp64

@@ -114,10 +114,11 @@ static int launch_stats(Ctx* c, const void* dX, int x_is_f32, const double* dy, 
   p.Gpart = c->dGpart; p.bpart = c->dBpart;
   p.n_slices = n_slices; p.n_tiles_1d = nt1;
 
-  // AUTO: the tcgen05 int8 kernel only inside its measured parity envelope -- shards of >= 262144 points (posterior
-  // mean within 1.1e-6 .. 2.4e-6 of the all-fp64 kernel for N = 250k .. 4M, profiles/r01_i8_scaling.txt; the limit
-  // is the two dropped low-order digit products, tools/i8_error_model.py) and small scaled norms (gate below).
-  // Smaller shards stay on the fp64 DMMA kernel (2e-7), which is fast enough at that size.
+  // AUTO: the tcgen05 int8 kernel inside its measured parity envelope -- accumulate calls of >= 32768 points (posterior
+  // mean within 1.1e-6 .. 2.4e-6 of the all-fp64 kernel for N = 16k .. 4M: profiles/r01_i8_scaling.txt,
+  // profiles/r02n_i8_small_shards.txt; the limit is the two dropped low-order digit products, tools/i8_error_model.py,
+  // and does not grow towards small N) and small scaled norms (gate below).  Smaller calls stay on the fp64 DMMA kernel
+  // (2e-7), which needs < 2 ms at that size.
   // Path of this launch: 0 = fp64 DMMA kernel, 1 = int8 Gram with tensor-core distances (one term, d <= 32, benign norms),
   // 2 = int8 Gram with direct fp32 distances (up to 4 terms, any norms).
   const bool tensor_ok = c->i8_ok, direct_ok = c->i8_direct_ok && c->i8_impl == 1 && n_plan > 0;
@@ -130,7 +131,7 @@ static int launch_stats(Ctx* c, const void* dX, int x_is_f32, const double* dy, 
   } else if (c->precision == SGP_PREC_I8_DIRECT) {
     if (!direct_ok) return fail(c, SGP_E_BADARG, "SGP_PREC_I8_DIRECT needs a kernel with 1..4 non-Eye terms and n_terms * d <= 72");
     path = 2;
-  } else if (c->precision == SGP_PREC_AUTO && n_call >= 262144) {
+  } else if (c->precision == SGP_PREC_AUTO && n_call >= kAutoI8MinPoints) {
     path = tensor_ok ? 1 : (direct_ok ? 2 : 0);
     if (!first_of_call) path = c->call_path;
   }

@@ -14,6 +14,8 @@
 
 namespace sgp {
 
+// SGP_PREC_AUTO runs the int8 Gram on accumulate calls of at least this many points (smaller ones: fp64 DMMA kernel)
+constexpr long long kAutoI8MinPoints = 32768;
 constexpr int kMaxTerms = 4;      // non-Eye terms of a flattened kernel
 constexpr int kTile = 128;        // edge of one G tile (active-set indices per CTA tile)
 constexpr int kSMsB200 = 148;

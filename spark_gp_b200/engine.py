@@ -184,7 +184,7 @@ class ProjectedProcessEngine:
         except OperandRangeError:
             # tensor-core distances refused the shard: the int8 Gram with direct fp32 distances takes larger norms; the
             # fp64 DMMA kernel takes anything
-            if self.last_path() == N.SGP_PREC_I8 and len(X) >= 262144:
+            if self.last_path() == N.SGP_PREC_I8 and len(X) >= 32768:
                 self.set_precision(N.SGP_PREC_I8_DIRECT)
                 try:
                     return run()

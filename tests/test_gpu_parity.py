@@ -585,7 +585,7 @@ def _oracle_stats_chunked(ok, X, y, Z, chunk=2048):
 
 
 def test_i8_headline_path_vs_oracle(eng):
-    """BASELINE configs[1] shape on a shard AUTO routes to the tcgen05 int8 kernel (>= 262144 points): G, b <= 1e-6
+    """BASELINE configs[1] shape on a shard AUTO routes to the tcgen05 int8 kernel (>= 32768 points): G, b <= 1e-6
     (SURVEY 8(d) gate) and posterior mean / variance at 1000 held-out points <= 1e-5 against the ORACLE itself (all
     worker cores, ~3 s) -- not against another kernel of this library."""
     from oracle.cpu_baseline import stats_parallel
