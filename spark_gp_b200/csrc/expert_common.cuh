@@ -125,6 +125,7 @@ __device__ __forceinline__ void ex_invert_lower(double* M, int n, int ld, double
     for (int i = k + 1 + warp; i < n; i += EX_WARPS) {
       const double f = M[i * ld + k];
       for (int j = lane; j < k; j += 32) M[i * ld + j] = fma(-f, rowbuf[j], M[i * ld + j]);
+      __syncwarp();                                           // every lane has read M[i][k] before lane 0 overwrites it
       if (lane == 0) M[i * ld + k] = -f * rowbuf[k];
     }
   }
