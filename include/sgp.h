@@ -75,13 +75,19 @@ enum {
                               as 23-bit fixed point in three balanced int8 digits, Gram = six kind::i8 products with
                               EXACT int32 accumulation, folded into fp64.  Kernels with one non-Eye term, d <= 32; other
                               qualifying shapes are served by SGP_PREC_I8_DIRECT (sgp_last_path tells which ran).       */
-  SGP_PREC_AUTO = 3,       /* default: SGP_PREC_I8 when the kernel/shape qualifies AND the accumulate call brings >= 32768 points,
-                              else SGP_PREC_I8_DIRECT when THAT qualifies, else SGP_PREC_F64 ('precision')    */
+  SGP_PREC_AUTO = 3,       /* default.  An accumulate call of >= 32768 points whose scaled squared norms are small (mean over
+                              points + mean over the active set <= 8: the kernel values are not tiny) runs the int8 Gram --
+                              SGP_PREC_I8 when the kernel / shape qualifies, else SGP_PREC_I8_DIRECT when THAT qualifies;
+                              everything else runs SGP_PREC_F64.  The budget is decided on the first chunk of a call and
+                              re-checked over the whole begin..finish window (SGP_E_RANGE at finish -> rerun in F64).
+                              On large-norm data the fixed-point elements (absolute error 2^-24) are not parity-grade
+                              whatever the distance form ('precision': airfoil-like data 1.5e-4 .. 1.5e-2 on
+                              the posterior mean), hence the budget applies to both int8 modes.                         */
   SGP_PREC_I8_DIRECT = 4   /* same exact int8 Gram as SGP_PREC_I8, but the exponents come from fp32 DIRECT-FORM distances on
                               the CUDA cores (no cancellation; coordinates are centred on the active-set mean in fp64
                               first) and the kernel may be a sum of up to 4 non-Eye terms (kernel/SumOfKernels.scala:57-58)
-                              with n_terms * roundup(d, 4) <= 72.  Scaled squared norms up to 2048.  AUTO picks it for large
-                              shards that SGP_PREC_I8 cannot take (several terms, 32 < d <= 72, norms above its budget). */
+                              with n_terms * roundup(d, 4) <= 72.  Scaled squared norms up to 2048 (statistics <= 1e-6);
+                              requesting it explicitly asserts that the data are benign (see SGP_PREC_AUTO).            */
 };
 
 /* ---- context ------------------------------------------------------------------------------ */

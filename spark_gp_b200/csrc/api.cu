@@ -3,6 +3,7 @@
 
 #include <dlfcn.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <new>
@@ -177,8 +178,11 @@ static int launch_stats(Ctx* c, const void* dX, int x_is_f32, const double* dy, 
       SGP_CUDA(c, cudaMemcpyAsync(&xsum, c->dI8NormSum + 1, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
       SGP_CUDA(c, cudaStreamSynchronize(c->stream));
       if (xsum / static_cast<double>(n) + c->i8_z_norm_mean > c->i8_norm_budget) {
+        // Large scaled norms mean tiny kernel values, and the fixed-point digits carry an ABSOLUTE error of 2^-24: on
+        // such shards the int8 Gram -- with either distance form -- loses the posterior mean (airfoil-like data: 1.5e-4
+        // to 1.5e-2 against 7e-7 .. 7e-6 of the fp64 kernel, profiles/r02o_i8_conditioning.txt).  fp64 DMMA kernel.
         use_i8 = false;
-        path = direct_ok ? 2 : 0;      // large norms: exponents from direct-form fp32 distances instead (no cancellation)
+        path = 0;
       }
     }
   }
@@ -190,11 +194,25 @@ static int launch_stats(Ctx* c, const void* dX, int x_is_f32, const double* dy, 
       SGP_CUDA(c, cudaMalloc(&c->dI8Xt, xb));
       c->i8_xt_bytes = xb;
     }
+    // AUTO applies the same magnitude budget as with tensor-core distances (on the WIDEST term's scaled squared norms: it
+    // sets the size of the kernel values): first chunk here, whole window at finish
+    const bool dgate = (c->precision == SGP_PREC_AUTO) && first_of_call;
+    const bool dbudget = (c->precision == SGP_PREC_AUTO);
+    if (dgate) SGP_CUDA(c, cudaMemsetAsync(c->dI8NormSum + 1, 0, sizeof(double), c->stream));
     SGP_CUDA(c, launch_i8_prep_points_direct(reinterpret_cast<float*>(c->dI8Xt), c->dI8Ys, dX, x_is_f32, dy, n, c->d,
                                              c->i8_dpad4, c->kf.n_terms, c->dI8DScale,
                                              c->dI8DScale + static_cast<size_t>(kMaxTerms) * c->i8_dpad4, c->dI8Flags,
-                                             c->i8_direct_r2max, c->stream));
+                                             c->i8_direct_r2max, dbudget ? c->dI8NormSum : nullptr,
+                                             dgate ? c->dI8NormSum + 1 : nullptr, c->stream));
     c->launches += 1;
+    if (dgate) {
+      double xsum = 0.0;
+      SGP_CUDA(c, cudaMemcpyAsync(&xsum, c->dI8NormSum + 1, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+      SGP_CUDA(c, cudaStreamSynchronize(c->stream));
+      if (xsum / static_cast<double>(n) + c->i8d_z_norm_mean > c->i8_norm_budget) path = 0;
+    }
+  }
+  if (path == 2) {
     direct.on = 1; direct.n_terms = c->kf.n_terms; direct.dpad4 = c->i8_dpad4;
     double csum = 0.0;
     for (int t = 0; t < c->kf.n_terms; ++t) csum += c->kf.scale[t];
@@ -203,7 +221,8 @@ static int launch_stats(Ctx* c, const void* dX, int x_is_f32, const double* dy, 
     c->i8_direct_used = true;
   }
   if (first_of_call) c->call_path = path;
-  if (use_i8) { c->i8_used = true; c->i8_points += n; }
+  if (use_i8 || path == 2) c->i8_points += n;
+  if (use_i8) c->i8_used = true;
   c->last_path = (path == 1) ? SGP_PREC_I8 : (path == 2) ? SGP_PREC_I8_DIRECT
                  : (c->precision == SGP_PREC_F64_STRICT ? SGP_PREC_F64_STRICT : SGP_PREC_F64);
   if (c->gram_events_used == c->gram_events.size()) {          // grow the event pool (steady state: no creation)
@@ -485,6 +504,21 @@ int sgp_stats_begin(sgp_ctx* h, const sgp_kernel_desc* k, const double* Z, int32
         for (int i = 0; i < m; ++i) acc += Z[static_cast<size_t>(i) * d + j];
         sc[static_cast<size_t>(kMaxTerms) * dpad4 + j] = acc / m;
       }
+      {                                                   // mean scaled squared norm of the active set, widest term
+        double best = 1e300;
+        for (int t = 0; t < kf.n_terms; ++t) {
+          double zsum = 0.0;
+          for (int i = 0; i < m; ++i)
+            for (int j = 0; j < d; ++j) {
+              const double v = (Z[static_cast<size_t>(i) * d + j] - sc[static_cast<size_t>(kMaxTerms) * dpad4 + j]) *
+                               sc[static_cast<size_t>(t) * dpad4 + j];
+              zsum += v * v;
+            }
+          best = std::min(best, zsum / m);
+        }
+        c->i8d_z_norm_mean = best;
+        if (const char* e = getenv("SGP_I8_NORM_BUDGET")) c->i8_norm_budget = atof(e);
+      }
       const size_t zd_bytes = static_cast<size_t>(c->m_pad / kTile) * kf.n_terms * kTile * dpad4 * sizeof(float);
       if (!same_shape || !c->dI8Zd) {
         cudaFree(c->dI8Zd); cudaFree(c->dI8DScale); c->dI8Zd = nullptr; c->dI8DScale = nullptr;
@@ -592,8 +626,9 @@ int sgp_stats_finish(sgp_ctx* h, double* G_out, double* b_out) {
     // bailed out before it would leave its peers blocked in ncclAllReduce.
     const bool i8 = c->i8_ok && c->i8_used && c->dI8Flags;
     const bool i8d = c->i8_direct_used && c->dI8Flags;          // direct mode: bit 2 = scaled squared norm above its limit
-    const bool budget = i8 && c->precision == SGP_PREC_AUTO;
-    const double limit = (c->i8_norm_budget - c->i8_z_norm_mean) * static_cast<double>(c->i8_points) * 1.25;
+    const bool budget = (i8 || i8d) && c->precision == SGP_PREC_AUTO;
+    const double zmean = (i8 && i8d) ? std::min(c->i8_z_norm_mean, c->i8d_z_norm_mean) : (i8 ? c->i8_z_norm_mean : c->i8d_z_norm_mean);
+    const double limit = (c->i8_norm_budget - zmean) * static_cast<double>(c->i8_points) * 1.25;
     SGP_CUDA(c, launch_status_to_double(c->dGb + mm + c->m, (i8 || i8d) ? c->dI8Flags : nullptr, (i8 ? 1 : 0) | (i8d ? 4 : 0),
                                         budget ? c->dI8NormSum : nullptr, limit, c->stream));
     c->launches += 1;

@@ -343,14 +343,15 @@ __global__ void prep_points_direct_kernel(float* __restrict__ Xd, float* __restr
                                           int x_is_f32, const double* __restrict__ y, long long n, long long n_units, int d,
                                           int dpad4, int n_terms, const double* __restrict__ scale /*[n_terms][dpad4]*/,
                                           const double* __restrict__ centre /*[dpad4]*/, int* __restrict__ flags,
-                                          float r2max) {
+                                          float r2max, double* __restrict__ norm_sum, double* __restrict__ norm_sum_call) {
+  __shared__ double warp_norm[4];
   const long long pt = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-  if (pt >= n_units * UP) return;
+  const bool in_grid = pt < n_units * UP;
   const bool valid = pt < n;
   const long long unit = pt / UP;
   const int pp = static_cast<int>(pt % UP);
   float r2[kMaxTerms] = {0.f, 0.f, 0.f, 0.f};
-  for (int k = 0; k < dpad4; ++k) {
+  for (int k = 0; k < dpad4 && in_grid; ++k) {
     double x = 0.0;
     if (valid && k < d) {
       const size_t off = static_cast<size_t>(pt) * d + k;
@@ -366,7 +367,22 @@ __global__ void prep_points_direct_kernel(float* __restrict__ Xd, float* __restr
   }
   // fp32 coordinates: the exponent's rounding error grows like 2^-24 * sqrt(q) * (|x~| + |z~|)
   if (valid && !(fmaxf(fmaxf(r2[0], r2[1]), fmaxf(r2[2], r2[3])) <= r2max)) atomicOr(flags, 4);
-  if (ys) ys[pt] = (valid && y) ? static_cast<float>(y[pt]) : 0.f;
+  if (ys && in_grid) ys[pt] = (valid && y) ? static_cast<float>(y[pt]) : 0.f;
+  if (norm_sum) {                               // AUTO's magnitude budget: scaled squared norm under the WIDEST term
+    float rmin = r2[0];
+    for (int t = 1; t < n_terms; ++t) rmin = fminf(rmin, r2[t]);
+    double v2 = valid ? static_cast<double>(rmin) : 0.0;
+    for (int o = 16; o > 0; o >>= 1) v2 += __shfl_xor_sync(0xffffffffu, v2, o);
+    if ((threadIdx.x & 31) == 0) warp_norm[threadIdx.x >> 5] = v2;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const double tot = (warp_norm[0] + warp_norm[1]) + (warp_norm[2] + warp_norm[3]);
+      if (tot > 0.0) {
+        atomicAdd(norm_sum, tot);
+        if (norm_sum_call) atomicAdd(norm_sum_call, tot);
+      }
+    }
+  }
 }
 
 __global__ void prep_active_direct_kernel(float* __restrict__ Zd, const double* __restrict__ Z, int m, int m_pad, int d,
@@ -813,11 +829,12 @@ cudaError_t launch_i8_prep_active_direct(float* Zd, const double* dZ, int m, int
 
 cudaError_t launch_i8_prep_points_direct(float* Xd, float* ys, const void* dX, int x_is_f32, const double* dy, long long n,
                                          int d, int dpad4, int n_terms, const double* dScale, const double* dCentre, int* flags,
-                                         float r2max, cudaStream_t s) {
+                                         float r2max, double* dNormSum, double* dNormSumCall, cudaStream_t s) {
   const long long units = (n + UP - 1) / UP;
   const long long threads = units * UP;
   prep_points_direct_kernel<<<static_cast<unsigned>((threads + 127) / 128), 128, 0, s>>>(Xd, ys, dX, x_is_f32, dy, n, units, d,
-                                                                                       dpad4, n_terms, dScale, dCentre, flags, r2max);
+                                                                                       dpad4, n_terms, dScale, dCentre, flags, r2max, dNormSum,
+                                                                                       dNormSumCall);
   return cudaGetLastError();
 }
 

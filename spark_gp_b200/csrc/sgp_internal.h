@@ -91,6 +91,7 @@ struct Ctx {
   double* dI8DScale = nullptr;   // [n_terms][dpad4] sqrt(log2 e) * beta_tk ; then [dpad4] centre
   bool i8_direct_used = false;
   bool i8_used = false;          // an int8 launch contributed to the current statistics
+  double i8d_z_norm_mean = 0.0;    // direct mode: mean scaled squared norm of the active set (widest term) for AUTO's budget
   float i8_direct_r2max = 2048.f;  // direct mode: largest scaled squared norm accepted (env SGP_I8_DIRECT_R2MAX); measured
                                    // dG 6.6e-7 at ~1300 and 2.7e-6 at ~7700 on clustered data (tests: error_growth)
   int call_path = 0;             // AUTO's decision for the current accumulate call (taken on its first chunk): 0 fp64,
@@ -190,7 +191,7 @@ cudaError_t launch_i8_prep_active_direct(float* Zd, const double* dZ, int m, int
                                          cudaStream_t s);
 cudaError_t launch_i8_prep_points_direct(float* Xd, float* ys, const void* dX, int x_is_f32, const double* dy, long long n,
                                          int d, int dpad4, int n_terms, const double* dScale, const double* dCentre, int* flags,
-                                         float r2max, cudaStream_t s);
+                                         float r2max, double* dNormSum, double* dNormSumCall, cudaStream_t s);
 struct I8Direct {
   int on = 0;            // 1: exponents from fp32 direct-form distances on the CUDA cores (any norms, up to 4 terms)
   int n_terms = 0, dpad4 = 0;

@@ -172,8 +172,7 @@ class ProjectedProcessEngine:
     def statistics(self, kernel: Kernel, active_set, X, y, shard_points: int = 1 << 22):
         """`getMatrixKmnKnmAndVectorKmny` over host data in shards (PGPH:23 broadcast, PGPH:25-35 seqOp over shards).
         When the tcgen05 int8 path reports SGP_E_RANGE (coordinates outside its operand range, or AUTO's magnitude
-        budget exceeded over the whole window) the pass is repeated with direct fp32 distances, then on the fp64 DMMA
-        kernel -- still on the GPU."""
+        budget exceeded over the whole window) the pass is repeated on the fp64 DMMA kernel -- still on the GPU."""
         def run():
             self.begin(kernel, active_set)
             for s in range(0, len(X), shard_points):
@@ -182,14 +181,8 @@ class ProjectedProcessEngine:
         try:
             return run()
         except OperandRangeError:
-            # tensor-core distances refused the shard: the int8 Gram with direct fp32 distances takes larger norms; the
-            # fp64 DMMA kernel takes anything
-            if self.last_path() == N.SGP_PREC_I8 and len(X) >= 32768:
-                self.set_precision(N.SGP_PREC_I8_DIRECT)
-                try:
-                    return run()
-                except (OperandRangeError, ValueError):
-                    pass
+            # the int8 Gram refused the shard (coordinates outside its operand range, or scaled norms above AUTO's budget:
+            # tiny kernel values, where its fixed-point elements are not parity-grade): the fp64 DMMA kernel takes anything
             self.set_precision(N.SGP_PREC_F64)
             return run()
 
