@@ -121,7 +121,7 @@ static int launch_stats(Ctx* c, const void* dX, int x_is_f32, const double* dy, 
   // and does not grow towards small N) and small scaled norms (gate below).  Smaller calls stay on the fp64 DMMA kernel
   // (2e-7), which needs < 2 ms at that size.
   // Path of this launch: 0 = fp64 DMMA kernel, 1 = int8 Gram with tensor-core distances (one term, d <= 32, benign norms),
-  // 2 = int8 Gram with direct fp32 distances (up to 4 terms, any norms).
+  // 2 = int8 Gram with direct fp32 distances (up to 4 terms, d <= 72; AUTO: same magnitude budget as path 1).
   const bool tensor_ok = c->i8_ok, direct_ok = c->i8_direct_ok && c->i8_impl == 1 && n_plan > 0;
   int path = 0;
   if (c->precision == SGP_PREC_I8) {
@@ -488,7 +488,7 @@ int sgp_stats_begin(sgp_ctx* h, const sgp_kernel_desc* k, const double* Z, int32
     c->launches += 1;
     SGP_CUDA(c, cudaStreamSynchronize(c->stream));               // sc / ctr are locals
   }
-  // ---- direct-distance mode of the int8 Gram: 1..4 non-Eye terms, n_terms * dpad4 <= 72 (smem), any norms ------------
+  // ---- direct-distance mode of the int8 Gram: 1..4 non-Eye terms, n_terms * dpad4 <= 72 (smem) ------------
   {
     const int dpad4 = (d + 3) & ~3;
     c->i8_direct_ok = kf.n_terms >= 1 && kf.n_terms * dpad4 <= 72;

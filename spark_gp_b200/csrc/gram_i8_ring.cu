@@ -270,7 +270,7 @@ struct I8Params {
   // generic sizes of the operand staging (tensor-distance mode: fp16 images; direct mode: fp32 coordinate tiles)
   uint32_t xbytes;      // bytes of one 64-point unit of the point operand
   uint32_t zbytes;      // bytes of one active tile of the active-set operand
-  // direct-distance mode (template DIRECT): exponents from fp32 direct-form distances on the CUDA cores -- any norms, up to 4
+  // direct-distance mode (template DIRECT): exponents from fp32 direct-form distances on the CUDA cores -- no cancellation, up to 4
   // non-Eye terms.  Xt = [n_units][n_terms][64][dpad4] fp32, Zt = [n_tiles_1d][n_terms][128][dpad4 + 4] fp32, coordinates
   // centred and pre-scaled by sqrt(log2 e) * beta_t
   int n_terms, dpad4;
