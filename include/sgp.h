@@ -76,7 +76,7 @@ enum {
                               EXACT int32 accumulation, folded into fp64.  Kernels with one non-Eye term, d <= 32; other
                               qualifying shapes are served by SGP_PREC_I8_DIRECT (sgp_last_path tells which ran).       */
   SGP_PREC_AUTO = 3,       /* default.  An accumulate call of >= 32768 points whose scaled squared norms are small (mean over
-                              points + mean over the active set <= 8: the kernel values are not tiny) runs the int8 Gram --
+                              points + mean over the active set <= 6: the kernel values are not tiny) runs the int8 Gram --
                               SGP_PREC_I8 when the kernel / shape qualifies, else SGP_PREC_I8_DIRECT when THAT qualifies;
                               everything else runs SGP_PREC_F64.  The budget is decided on the first chunk of a call and
                               re-checked over the whole begin..finish window (SGP_E_RANGE at finish -> rerun in F64).

@@ -102,7 +102,8 @@ struct Ctx {
   double* dI8NormSum = nullptr;  // [0]: sum of |x^|^2 over every int8 chunk since begin; [1]: first chunk of this call
   long long i8_points = 0;       // points that went through the int8 kernel since begin
   double i8_z_norm_mean = 0.0;   // mean over the active set of |z^|^2
-  double i8_norm_budget = 8.0;   // AUTO: int8 path only if mean|x^|^2 + mean|z^|^2 <= budget
+  double i8_norm_budget = 6.0;   // AUTO: int8 path only if mean|x^|^2 + mean|z^|^2 <= budget (posterior mean vs the all-fp64
+                                 // mode at 4.3 / 5.8 / 7.2 / 7.9: 1.8e-6 / 2.4e-6 / 5.7e-6 / 1.0e-5, profiles/r02p_i8_budget_edge.txt)
   uint8_t* dI8Zt = nullptr;      // active-set operand images
   uint8_t* dI8Xt = nullptr;  size_t i8_xt_bytes = 0;   // point operand images (scratch)
   float* dI8Ys = nullptr;    size_t i8_ys_bytes = 0;
