@@ -243,35 +243,51 @@ __device__ __forceinline__ __half operand_col(const SplitRow& s, int dp, int L, 
   return zero;
 }
 
-// X (n x d, fp32/fp64) -> images [unit][chunk][64 rows x 128 B] and ys (fp32, zero padded)
+// X (n x d, fp32/fp64) -> images [unit][chunk][64 rows x 128 B] and ys (fp32, zero padded).  DP = d padded to 16 (16 or 32):
+// everything is unrolled and stays in registers (a first version with run-time dp kept the split row in local memory and
+// decoded every operand column with a division: ~170 us per 1M x 16 points, 5 % of the statistics step).
+// B-operand columns (see the table above): [0,DP) 2 xh | [DP,2DP) 2 xh | [2DP,3DP) 2 xl | [3DP,3DP+16) r1 r2 r3 1 1 1 0.. | 0..
+template <int DP>
 __global__ void prep_points_kernel(uint8_t* __restrict__ Xt, float* __restrict__ ys, const void* __restrict__ X,
                                    int x_is_f32, const double* __restrict__ y, long long n, long long n_units,
-                                   int d, int dp, int nchunks, const double* __restrict__ scale /*[dp]*/,
-                                   const double* __restrict__ centre /*[dp]*/, int* __restrict__ flags,
+                                   int d, const double* __restrict__ scale /*[DP]*/,
+                                   const double* __restrict__ centre /*[DP]*/, int* __restrict__ flags,
                                    double* __restrict__ norm_sum, double* __restrict__ norm_sum_call) {
   // 128 threads = two 64-point units.  A thread builds the operand row of its point into shared memory; the block then
-  // copies the rows out with 16-byte chunks of one 128-byte image row on consecutive threads (full-line stores).  Writing
-  // the rows straight from the owning thread put the 32 stores of a warp instruction into 32 different lines: 167 us per
-  // 1M x 16 points, 5 % of the statistics step.
+  // copies the rows out with 16-byte chunks of one 128-byte image row on consecutive threads (full-line stores).
+  constexpr int NCH = (3 * DP + 16 + 63) / 64;                      // 64-column K chunks: 1 (DP = 16) or 2 (DP = 32)
+  constexpr int ROW_BYTES = NCH * 128 + 16;                         // +16: the row-owner stores spread over the banks
   extern __shared__ __align__(16) uint8_t prep_smem[];
   __shared__ double warp_norm[4];
-  const int row_bytes = nchunks * 128 + 16;                        // +16: the row-owner stores spread over the banks
   const long long pt = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   const bool in_grid = pt < n_units * UP;
   const bool valid = pt < n;
-  double v[32];
-  for (int k = 0; k < dp; ++k) {
-    double x = 0.0;
+  __half2 hh[DP / 2], ll[DP / 2];                                   // 2 xh, 2 xl, two columns per register
+  double acc = 0.0;
+#pragma unroll
+  for (int k = 0; k < DP; k += 2) {
+    double v0 = 0.0, v1 = 0.0;
     if (valid && k < d) {
       const size_t off = static_cast<size_t>(pt) * d + k;
-      x = x_is_f32 ? static_cast<double>(reinterpret_cast<const float*>(X)[off]) : reinterpret_cast<const double*>(X)[off];
-      x = (x - centre[k]) * scale[k];
+      v0 = x_is_f32 ? static_cast<double>(reinterpret_cast<const float*>(X)[off]) : reinterpret_cast<const double*>(X)[off];
+      v0 = (v0 - centre[k]) * scale[k];
     }
-    v[k] = x;
+    if (valid && k + 1 < d) {
+      const size_t off = static_cast<size_t>(pt) * d + k + 1;
+      v1 = x_is_f32 ? static_cast<double>(reinterpret_cast<const float*>(X)[off]) : reinterpret_cast<const double*>(X)[off];
+      v1 = (v1 - centre[k + 1]) * scale[k + 1];
+    }
+    const __half h0 = __double2half(v0), h1 = __double2half(v1);
+    const __half l0 = __double2half(v0 - static_cast<double>(__half2float(h0)));
+    const __half l1 = __double2half(v1 - static_cast<double>(__half2float(h1)));
+    const double r0 = static_cast<double>(__half2float(h0)) + static_cast<double>(__half2float(l0));
+    const double r1 = static_cast<double>(__half2float(h1)) + static_cast<double>(__half2float(l1));
+    acc = fma(r0, r0, acc);
+    acc = fma(r1, r1, acc);
+    hh[k / 2] = __halves2half2(__hadd(h0, h0), __hadd(h1, h1));     // 2 x (exact)
+    ll[k / 2] = __halves2half2(__hadd(l0, l0), __hadd(l1, l1));
   }
-  SplitRow s;
-  double norm2;
-  split_row(v, dp, s, norm2);
+  const double norm2 = acc;
   if (valid && !(norm2 <= 16384.0)) atomicOr(flags, 1);          // out of the fp16 operand range -> caller falls back
   if (norm_sum) {                                                // sum of scaled squared norms (AUTO's magnitude gate)
     double v2 = valid ? norm2 : 0.0;
@@ -279,14 +295,37 @@ __global__ void prep_points_kernel(uint8_t* __restrict__ Xt, float* __restrict__
     if ((threadIdx.x & 31) == 0) warp_norm[threadIdx.x >> 5] = v2;     // one atomic per block (same-address atomics serialise)
   }
   if (in_grid) ys[pt] = (valid && y) ? static_cast<float>(y[pt]) : 0.f;
-  uint8_t* myrow = prep_smem + threadIdx.x * row_bytes;
-  for (int c = 0; c < nchunks; ++c) {
-    for (int c16 = 0; c16 < 8; ++c16) {
-      __align__(16) __half h[8];
+  // three-piece fp16 expansion of -|x^|^2; a padded point gets T = -60000 -> kappa = 0
+  const double nn = -norm2;
+  __half n1 = __double2half(nn);
+  const double e1 = nn - static_cast<double>(__half2float(n1));
+  __half n2 = __double2half(e1);
+  __half n3 = __double2half(e1 - static_cast<double>(__half2float(n2)));
+  const __half zero = __float2half(0.f), one = __float2half(1.f);
+  if (!valid) { n1 = __float2half(-60000.f); n2 = zero; n3 = zero; }
+  uint4* myrow = reinterpret_cast<uint4*>(prep_smem + threadIdx.x * ROW_BYTES);
+  auto pack4 = [](const __half2* p) {
+    uint4 u;
+    u.x = *reinterpret_cast<const uint32_t*>(p + 0); u.y = *reinterpret_cast<const uint32_t*>(p + 1);
+    u.z = *reinterpret_cast<const uint32_t*>(p + 2); u.w = *reinterpret_cast<const uint32_t*>(p + 3);
+    return u;
+  };
+  constexpr int C = DP / 8;                                        // 16-byte chunks per DP columns
 #pragma unroll
-      for (int e = 0; e < 8; ++e) h[e] = operand_col<true>(s, dp, c * 64 + c16 * 8 + e, valid);
-      *reinterpret_cast<uint4*>(myrow + c * 128 + c16 * 16) = *reinterpret_cast<const uint4*>(h);
-    }
+  for (int j = 0; j < C; ++j) {
+    const uint4 h4 = pack4(hh + 4 * j), l4 = pack4(ll + 4 * j);
+    myrow[j] = h4; myrow[C + j] = h4; myrow[2 * C + j] = l4;
+  }
+  {
+    const __half2 a0 = __halves2half2(n1, n2), a1 = __halves2half2(n3, one), a2 = __halves2half2(one, one),
+                  a3 = __halves2half2(zero, zero);
+    uint4 u;
+    u.x = *reinterpret_cast<const uint32_t*>(&a0); u.y = *reinterpret_cast<const uint32_t*>(&a1);
+    u.z = *reinterpret_cast<const uint32_t*>(&a2); u.w = *reinterpret_cast<const uint32_t*>(&a3);
+    myrow[3 * C] = u;
+    myrow[3 * C + 1] = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+    for (int j = 3 * C + 2; j < NCH * 8; ++j) myrow[j] = make_uint4(0u, 0u, 0u, 0u);
   }
   __syncthreads();
   if (norm_sum && threadIdx.x == 0) {
@@ -297,13 +336,13 @@ __global__ void prep_points_kernel(uint8_t* __restrict__ Xt, float* __restrict__
     }
   }
   const long long unit0 = static_cast<long long>(blockIdx.x) * 2;
-  const int per_unit = nchunks * 512;                              // 16-byte chunks per unit: [chunk][64 rows][8]
-  for (int q = threadIdx.x; q < 2 * per_unit; q += blockDim.x) {
-    const int u = q / per_unit, rem = q % per_unit;
+  constexpr int PER_UNIT = NCH * 512;                              // 16-byte chunks per unit: [chunk][64 rows][8]
+  for (int q = threadIdx.x; q < 2 * PER_UNIT; q += blockDim.x) {
+    const int u = q / PER_UNIT, rem = q % PER_UNIT;
     const int c = rem >> 9, r = (rem >> 3) & 63, c16 = rem & 7;
     if (unit0 + u >= n_units) break;
-    const uint4 val = *reinterpret_cast<const uint4*>(prep_smem + (u * 64 + r) * row_bytes + c * 128 + c16 * 16);
-    uint8_t* img = Xt + (static_cast<size_t>(unit0 + u) * nchunks + c) * XIMG_BYTES;
+    const uint4 val = *reinterpret_cast<const uint4*>(prep_smem + (u * 64 + r) * ROW_BYTES + c * 128 + c16 * 16);
+    uint8_t* img = Xt + (static_cast<size_t>(unit0 + u) * NCH + c) * XIMG_BYTES;
     *reinterpret_cast<uint4*>(img + sw128_off(r, c16)) = val;
   }
 }
@@ -813,9 +852,14 @@ cudaError_t launch_i8_prep_points(uint8_t* Xt, float* ys, const void* dX, int x_
   const int dp = (d + 15) / 16 * 16;
   const long long units = (n + UP - 1) / UP;
   const long long threads = units * UP;
-  const int nch = i8_nchunks(d);
-  prep_points_kernel<<<static_cast<unsigned>((threads + 127) / 128), 128, 128 * (nch * 128 + 16), s>>>(
-      Xt, ys, dX, x_is_f32, dy, n, units, d, dp, nch, dScale, dCentre, dFlags, dNormSum, dNormSumCall);
+  const unsigned grid = static_cast<unsigned>((threads + 127) / 128);
+  (void)dp;
+  if (d <= 16)
+    prep_points_kernel<16><<<grid, 128, 128 * (1 * 128 + 16), s>>>(Xt, ys, dX, x_is_f32, dy, n, units, d, dScale, dCentre, dFlags,
+                                                                  dNormSum, dNormSumCall);
+  else
+    prep_points_kernel<32><<<grid, 128, 128 * (2 * 128 + 16), s>>>(Xt, ys, dX, x_is_f32, dy, n, units, d, dScale, dCentre, dFlags,
+                                                                  dNormSum, dNormSumCall);
   return cudaGetLastError();
 }
 
