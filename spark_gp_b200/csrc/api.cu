@@ -62,6 +62,7 @@ static void free_active_set(Ctx* c) {
   cudaFree(c->dMagicVec); cudaFree(c->dMagicMat);
   cudaFree(c->dI8Scale); cudaFree(c->dI8Centre); cudaFree(c->dI8Flags); cudaFree(c->dI8Zt); cudaFree(c->dI8NormSum);
   cudaFree(c->dI8Zd); cudaFree(c->dI8DScale); c->dI8Zd = nullptr; c->dI8DScale = nullptr; c->i8_direct_ok = false;
+  c->i8d_zd_bytes = c->i8d_sc_bytes = 0; c->i8d_prepared = false;
   c->dI8NormSum = nullptr;
   c->dZ = c->dZs = c->dBeta = c->dGb = c->dMagicVec = c->dMagicMat = nullptr;
   c->dI8Scale = c->dI8Centre = nullptr; c->dI8Flags = nullptr; c->dI8Zt = nullptr; c->i8_ok = false;
@@ -80,6 +81,28 @@ static int ensure_partials(Ctx* c, int n_slices) {
     SGP_CUDA(c, cudaMalloc(&c->dBpart, bb));
     c->bpart_bytes = bb;
   }
+  return SGP_OK;
+}
+
+// Device side of the direct-distance mode for the current begin() window: per-term scales + centre, active-set tiles
+int direct_prepare(Ctx* c) {
+  if (c->i8d_prepared) return SGP_OK;
+  const int dpad4 = c->i8_dpad4;
+  const size_t zd_bytes = static_cast<size_t>(c->m_pad / kTile) * c->kf.n_terms * kTile * dpad4 * sizeof(float);
+  const size_t sc_bytes = c->i8d_sc.size() * 8;
+  if (zd_bytes > c->i8d_zd_bytes || sc_bytes > c->i8d_sc_bytes || !c->dI8Zd) {
+    cudaFree(c->dI8Zd); cudaFree(c->dI8DScale); c->dI8Zd = nullptr; c->dI8DScale = nullptr;
+    c->i8d_zd_bytes = c->i8d_sc_bytes = 0;
+    SGP_CUDA(c, cudaMalloc(&c->dI8Zd, zd_bytes));
+    SGP_CUDA(c, cudaMalloc(&c->dI8DScale, sc_bytes));
+    c->i8d_zd_bytes = zd_bytes; c->i8d_sc_bytes = sc_bytes;
+  }
+  SGP_CUDA(c, cudaMemcpyAsync(c->dI8DScale, c->i8d_sc.data(), sc_bytes, cudaMemcpyHostToDevice, c->stream));
+  SGP_CUDA(c, launch_i8_prep_active_direct(c->dI8Zd, c->dZ, c->m, c->m_pad, c->d, dpad4, c->kf.n_terms, c->dI8DScale,
+                                           c->dI8DScale + static_cast<size_t>(kMaxTerms) * dpad4, c->dI8Flags,
+                                           c->i8_direct_r2max, c->stream));
+  c->launches += 1;
+  c->i8d_prepared = true;
   return SGP_OK;
 }
 
@@ -196,6 +219,8 @@ static int launch_stats(Ctx* c, const void* dX, int x_is_f32, const double* dy, 
     }
     // AUTO applies the same magnitude budget as with tensor-core distances (on the WIDEST term's scaled squared norms: it
     // sets the size of the kernel values): first chunk here, whole window at finish
+    rc = direct_prepare(c);
+    if (rc != SGP_OK) return rc;
     const bool dgate = (c->precision == SGP_PREC_AUTO) && first_of_call;
     const bool dbudget = (c->precision == SGP_PREC_AUTO);
     if (dgate) SGP_CUDA(c, cudaMemsetAsync(c->dI8NormSum + 1, 0, sizeof(double), c->stream));
@@ -450,6 +475,7 @@ int sgp_stats_begin(sgp_ctx* h, const sgp_kernel_desc* k, const double* Z, int32
   }
   // ---- tcgen05 int8 path: qualifies for one non-Eye term and d <= 32 (two 64-column K chunks) -------------
   c->i8_ok = (kf.n_terms == 1 && d <= 32);
+  std::vector<double> sc16, ctr16;               // live until the synchronisation at the end of this function
   if (!c->dI8Flags) {
     SGP_CUDA(c, cudaMalloc(&c->dI8Flags, sizeof(int)));
     SGP_CUDA(c, cudaMalloc(&c->dI8NormSum, 2 * sizeof(double)));
@@ -458,7 +484,8 @@ int sgp_stats_begin(sgp_ctx* h, const sgp_kernel_desc* k, const double* Z, int32
   SGP_CUDA(c, cudaMemsetAsync(c->dI8NormSum, 0, 2 * sizeof(double), c->stream));
   if (c->i8_ok) {
     const int dp16 = (d + 15) / 16 * 16;
-    std::vector<double> sc(dp16, 0.0), ctr(dp16, 0.0);
+    std::vector<double>& sc = sc16; std::vector<double>& ctr = ctr16;
+    sc.assign(dp16, 0.0); ctr.assign(dp16, 0.0);
     const double s2 = std::sqrt(1.4426950408889634074);          // sqrt(log2 e): exponent in base 2
     for (int j = 0; j < d; ++j) {
       sc[j] = s2 * beta[j];
@@ -486,7 +513,6 @@ int sgp_stats_begin(sgp_ctx* h, const sgp_kernel_desc* k, const double* Z, int32
     SGP_CUDA(c, launch_i8_prep_active(c->dI8Zt, c->dZ, m, c->m_pad, d, c->dI8Scale, c->dI8Centre, c->dI8Flags,
                                       c->stream));
     c->launches += 1;
-    SGP_CUDA(c, cudaStreamSynchronize(c->stream));               // sc / ctr are locals
   }
   // ---- direct-distance mode of the int8 Gram: 1..4 non-Eye terms, n_terms * dpad4 <= 72 (smem) ------------
   {
@@ -495,7 +521,8 @@ int sgp_stats_begin(sgp_ctx* h, const sgp_kernel_desc* k, const double* Z, int32
     if (c->i8_direct_ok) {
       c->i8_dpad4 = dpad4;
       if (const char* e = getenv("SGP_I8_DIRECT_R2MAX")) c->i8_direct_r2max = static_cast<float>(atof(e));
-      std::vector<double> sc(static_cast<size_t>(kMaxTerms + 1) * dpad4, 0.0);      // [term][k] scales, then the centre
+      std::vector<double>& sc = c->i8d_sc;                                           // [term][k] scales, then the centre
+      sc.assign(static_cast<size_t>(kMaxTerms + 1) * dpad4, 0.0);
       const double s2 = std::sqrt(1.4426950408889634074);
       for (int t = 0; t < kf.n_terms; ++t)
         for (int j = 0; j < d; ++j) sc[static_cast<size_t>(t) * dpad4 + j] = s2 * beta[static_cast<size_t>(t) * dpad + j];
@@ -519,20 +546,10 @@ int sgp_stats_begin(sgp_ctx* h, const sgp_kernel_desc* k, const double* Z, int32
         c->i8d_z_norm_mean = best;
         if (const char* e = getenv("SGP_I8_NORM_BUDGET")) c->i8_norm_budget = atof(e);
       }
-      const size_t zd_bytes = static_cast<size_t>(c->m_pad / kTile) * kf.n_terms * kTile * dpad4 * sizeof(float);
-      if (!same_shape || !c->dI8Zd) {
-        cudaFree(c->dI8Zd); cudaFree(c->dI8DScale); c->dI8Zd = nullptr; c->dI8DScale = nullptr;
-        SGP_CUDA(c, cudaMalloc(&c->dI8Zd, zd_bytes));
-        SGP_CUDA(c, cudaMalloc(&c->dI8DScale, sc.size() * 8));
-      }
-      SGP_CUDA(c, cudaMemcpyAsync(c->dI8DScale, sc.data(), sc.size() * 8, cudaMemcpyHostToDevice, c->stream));
-      SGP_CUDA(c, launch_i8_prep_active_direct(c->dI8Zd, c->dZ, m, c->m_pad, d, dpad4, kf.n_terms, c->dI8DScale,
-                                               c->dI8DScale + static_cast<size_t>(kMaxTerms) * dpad4, c->dI8Flags,
-                                               c->i8_direct_r2max, c->stream));
-      c->launches += 1;
-      SGP_CUDA(c, cudaStreamSynchronize(c->stream));             // sc is a local
+      // the device side (scales upload, active-set tiles) is prepared on first use of the mode: direct_prepare()
     }
   }
+  c->i8d_prepared = false;
   c->i8_direct_used = false;
   SGP_CUDA(c, cudaStreamSynchronize(c->stream));   // Z / beta are host temporaries of the caller
   c->gram_events_used = 0;

@@ -91,6 +91,9 @@ struct Ctx {
   double* dI8DScale = nullptr;   // [n_terms][dpad4] sqrt(log2 e) * beta_tk ; then [dpad4] centre
   bool i8_direct_used = false;
   bool i8_used = false;          // an int8 launch contributed to the current statistics
+  std::vector<double> i8d_sc;      // direct mode: host copy of [term][k] scales + centre of the current begin() window
+  bool i8d_prepared = false;       // ... uploaded and the active-set tiles built (on first use of the mode in the window)
+  size_t i8d_zd_bytes = 0, i8d_sc_bytes = 0;
   double i8d_z_norm_mean = 0.0;    // direct mode: mean scaled squared norm of the active set (widest term) for AUTO's budget
   float i8_direct_r2max = 2048.f;  // direct mode: largest scaled squared norm accepted (env SGP_I8_DIRECT_R2MAX); measured
                                    // dG 6.6e-7 at ~1300 and 2.7e-6 at ~7700 on clustered data (tests: error_growth)
