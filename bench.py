@@ -476,15 +476,22 @@ def fit_number(sg, args):
     gp = (sg.GaussianProcessRegression().setKernel(lambda: 1 * sg.ARDRBFKernel(np.full(d, np.sqrt(18.0 / d)))
                                                    + sg.const(1) * sg.EyeKernel())
           .setDatasetSizeForExpert(N_E).setActiveSetSize(m).setSigma2(SIGMA2).setMaxIter(max_iter).setTol(1e-6).setSeed(13))
-    gp.fit(X[:50_000], y[:50_000])                                      # warm-up (contexts, workspaces)
+    gp.fit(X[:50_000], y[:50_000])                                      # warm-up: contexts, lazy library initialisation
     t0 = time.perf_counter()
-    gp.fit(X, y)
-    dt = time.perf_counter() - t0
+    gp.fit(X, y)                                                        # first full-size fit: allocates every workspace
+    dt_first = time.perf_counter() - t0
+    dts = []
+    for _ in range(3):                                                  # steady state (contexts and workspaces pooled)
+        t0 = time.perf_counter()
+        gp.fit(X, y)
+        dts.append(time.perf_counter() - t0)
+    dt = float(np.median(dts))
     info = gp.last_objective or {}
-    return {"value": len(X) / dt, "unit": UNIT, "seconds": dt, "maxIter": max_iter,
+    return {"value": len(X) / dt, "unit": UNIT, "seconds": dt, "seconds_first_call": dt_first, "maxIter": max_iter,
             "objective_evaluations": info.get("evaluations"), "lbfgsb_iterations": info.get("iterations"),
             "what": "GaussianProcessRegression.fit(1M x 16, expert=100, active=1000): L-BFGS-B on the GPU BCM objective "
-                    "(fixed maxIter) + projected-process statistics + tail, host wall clock"}
+                    "(fixed maxIter) + projected-process statistics + tail, host wall clock; median of 3 after one full-size fit "
+                    "(seconds_first_call = that first fit, which allocates the workspaces)"}
 
 
 def main():
