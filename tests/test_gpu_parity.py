@@ -1,8 +1,10 @@
 """GPU parity tests (run on a B200: `pytest -m gpu`).  Everything goes through the C-ABI (ctypes) and is
 compared with the fp64 oracle on identical seeded inputs, or with the committed golden fixtures.
 
-Arithmetic modes (include/sgp.h): AUTO (default) = the tcgen05 int8 exact-accumulation kernel when the kernel has
-one non-Eye term and d <= 32, else the fp64 DMMA kernel (F64); F64_STRICT = all-fp64 verification mode.
+Arithmetic modes (include/sgp.h): AUTO (default) = the tcgen05 int8 exact-accumulation Gram on accumulate calls of
+>= 32768 points whose scaled squared norms are inside the magnitude budget (tensor-core distances for one non-Eye term and
+d <= 32, direct fp32 distances for sums of up to 4 terms / d <= 72), else the fp64 DMMA kernel (F64); I8 / I8_DIRECT force
+the two int8 modes; F64_STRICT = all-fp64 verification mode.
 
 Tolerances (written here once):
   TOL_STRICT = 1e-11  G, b in SGP_PREC_F64_STRICT (all-fp64) mode, relative to max|G| / max|b|
@@ -127,7 +129,7 @@ def test_small_golden_cases(eng, name, mode):
     strict = mode == "strict"
     prec = {"strict": N.SGP_PREC_F64_STRICT, "f64": N.SGP_PREC_F64, "auto": N.SGP_PREC_AUTO}[mode]
     G, b = run_stats(eng, kernel, c["X"], c["y"], c["Z"], prec)
-    tol = TOL_STRICT if strict else TOL_STATS          # AUTO keeps shards < 65536 points on the fp64 kernel
+    tol = TOL_STRICT if strict else TOL_STATS          # AUTO keeps calls of < 32768 points on the fp64 kernel
     assert rel(G, c["G"]) < tol and rel(b, c["b"]) < tol
     assert np.array_equal(G, G.T)
     mv, mm = eng.magic()
