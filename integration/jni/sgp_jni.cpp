@@ -195,5 +195,40 @@ JNIEXPORT void JNICALL Java_org_apache_spark_ml_commons_NativeProjectedProcess_e
   if (rc != SGP_OK) throw_for(env, ctx, rc);
 }
 
+// GreedilyOptimizingActiveSetProvider (ActiveSetProvider.scala:58-139) on one executor's points: row indices of the selected
+// points (rank-1 updates on the device, sgp_greedy_active_set); firstIndex replaces takeSample(1, seed), ASP:70
+JNIEXPORT jlongArray JNICALL Java_org_apache_spark_ml_commons_NativeProjectedProcess_greedyActiveSet(
+    JNIEnv* env, jclass, jlong h, jintArray types, jdoubleArray scales, jdoubleArray sigmas, jdoubleArray betas,
+    jdoubleArray X, jdoubleArray y, jlong n, jint d, jlong nExperts, jlong firstIndex, jint activeSetSize) {
+  sgp_ctx* ctx = reinterpret_cast<sgp_ctx*>(h);
+  const jsize nt = env->GetArrayLength(types);
+  jint* ty = env->GetIntArrayElements(types, nullptr);
+  jdouble* sc = env->GetDoubleArrayElements(scales, nullptr);
+  jdouble* sg = env->GetDoubleArrayElements(sigmas, nullptr);
+  jdouble* be = env->GetDoubleArrayElements(betas, nullptr);
+  jdouble* xx = env->GetDoubleArrayElements(X, nullptr);
+  jdouble* yy = env->GetDoubleArrayElements(y, nullptr);
+  std::vector<sgp_kernel_term> terms(nt);
+  int ard = 0;
+  for (jsize t = 0; t < nt; ++t) {
+    terms[t].type = ty[t]; terms[t].reserved = 0; terms[t].scale = sc[t]; terms[t].sigma = sg[t];
+    terms[t].beta = (ty[t] == SGP_TERM_ARD) ? be + (ard++) * d : nullptr;
+  }
+  sgp_kernel_desc desc{static_cast<int32_t>(nt), 0, terms.data()};
+  std::vector<int64_t> idx(activeSetSize);
+  const int rc = sgp_greedy_active_set(ctx, &desc, xx, yy, n, d, nExperts, firstIndex, activeSetSize, idx.data());
+  env->ReleaseIntArrayElements(types, ty, JNI_ABORT);
+  env->ReleaseDoubleArrayElements(scales, sc, JNI_ABORT);
+  env->ReleaseDoubleArrayElements(sigmas, sg, JNI_ABORT);
+  env->ReleaseDoubleArrayElements(betas, be, JNI_ABORT);
+  env->ReleaseDoubleArrayElements(X, xx, JNI_ABORT);
+  env->ReleaseDoubleArrayElements(y, yy, JNI_ABORT);
+  if (rc != SGP_OK) { throw_for(env, ctx, rc); return nullptr; }
+  jlongArray res = env->NewLongArray(activeSetSize);
+  static_assert(sizeof(jlong) == sizeof(int64_t), "jlong is 64 bits");
+  env->SetLongArrayRegion(res, 0, activeSetSize, reinterpret_cast<const jlong*>(idx.data()));
+  return res;
+}
+
 }  // extern "C"
 #endif  // __has_include(<jni.h>)

@@ -28,6 +28,12 @@ private[ml] object NativeProjectedProcess {
                         d: Int, hKind: Array[Int], hTerm: Array[Int], hDim: Array[Int], hValue: Array[Double],
                         hCoef: Array[Double], tol: Double): Array[Double]
   @native def expertsGetF(ctx: Long, f: Array[Double]): Unit
+  /** Row indices of the points GreedilyOptimizingActiveSetProvider selects (ActiveSetProvider.scala:58-139) among the n
+    * points of x (row-major, d columns); rank-1 updates on the device.  firstIndex replaces takeSample(1, seed), ASP:70;
+    * nExperts = Math.round(n / datasetSizeForExpert), GPC:27. */
+  @native def greedyActiveSet(ctx: Long, types: Array[Int], scales: Array[Double], sigmas: Array[Double],
+                              betas: Array[Double], x: Array[Double], y: Array[Double], n: Long, d: Int, nExperts: Long,
+                              firstIndex: Long, activeSetSize: Int): Array[Long]
 
   /** Flattens the kernel DSL tree into (type, scale, sigma, beta) terms; `scale` multiplies down the tree
     * (ScalarTimesKernel.scala:20-28), Eye terms are kept (they carry whiteNoiseVar / the K_mm diagonal). */
