@@ -64,3 +64,18 @@ def test_product_never_imports_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
                 assert "oracle/" not in text or f == "__init__.py", f
+
+
+def test_jni_glue_syntax_checks_against_stub_header():
+    """integration/jni/sgp_jni.cpp is guarded by __has_include(<jni.h>) (no JDK in this image); with the stand-in header of
+    tests/support/jni_stub it must at least parse and type-check against include/sgp.h."""
+    import shutil, subprocess
+    gxx = shutil.which("g++")
+    if gxx is None:
+        import pytest
+        pytest.skip("no g++")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([gxx, "-std=c++17", "-fsyntax-only", "-Wall", "-I" + os.path.join(root, "tests", "support", "jni_stub"),
+                        "-I" + os.path.join(root, "include"), os.path.join(root, "integration", "jni", "sgp_jni.cpp")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
