@@ -224,3 +224,60 @@ def test_scale_matches_oracle():
     got, want = sg.scale(X), oracle.scale(X)
     assert np.array_equal(got, want)
     assert np.allclose(got.mean(0), 0.0, atol=1e-14) and np.allclose(got[:, [0, 1, 3]].std(0), 1.0) and np.all(got[:, 2] == 0.0)
+
+
+def test_greedy_rank1_update_identities():
+    """The algebra of csrc/greedy.cu restated in NumPy and checked against the reference's per-round quantities
+    (oracle.active_set: inv(K_mm), inv(s2 K_mm + G), magic vector; p_i, q_i, mu_i of ASP:109-113): adding one active point
+    borders K_mm and A = s2 K_mm + G, so
+        p_i' = p_i + (u~.k_i - k*_i)^2 / s~,   q_i' = q_i + (u.k_i - k*_i)^2 / s,   mu_i' = mu_i + a (u.k_i - k*_i)
+    with u~ = inv(K_mm) c, s~ = kii - c.u~, u = inv(A) w, w = s2 c + K_mn k*, s = s2 kii + k*.k* - w.u, a = (u.b - k*.y) / s."""
+    rng = np.random.default_rng(9)
+    n, d, rounds = 400, 3, 12
+    X = rng.random((n, d)); y = np.sin(3 * X.sum(1)) + 0.1 * rng.standard_normal(n)
+    beta = np.full(d, 2.5)
+    kern = lambda: 1.2 * oracle.ARDRBFKernel(beta) + oracle.const(0.3) * oracle.EyeKernel()
+    k0 = kern()
+    s2 = k0.white_noise_var
+    kii = 1.2 + 0.3                                               # trainingKernelDiag: every leaf has k(x, x) = 1
+    picks = rng.permutation(n)[:rounds]
+    Kt = np.zeros((0, n)); Kinv = np.zeros((0, 0)); Ainv = np.zeros((0, 0)); b = np.zeros(0); mv = np.zeros(0)
+    p = np.zeros(n); q = np.zeros(n); mu = np.zeros(n)
+    for r, idx in enumerate(picks):
+        kstar = kern().set_training_vectors(X[[idx]]).cross_kernel(X)[:, 0]      # k(x_i, x_idx) for every point i
+        m = len(Kt)
+        c = Kt[:, idx] if m else np.zeros(0)
+        g = Kt @ kstar if m else np.zeros(0)
+        gamma, bnew = kstar @ kstar, kstar @ y
+        ut = Kinv @ c if m else np.zeros(0)
+        w = s2 * c + g
+        u = Ainv @ w if m else np.zeros(0)
+        s1 = kii - c @ ut
+        s = s2 * kii + gamma - w @ u
+        a = ((u @ b) - bnew) / s
+        t1 = Kt.T @ ut if m else np.zeros(n)
+        t2 = Kt.T @ u if m else np.zeros(n)
+        p += (t1 - kstar) ** 2 / s1; q += (t2 - kstar) ** 2 / s; mu += a * (t2 - kstar)
+        # bordered inverses
+        def border(inv, v, sc):
+            out = np.zeros((m + 1, m + 1))
+            out[:m, :m] = inv + np.outer(v, v) / sc
+            out[:m, m] = out[m, :m] = -v / sc
+            out[m, m] = 1.0 / sc
+            return out
+        Kinv, Ainv = border(Kinv, ut, s1), border(Ainv, u, s)
+        mv = np.concatenate([mv + u * a, [-a]]); b = np.concatenate([b, [bnew]])
+        Kt = np.vstack([Kt, kstar])
+        # the reference's quantities for this active set, from scratch
+        active = X[picks[:r + 1]]
+        inst = kern().set_training_vectors(active)
+        kmm = inst.training_kernel()
+        cross = inst.cross_kernel(X).T                            # m x n (crossKernel: rows = test vectors, Kernel.scala:69-74)
+        G = cross @ cross.T
+        A = s2 * kmm + G
+        assert np.allclose(Kinv, np.linalg.inv(kmm), rtol=1e-8, atol=1e-10)
+        assert np.allclose(Ainv, np.linalg.inv(A), rtol=1e-7, atol=1e-12)
+        assert np.allclose(mv, np.linalg.solve(A, cross @ y), rtol=1e-7, atol=1e-12)
+        assert np.allclose(p, np.einsum("ji,jk,ki->i", cross, np.linalg.inv(kmm), cross), rtol=1e-8, atol=1e-12)
+        assert np.allclose(q, np.einsum("ji,jk,ki->i", cross, np.linalg.inv(A), cross), rtol=1e-7, atol=1e-12)
+        assert np.allclose(mu, cross.T @ np.linalg.solve(A, cross @ y), rtol=1e-7, atol=1e-12)
