@@ -281,3 +281,31 @@ def test_greedy_rank1_update_identities():
         assert np.allclose(p, np.einsum("ji,jk,ki->i", cross, np.linalg.inv(kmm), cross), rtol=1e-8, atol=1e-12)
         assert np.allclose(q, np.einsum("ji,jk,ki->i", cross, np.linalg.inv(A), cross), rtol=1e-7, atol=1e-12)
         assert np.allclose(mu, cross.T @ np.linalg.solve(A, cross @ y), rtol=1e-7, atol=1e-12)
+
+
+def test_bcm_register_kernel_identities():
+    """The two identities `bcm_nll_reg_kernel` (csrc/bcm_nll.cu) rests on, in NumPy: (1) n sweeps of Goodnight's sweep
+    operator turn an SPD matrix into minus its inverse, the pivots are the Schur complements (all positive) and their logs
+    sum to log|det|; (2) the per-dimension gradient sums are quadratic forms,
+    sum_ab (x_ak - x_bk)^2 M_ab = 2 (sum_a x_ak^2 m_a - x_k' M x_k) with m = M 1, for any symmetric M."""
+    rng = np.random.default_rng(4)
+    n, d = 37, 5
+    X = rng.standard_normal((n, d))
+    K = np.exp(-0.5 * ((X[:, None, :] - X[None, :, :]) ** 2).sum(-1)) + 0.1 * np.eye(n)
+    A = K.copy()
+    logdet = 0.0
+    for k in range(n):
+        piv = A[k, k]
+        assert piv > 0
+        logdet += np.log(piv)
+        col = A[:, k].copy()
+        A -= np.outer(col, col) / piv                      # rank-1 update everywhere ...
+        A[:, k] = col / piv; A[k, :] = col / piv            # ... then the pivot column / row
+        A[k, k] = -1.0 / piv
+    assert np.allclose(-A, np.linalg.inv(K), rtol=1e-9, atol=1e-10)
+    assert abs(logdet - np.linalg.slogdet(K)[1]) < 1e-9
+    W = rng.standard_normal((n, n)); M = K * (W + W.T)      # any symmetric pair weight
+    m1 = M.sum(1)
+    for k in range(d):
+        direct = (((X[:, None, k] - X[None, :, k]) ** 2) * M).sum()
+        assert abs(direct - 2.0 * ((X[:, k] ** 2) @ m1 - X[:, k] @ M @ X[:, k])) < 1e-9 * max(1.0, abs(direct))
