@@ -76,7 +76,6 @@ constexpr uint32_t A_KS_COLS = 24;      // TMEM columns of one k-step of the A o
 constexpr float C0 = 8355000.0f;        // fixed-point scale: u <= C0*(1+2e-3) keeps u + 0x4040 < 2^23
 constexpr float MAGIC = 8388608.0f + 16448.0f;   // 2^23 + 0x4040
 constexpr int ZPANEL_BYTES = 16384;     // fp16 active-set operand image: 128 rows x 128 bytes, SWIZZLE_128B K-major
-constexpr int PANEL_BYTES = ZPANEL_BYTES;
 constexpr int XIMG_BYTES = 8192;        // fp16 point operand image: 64 rows x 128 bytes
 // int8 digit planes of one panel unit: 128 active rows x 64 points = 128 rows x 64 BYTES, K-major SWIZZLE_64B, so that a
 // unit's plane is one contiguous 8 KB image (the unit is the granule that travels through the L2 ring)
@@ -84,7 +83,6 @@ constexpr int PLANE_BYTES = 8192;
 constexpr int SLOT_BYTES = 3 * PLANE_BYTES;   // P0 | P1 | P2 of one unit
 constexpr int NPI_PUB = 4;              // panel-I ring depth of a publishing (diagonal) CTA: a slot is held until the bulk
                                         // store that ships it has completed
-constexpr int NPI = 2;                  // ... of every other CTA
 constexpr int NPJ_MAX = 5;              // panel-J ring depth (off-diagonal CTAs) = L2 -> smem prefetch distance: 5 slots with
                                         // one K chunk, 3 with two (227 KB limit); smem slots = 2 x I + npj x J (publisher: 4 x I)
 // Depth (units) of the global ring between a publisher and its consumers.  It must comfortably exceed the loop lag
@@ -176,12 +174,6 @@ __device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
 }
-__device__ __forceinline__ void mma_i8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
-}
 // A operand from tensor memory (rows = lanes, K bytes packed along 32-bit columns), B from shared memory
 __device__ __forceinline__ void mma_i8_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
   asm volatile(
@@ -253,10 +245,6 @@ __host__ __device__ constexpr uint32_t idesc_i8_s32(int M, int N, bool a_signed,
          (static_cast<uint32_t>(M >> 4) << 24);
 }
 
-// byte offset of (row r, 16-byte chunk c16 in [0,8)) inside a K-major SWIZZLE_128B tile with 128-byte rows
-__host__ __device__ __forceinline__ uint32_t sw128_off(int r, int c16) {
-  return static_cast<uint32_t>((r >> 3) * 1024 + (r & 7) * 128 + ((c16 ^ (r & 7)) << 4));
-}
 
 // ---------------------------------------------------------------------------------------------------
 // The fused kernel
@@ -312,14 +300,6 @@ __device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
   unsigned v;
   asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
-}
-__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
-  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ void st_relaxed_u32(unsigned* p, unsigned v) {
   asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
